@@ -1,0 +1,35 @@
+# Builds the B200 (sm_100a) k-mer counting library, its C++ host CLI and the test oracle.
+#   make            -> tsxcount_b200/lib/libtsxcuda.so + tsxcount_b200/bin/tsxcount + oracle
+#   make lib | cli | oracle
+NVCC     ?= /usr/local/cuda/bin/nvcc
+HOSTCXX  := $(shell [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo g++)
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas -ccbin $(HOSTCXX) -cudart static
+CSRC     := tsxcount_b200/csrc
+HOST     := tsxcount_b200/host
+LIBDIR   := tsxcount_b200/lib
+BINDIR   := tsxcount_b200/bin
+LIB      := $(LIBDIR)/libtsxcuda.so
+CLI      := $(BINDIR)/tsxcount
+
+.PHONY: all lib cli oracle clean
+all: lib cli oracle
+
+lib: $(LIB)
+
+$(LIB): $(CSRC)/tsx_api.cu $(CSRC)/tsx_host_pack.cpp $(wildcard $(CSRC)/*.cuh) include/tsxcount_cuda.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/tsx_api.cu $(CSRC)/tsx_host_pack.cpp
+
+cli: $(CLI)
+
+$(CLI): $(wildcard $(HOST)/*.cpp) $(wildcard $(HOST)/*.h) include/tsxcount_cuda.h $(LIB)
+	@mkdir -p $(BINDIR)
+	$(HOSTCXX) -O2 -std=c++17 -Wall -fopenmp -Iinclude -o $@ $(wildcard $(HOST)/*.cpp) -L$(LIBDIR) -ltsxcuda -lz -Wl,-rpath,'$$ORIGIN/../lib'
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf $(LIBDIR) $(BINDIR)
+	$(MAKE) -C oracle clean

@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Mirrors the reference's own checks (paths relative to mjoppich/tsxCount):
+  --check            src/mains/main.cpp:224-396   every listed k-mer has the listed count, the number of
+                                                  distinct k-mers matches and no extra k-mer exists
+  testHashMapOld     src/mains/testExecution.h:363-497   4 k-mers added N, N/2, N/2, N/4 times
+  README example     README.md:13-24
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tsx():
+    import tsxcount_b200 as m
+    assert m._lib.load().tsxc_device_count() >= 1, "no sm_100 device visible"
+    return m
+
+
+def check_against_oracle(tsx, hm, oc):
+    """The reference's --check, strengthened: dump == oracle as a map, lookups agree, distinct agrees."""
+    kw = hm.kw
+    assert hm.getKmerCount() == oc.n_distinct
+    st = hm.stats()
+    assert st["kmers_added"] == oc.n_total
+    assert st["error_flags"] == 0
+    keys, counts = hm.getAllKmers()
+    got = {tuple(k): int(c) for k, c in zip(keys.tolist(), counts.tolist())}
+    assert len(got) == len(keys), "dump lists a k-mer twice"
+    want = oc.as_dict(kw)
+    assert got == want
+    if oc.n_distinct:
+        looked = hm.getKmerCounts(oc.keys_kw(kw))
+        assert np.array_equal(looked, oc.counts)
+
+
+def run_case(tsx, seqs, k, l, s, flags=0):
+    oc = orc.count_seqs(seqs, k)
+    with tsx.TSXHashMapCUDA(l, s, k, flags=flags) as hm:
+        hm.addSequences(seqs)
+        check_against_oracle(tsx, hm, oc)
+        return hm.stats(), oc
+
+
+# ---- config 1: the bundled example ----------------------------------------------------------------
+def test_c1_bundled_fastq_matches_golden_count_file(tsx, tmp_path):
+    fastq = orc.golden_path("c1_bundled_k14.fastq", tmp_path)
+    golden = orc.golden_path("c1_bundled_k14.fastq.14.count", tmp_path)
+    want = {}
+    with open(golden) as f:
+        for line in f:
+            kmer, cnt = line.rstrip("\n").split("\t")
+            want[kmer] = int(cnt)
+    assert len(want) == 194697 and sum(want.values()) == 202204
+    # reference defaults: k=14, l=26, s=4 (main.cpp:409-413); exact s exercises the overflow entries
+    with tsx.TSXHashMapCUDA(26, 4, 14, flags=tsx.TSXC_FLAG_EXACT_S) as hm:
+        hm.addFastq(fastq)
+        assert hm.getKmerCount() == 194697
+        st = hm.stats()
+        assert st["value_bits"] == 4 and st["overflow_entries"] == 52  # 52 k-mers have count > 15
+        out = tmp_path / "dump.count"
+        hm.dump(out)
+        got = {}
+        with open(out) as f:
+            for line in f:
+                kmer, cnt = line.rstrip("\n").split("\t")
+                assert kmer not in got
+                got[kmer] = int(cnt)
+        assert got == want
+        arr = tsx.sequtils.kmers_to_array(list(want.keys()), 14)
+        looked = hm.getKmerCounts(arr)
+        assert looked.tolist() == list(want.values())
+        # absent k-mers answer 0 (getKmerCount stops at the first empty slot, TSXHashMap.h:548-638)
+        absent = [k for k in ("ACGTACGTACGTAC", "TTTTTTTTTTTTTT", "GGGGGGGGGGGGGA") if k not in want]
+        assert all(hm.getKmerCount(k) == 0 for k in absent)
+
+
+def test_readme_example(tsx):
+    # README.md:13-24: ATCGAGTCAGTA, k=5 -> 8 k-mers
+    seq = b"ATCGAGTCAGTA"
+    st, oc = run_case(tsx, [seq], 5, 8, 4)
+    assert oc.n_total == 8
+
+
+# ---- synthetic configs at oracle-sized inputs -----------------------------------------------------
+CASES = [
+    # name, gen kwargs, n_reads, read_len, k, l, s, flags
+    ("c2_uniform_k31", dict(mode=0, seed=0xC2), 3000, 150, 31, 20, 0, 0),
+    ("c2_fakeseq_k31_exact_s4", dict(mode=1, seed=0xC2), 3000, 150, 31, 20, 4, 1),
+    ("c2_fakeseq_k31_wide", dict(mode=1, seed=0xC2), 3000, 150, 31, 20, 0, 0),
+    ("k32_uniform", dict(mode=0, seed=7), 2000, 150, 32, 19, 4, 0),
+    ("k32_small_table_class12", dict(mode=0, seed=8), 300, 150, 32, 16, 12, 1),
+    ("k33_uniform", dict(mode=0, seed=9), 2000, 150, 33, 19, 4, 0),
+    ("c3_zipf_k63_exact_s4", dict(mode=2, seed=0xC3, genome_len=1 << 8, sub_rate_q16=655), 4000, 150, 63, 19, 4, 1),
+    ("c3_zipf_k63_wide", dict(mode=2, seed=0xC3, genome_len=1 << 8, sub_rate_q16=655), 4000, 150, 63, 19, 0, 0),
+    ("k64_uniform", dict(mode=0, seed=10), 2000, 150, 64, 18, 4, 0),
+    ("k64_tiny_table_class24", dict(mode=0, seed=11), 40, 150, 64, 12, 4, 0),
+    ("k65_uniform", dict(mode=0, seed=12), 2000, 150, 65, 18, 4, 0),
+    ("k96_fakeseq", dict(mode=1, seed=13), 2000, 150, 96, 18, 4, 1),
+    ("c4_uniform_k127", dict(mode=0, seed=0xC4), 4000, 150, 127, 18, 0, 0),
+    ("c4_zipf_k127_exact_s4", dict(mode=2, seed=0xC4, genome_len=1 << 6, sub_rate_q16=300), 3000, 150, 127, 18, 4, 1),
+    ("k128_fakeseq", dict(mode=1, seed=14), 1500, 150, 128, 17, 4, 0),
+    ("c5_genome_k31", dict(mode=3, seed=0xC5, genome_len=50000, sub_rate_q16=328), 8000, 150, 31, 21, 4, 0),
+    ("k14_genome_exact_s2", dict(mode=3, seed=15, genome_len=3000, sub_rate_q16=100), 4000, 100, 14, 16, 2, 1),
+    ("k5_tiny", dict(mode=0, seed=16), 500, 40, 5, 8, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_synthetic_parity(tsx, case):
+    name, gen, n_reads, read_len, k, l, s, flags = case
+    seqs = orc.gen_reads(n_reads=n_reads, read_len=read_len, **gen)
+    run_case(tsx, seqs, k, l, s, flags)
+
+
+def test_all_layout_classes_are_exercised(tsx):
+    """(KW, W) classes (1,1) (1,2) (2,2) (2,4) (4,4) are all reached by CASES."""
+    lib = tsx._lib.load()
+    seen = set()
+    for name, gen, n_reads, read_len, k, l, s, flags in CASES:
+        st = tsx._lib.TsxcStats()
+        assert lib.tsxc_debug_layout(k, l, s, flags, 1, C.byref(st)) == 0, name
+        seen.add((st.key_words, st.entry_words))
+    assert seen == {(1, 1), (1, 2), (2, 2), (2, 4), (4, 4)}
+
+
+# ---- the reference's dormant known-answer test ------------------------------------------------------
+@pytest.mark.parametrize("k,l", [(14, 20), (31, 20), (63, 18), (127, 16)])
+def test_known_answer_four_kmers_two_overflow_levels(tsx, k, l):
+    # testExecution.h:406-409,423,493-496: values 10067, 2786, 9816, 156 added N, N/2, N/2, N/4 times,
+    # N = 2048*4*24, with s = 4: counts far beyond one overflow level of the reference
+    N = 2048 * 4 * 24
+    vals, reps = [10067, 2786, 9816, 156], [N, N // 2, N // 2, N // 4]
+    with tsx.TSXHashMapCUDA(l, 4, k, flags=tsx.TSXC_FLAG_EXACT_S) as hm:
+        kw = hm.kw
+        keys = np.zeros((4, kw), dtype=np.uint64)
+        keys[:, 0] = vals
+        rng = np.random.default_rng(1)
+        stream = np.repeat(np.arange(4), reps)
+        rng.shuffle(stream)
+        for part in np.array_split(stream, 7):          # several launches, interleaved k-mers
+            hm.addKmers(keys[part])
+        assert hm.getKmerCounts(keys).tolist() == reps
+        assert hm.getKmerCount() == 4
+        st = hm.stats()
+        assert st["overflow_entries"] == 4 and st["kmers_added"] == sum(reps)
+        k2, c2 = hm.getAllKmers()
+        assert sorted(zip(k2[:, 0].tolist(), c2.tolist())) == sorted(zip(vals, reps))
+
+
+# ---- edge cases -------------------------------------------------------------------------------------
+def test_empty_and_short_reads(tsx):
+    k = 21
+    seqs = [b"", b"ACGT", b"A" * 20, b"C" * 21, b"", b"ACGTACGTACGTACGTACGTACGTA", b"G"]
+    st, oc = run_case(tsx, seqs, k, 12, 4)
+    assert oc.n_total == 1 + 5
+    with tsx.TSXHashMapCUDA(12, 4, k) as hm:               # nothing at all
+        hm.addSequences([])
+        hm.addSequences([b"", b""])
+        assert hm.getKmerCount() == 0 and hm.getAllKmers()[0].shape[0] == 0
+
+
+def test_ragged_long_reads_cross_word_boundaries(tsx):
+    rng = np.random.default_rng(3)
+    seqs = []
+    for ln in [1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 1000, 19751, 5, 14, 15]:
+        seqs.append(bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=ln)))
+    for k in (14, 32, 33, 64, 65, 128):
+        run_case(tsx, seqs, k, 17, 4)
+
+
+def test_homopolymers_and_heavy_hitter_overflow(tsx):
+    # one slot receives every increment: run aggregation + warp aggregation + carry into the overflow entry
+    seqs = [b"A" * 5000, b"A" * 777, b"C" * 3000, b"ACGT" * 500, b"T" * 64]
+    for k, s, flags in ((31, 4, 1), (31, 0, 0), (63, 3, 1), (127, 2, 1)):
+        st, oc = run_case(tsx, seqs, k, 14, s, flags)
+        assert st["overflow_entries"] >= (1 if flags else 0)
+
+
+def test_non_acgt_bases_split_reads(tsx):
+    # N policy: no k-mer spans a non-ACGT byte; lower case is non-ACGT as in the reference
+    seqs = [b"ACGTACGTNACGTACGTACGT", b"NNNN", b"ACGTacgtACGTACGTACGT", b"ACGTACGTACGTN"]
+    st, oc = run_case(tsx, seqs, 8, 10, 4)
+    assert oc.n_skipped > 0 and oc.n_total == (1 + 5) + 0 + (0 + 5) + 5
+
+
+def test_invalid_and_full(tsx):
+    with pytest.raises(tsx.TsxcError) as e:                # TSXHashMap.h:91-94
+        tsx.TSXHashMapCUDA(28, 4, 14)
+    assert e.value.status == tsx.TSXC_E_INVALID
+    with pytest.raises(tsx.TsxcError) as e:
+        tsx.TSXHashMapCUDA(20, 4, 129)
+    assert e.value.status == tsx.TSXC_E_INVALID
+    # 2^6 slots cannot hold 5000 distinct 20-mers: reference exits 42 (TSXHashMap.h:340-343)
+    seqs = orc.gen_reads(seed=5, n_reads=50, read_len=120, mode=0)
+    with tsx.TSXHashMapCUDA(6, 4, 20) as hm:
+        with pytest.raises(tsx.TsxcError) as e:
+            hm.addSequences(seqs)
+        assert e.value.status == tsx.TSXC_E_TABLE_FULL
+
+
+def test_high_load_factor(tsx):
+    # ~0.9 load: long probe sequences, still exact
+    seqs = orc.gen_reads(seed=21, n_reads=1000, read_len=150, mode=0)  # 120k distinct 31-mers
+    st, oc = run_case(tsx, seqs, 31, 17, 4)                             # 131072 slots
+    assert oc.n_distinct / st["n_slots"] > 0.85 and st["max_reprobe"] > 3
+
+
+def test_repeated_batches_are_linear(tsx):
+    seqs = orc.gen_reads(seed=22, n_reads=500, read_len=150, mode=1)
+    oc = orc.count_seqs(seqs, 31)
+    with tsx.TSXHashMapCUDA(18, 4, 31, flags=tsx.TSXC_FLAG_EXACT_S) as hm:
+        for _ in range(3):
+            hm.addSequences(seqs)
+        assert hm.getKmerCount() == oc.n_distinct
+        assert np.array_equal(hm.getKmerCounts(oc.keys_kw(1)), 3 * oc.counts)
+        hm.clear()
+        assert hm.getKmerCount() == 0 and hm.getKmerCounts(oc.keys_kw(1)).sum() == 0
+
+
+def test_no_warp_aggregation_flag_same_result(tsx):
+    seqs = orc.gen_reads(seed=23, n_reads=800, read_len=150, mode=1)
+    run_case(tsx, seqs, 31, 18, 4, flags=tsx.TSXC_FLAG_NO_WARP_AGG | tsx.TSXC_FLAG_EXACT_S)
+
+
+# ---- device generator == oracle generator ------------------------------------------------------------
+@pytest.mark.parametrize("mode,genome,sub", [(0, 0, 0), (1, 0, 0), (2, 1 << 10, 655), (3, 100000, 328), (0, 0, 500)])
+def test_device_generator_matches_oracle(tsx, mode, genome, sub):
+    lib = tsx._lib.load()
+    n_reads, read_len, first, count = 5000, 150, 1234, 777
+    p = tsx.TsxcGenParams(0xABC, n_reads, read_len, mode, genome, sub, 0)
+    n_words = (count * read_len + 31) // 32
+    d_packed, d_off = C.c_void_p(), C.c_void_p()
+    tsx._lib.check(lib.tsxc_device_alloc(0, n_words * 8, C.byref(d_packed)))
+    tsx._lib.check(lib.tsxc_device_alloc(0, (count + 1) * 8, C.byref(d_off)))
+    try:
+        tsx._lib.check(lib.tsxc_gen_reads_device(C.byref(p), first, count, 0, None, d_packed, d_off))
+        packed = np.zeros(n_words, dtype=np.uint64)
+        off = np.zeros(count + 1, dtype=np.uint64)
+        tsx._lib.check(lib.tsxc_memcpy(0, packed.ctypes.data, d_packed, n_words * 8, 2))
+        tsx._lib.check(lib.tsxc_memcpy(0, off.ctypes.data, d_off, (count + 1) * 8, 2))
+    finally:
+        lib.tsxc_device_free(0, d_packed)
+        lib.tsxc_device_free(0, d_off)
+    seqs = orc.gen_reads(seed=0xABC, n_reads=n_reads, read_len=read_len, mode=mode, genome_len=genome,
+                         sub_rate_q16=sub, first=first, count=count)
+    ascii_, offsets = tsx.sequtils.concat_reads(seqs)
+    want_packed, want_off, nbad = tsx.sequtils.pack_reads(ascii_, offsets)
+    assert nbad == 0
+    assert np.array_equal(off, want_off)
+    assert np.array_equal(packed, want_packed[:n_words])
+
+
+# ---- hash-sharded table on one GPU (the multi-GPU data path without the exchange) -------------------
+@pytest.mark.parametrize("k,n_shards", [(31, 2), (31, 8), (63, 4), (127, 2)])
+def test_sharded_route_and_insert(tsx, k, n_shards):
+    lib = tsx._lib.load()
+    seqs = orc.gen_reads(seed=31, n_reads=3000, read_len=150, mode=1)
+    oc = orc.count_seqs(seqs, k)
+    ascii_, offsets = tsx.sequtils.concat_reads(seqs)
+    packed, seg, _ = tsx.sequtils.pack_reads(ascii_, offsets)
+    n_bases = int(seg[-1])
+    shards = [tsx.TSXHashMapCUDA(20, 4, k, shard_rank=r, n_shards=n_shards) for r in range(n_shards)]
+    kw = shards[0].kw
+    cap = oc.n_total  # worst case: everything to one shard
+    bufs = {}
+
+    def dalloc(name, nbytes):
+        p = C.c_void_p()
+        tsx._lib.check(lib.tsxc_device_alloc(0, nbytes, C.byref(p)))
+        bufs[name] = p
+        return p
+
+    try:
+        d_packed = dalloc("packed", packed.nbytes)
+        d_off = dalloc("off", seg.nbytes)
+        d_send = dalloc("send", n_shards * cap * kw * 8)
+        d_cnt = dalloc("cnt", n_shards * 8)
+        tsx._lib.check(lib.tsxc_memcpy(0, d_packed, packed.ctypes.data, packed.nbytes, 1))
+        tsx._lib.check(lib.tsxc_memcpy(0, d_off, seg.ctypes.data, seg.nbytes, 1))
+        zero = np.zeros(n_shards, dtype=np.uint64)
+        tsx._lib.check(lib.tsxc_memcpy(0, d_cnt, zero.ctypes.data, zero.nbytes, 1))
+        shards[0].routeReadsDevice(d_packed, d_off, len(seg) - 1, n_bases, d_send, cap, d_cnt)
+        shards[0].sync()
+        cnt = np.zeros(n_shards, dtype=np.uint64)
+        tsx._lib.check(lib.tsxc_memcpy(0, cnt.ctypes.data, d_cnt, cnt.nbytes, 2))
+        assert int(cnt.sum()) == oc.n_total
+        got = {}
+        for r, hm in enumerate(shards):
+            hm.addHashesDevice(C.c_void_p(d_send.value + r * cap * kw * 8), int(cnt[r]))
+            hm.sync()
+            keys, counts = hm.getAllKmers()
+            for key, c in zip(keys.tolist(), counts.tolist()):
+                assert tuple(key) not in got, "k-mer present in two shards"
+                got[tuple(key)] = int(c)
+        assert got == oc.as_dict(kw)
+        assert sum(hm.getKmerCount() for hm in shards) == oc.n_distinct
+        # a shard answers 0 for k-mers it does not own; the per-shard answers sum to the oracle's
+        total = sum(hm.getKmerCounts(oc.keys_kw(kw)) for hm in shards)
+        assert np.array_equal(total, oc.counts)
+    finally:
+        for p in bufs.values():
+            lib.tsxc_device_free(0, p)
+        for hm in shards:
+            hm.close()

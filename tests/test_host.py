@@ -1,0 +1,166 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the bijective
+hash round-trips (TSXHashMap::testHashFunction, TSXHashMap.h:724-735 of the reference), the entry layout
+selection, the 2-bit packer and the FASTQ reader.  No compute entry point is called without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+import tsxcount_b200 as tsx
+from tsxcount_b200 import _lib, sequtils
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    hdr = open(os.path.join(ROOT, "include", "tsxcount_cuda.h")).read()
+    declared = set(re.findall(r"\b(tsxc_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"tsxc_table", "tsxc_stats_t", "tsxc_gen_params"}
+    lib = _lib.load()
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert lib.tsxc_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    if lib.tsxc_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(tsx.TsxcError) as e:
+        tsx.TSXHashMapCUDA(20, 4, 14)
+    assert e.value.status == _lib.TSXC_E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tsxcount_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle_py" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/oracle.c has", ""), f
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 14, 16, 17, 31, 32, 33, 48, 63, 64, 65, 90, 96, 97, 127, 128])
+def test_hash_is_a_bijection_on_2k_bits(k):
+    lib = _lib.load()
+    kw = sequtils.key_words(k)
+    rng = np.random.default_rng(k)
+    nbits = 2 * k
+    seen = set()
+    for trial in range(300):
+        v = int.from_bytes(rng.bytes(32), "little") & ((1 << nbits) - 1)
+        if trial == 0:
+            v = 0
+        if trial == 1:
+            v = (1 << nbits) - 1
+        key = np.array([(v >> (64 * j)) & (2**64 - 1) for j in range(kw)], dtype=np.uint64)
+        h = np.zeros(kw, dtype=np.uint64)
+        back = np.zeros(kw, dtype=np.uint64)
+        assert lib.tsxc_debug_hash(k, key.ctypes.data, h.ctypes.data) == 0
+        assert lib.tsxc_debug_unhash(k, h.ctypes.data, back.ctypes.data) == 0
+        assert np.array_equal(back, key)
+        hv = sum(int(x) << (64 * j) for j, x in enumerate(h.tolist()))
+        assert hv < (1 << nbits), "hash leaves the 2k-bit domain"
+        seen.add(hv)
+    if nbits >= 20:
+        assert len(seen) == 300
+    if nbits <= 12:  # exhaustive: a permutation
+        imgs = set()
+        for v in range(1 << nbits):
+            key = np.array([v], dtype=np.uint64)
+            h = np.zeros(1, dtype=np.uint64)
+            lib.tsxc_debug_hash(k, key.ctypes.data, h.ctypes.data)
+            imgs.add(int(h[0]))
+        assert imgs == set(range(1 << nbits))
+
+
+def test_hash_low_bits_avalanche():
+    """Bucket indices come from the low bits of hash word 0: single-base changes anywhere in the k-mer
+    must flip them about half the time (the reference's triangular matrix fails this)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for k in (31, 63, 127):
+        kw = sequtils.key_words(k)
+        flips = []
+        for _ in range(200):
+            v = int.from_bytes(rng.bytes(32), "little") & ((1 << (2 * k)) - 1)
+            pos = int(rng.integers(0, 2 * k))
+            outs = []
+            for x in (v, v ^ (1 << pos)):
+                key = np.array([(x >> (64 * j)) & (2**64 - 1) for j in range(kw)], dtype=np.uint64)
+                h = np.zeros(kw, dtype=np.uint64)
+                lib.tsxc_debug_hash(k, key.ctypes.data, h.ctypes.data)
+                outs.append(int(h[0]) & 0xFFFFFFFF)
+            flips.append(bin(outs[0] ^ outs[1]).count("1"))
+        assert 13 < np.mean(flips) < 19, (k, np.mean(flips))
+
+
+def test_layout_selection():
+    lib = _lib.load()
+
+    def layout(k, l, s, flags=0, shards=1):
+        st = _lib.TsxcStats()
+        rc = lib.tsxc_debug_layout(k, l, s, flags, shards, C.byref(st))
+        return rc, st
+
+    rc, st = layout(31, 34, 0)                      # config 2: 8-byte entries, 4 per 32-byte bucket
+    assert rc == 0 and (st.key_words, st.entry_words, st.slots_per_bucket) == (1, 1, 4)
+    assert st.table_bytes == (1 << 34) * 8 and st.quotient_bits == 62 - 32 and st.value_bits >= 20
+    rc, st = layout(14, 26, 4, _lib.TSXC_FLAG_EXACT_S)   # config 1 defaults (main.cpp:409-413)
+    assert rc == 0 and st.value_bits == 4 and st.entry_words == 1
+    rc, st = layout(63, 33, 0)                      # config 3: 16-byte entries
+    assert rc == 0 and (st.key_words, st.entry_words, st.slots_per_bucket) == (2, 2, 2)
+    rc, st = layout(127, 32, 0)                     # config 4: 32-byte entries, one per sector
+    assert rc == 0 and (st.key_words, st.entry_words, st.slots_per_bucket) == (4, 4, 1)
+    assert st.table_bytes == (1 << 32) * 32
+    rc, st = layout(31, 37, 0, 0, 8)                # config 5: 8 shards of 2^34 slots
+    assert rc == 0 and st.n_slots == 1 << 34 and st.n_shards == 8
+    assert layout(14, 28, 4)[0] == _lib.TSXC_E_INVALID      # 2k <= l (TSXHashMap.h:91-94)
+    assert layout(129, 20, 4)[0] == _lib.TSXC_E_INVALID
+    assert layout(31, 20, 4, 0, 3)[0] == _lib.TSXC_E_UNSUPPORTED  # shard count must be a power of two
+
+
+def test_pack_reads_matches_oracle_encoding():
+    seqs = orc.gen_reads(seed=9, n_reads=50, read_len=77, mode=0) + [b"", b"ACGT", b"A"]
+    ascii_, off = sequtils.concat_reads(seqs)
+    packed, seg, nbad = sequtils.pack_reads(ascii_, off)
+    assert nbad == 0 and np.array_equal(seg, off)
+    total = int(off[-1])
+    v = 0
+    for j, w in enumerate(packed.tolist()):
+        v |= w << (64 * j)
+    text = b"".join(seqs)
+    assert all("ACGT"[(v >> (2 * i)) & 3] == chr(text[i]) for i in range(total))
+    assert v >> (2 * total) == 0
+
+
+def test_pack_reads_splits_at_non_acgt():
+    ascii_, off = sequtils.concat_reads([b"ACGTNACG", b"NN", b"acgT", b"GGGG"])
+    packed, seg, nbad = sequtils.pack_reads(ascii_, off)
+    assert nbad == 1 + 2 + 3
+    lens = np.diff(seg).tolist()
+    assert [x for x in lens if x] == [4, 3, 1, 4]
+    assert sequtils.to_sequence(packed[:1], 12) == "ACGTACGTGGGG"
+
+
+def test_from_to_sequence_roundtrip():
+    for s in ("A", "ACGT", "T" * 32, "ACGTTGCA" * 8 + "A", "G" * 128):
+        assert sequtils.to_sequence(sequtils.from_sequence(s), len(s)) == s
+    assert int(sequtils.from_sequence("CAAA")[0]) == 1      # first base = least significant digit
+    with pytest.raises(ValueError):
+        sequtils.from_sequence("ACGN")
+
+
+def test_read_fastq_reference_semantics(tmp_path):
+    # FastXReader.h:363-372: empty lines are skipped anywhere; records are groups of 4 non-empty lines
+    p = tmp_path / "x.fastq"
+    p.write_bytes(b"@r1\nACGT\n+\n&&&&\n\n@r2\n\nGGCC\n+\n&&&&\n@r3\nTT\n+\n")
+    assert sequtils.read_fastq(p) == [b"ACGT", b"GGCC"]
+    import gzip
+    gz = tmp_path / "y.fastq.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(b"@r1\nACGT\n+\n&&&&\n")
+    assert sequtils.read_fastq(gz) == [b"ACGT"]

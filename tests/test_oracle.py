@@ -1,0 +1,97 @@
+"""CPU tests of the oracle itself: it must reproduce every golden vector the reference holds for this
+path before anything is compared against it."""
+import gzip
+import hashlib
+import json
+import os
+
+import numpy as np
+
+import oracle_py as orc
+
+GOLD = orc.GOLDEN
+
+
+def test_oracle_reproduces_bundled_count_file_byte_for_byte(tmp_path):
+    # data/small_t7.1000.fastq + .14.count of the reference (fixture copies in tests/golden/)
+    fastq = orc.golden_path("c1_bundled_k14.fastq", tmp_path)
+    out = tmp_path / "o.count"
+    orc.write_dump_fastq(fastq, 14, out)
+    want = gzip.open(os.path.join(GOLD, "c1_bundled_k14.fastq.14.count.gz"), "rb").read()
+    got = open(out, "rb").read()
+    assert got == want
+    assert got.count(b"\n") == 194697
+
+
+def test_bundled_numbers():
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        oc = orc.count_fastq(orc.golden_path("c1_bundled_k14.fastq", d), 14)
+    assert (oc.n_distinct, oc.n_total, int(oc.counts.max())) == (194697, 202204, 589)
+    assert int((oc.counts > 15).sum()) == 52 and int((oc.counts > 255).sum()) == 5
+
+
+def test_reference_binary_pins_are_green_and_fixtures_unchanged(tmp_path):
+    """tests/golden/ref_binary_pins.json is written by oracle/make_ref_pins.py: the UNMODIFIED reference
+    binary ran --check against the oracle's dump for each case and reported total errors 0."""
+    pins = json.load(open(os.path.join(GOLD, "ref_binary_pins.json")))
+    assert len(pins["cases"]) >= 5
+    for case in pins["cases"]:
+        assert case["pinned"], case["name"]
+        for r in case["runs"]:
+            assert r["total_errors"] == 0 and r["xor_kmer_count"] == 0
+            assert r["reference_kmer_count"] == case["oracle_distinct"] == r["tsxcount_kmer_count"]
+        # the committed fixtures are the files the reference binary saw, and the oracle still
+        # produces the same dump from them
+        name, k = case["name"], case["k"]
+        fq = os.path.join(GOLD, f"{name}.fastq.gz")
+        if not os.path.exists(fq):
+            continue
+        fastq = orc.golden_path(f"{name}.fastq", tmp_path)
+        assert hashlib.sha256(open(fastq, "rb").read()).hexdigest() == case["fastq_sha256"]
+        out = tmp_path / f"{name}.count"
+        orc.write_dump_fastq(fastq, k, out)
+        assert hashlib.sha256(open(out, "rb").read()).hexdigest() == case["count_sha256"]
+
+
+def test_readme_example():
+    # README.md:13-24 of the reference
+    oc = orc.count_seqs([b"ATCGAGTCAGTA"], 5)
+    assert oc.n_total == 8 and oc.n_distinct == 8
+
+
+def test_extraction_semantics():
+    # testExecution.h:15-36: len < k -> nothing; len == k -> one k-mer; no k-mer crosses reads
+    oc = orc.count_seqs([b"ACG", b"ACGT", b"ACGTA", b""], 4)
+    assert oc.n_total == 1 + 2
+    d = oc.as_dict(1)
+    enc = lambda s: sum("ACGT".index(c) << (2 * i) for i, c in enumerate(s))  # noqa: E731
+    assert d == {(enc("ACGT"),): 2, (enc("CGTA"),): 1}
+
+
+def test_encoding_first_base_is_least_significant():
+    # SequenceUtils.h:96-123
+    import ctypes as C
+    key = (C.c_uint64 * 4)()
+    assert orc.lib().orc_encode_kmer(b"CAAA", 4, key) == 0 and key[0] == 1
+    assert orc.lib().orc_encode_kmer(b"AAAT", 4, key) == 0 and key[0] == 3 << 6
+    assert orc.lib().orc_encode_kmer(b"ACGN", 4, key) == -1
+    buf = C.create_string_buffer(5)
+    key[0] = 0b11100100
+    orc.lib().orc_decode_kmer(key, 4, buf)
+    assert buf.value == b"ACGT"
+
+
+def test_n_policy_skips_spanning_kmers():
+    oc = orc.count_seqs([b"ACGTNACGT"], 4)
+    assert oc.n_total == 2 and oc.n_skipped == 4
+
+
+def test_generator_is_deterministic_and_shaped():
+    a = orc.gen_reads(seed=1, n_reads=100, read_len=150, mode=1)
+    b = orc.gen_reads(seed=1, n_reads=100, read_len=150, mode=1, first=10, count=5)
+    assert a[10:15] == b and all(len(s) == 150 and set(s) <= set(b"ACGT") for s in a)
+    assert any(b"A" * 25 in s for s in a)          # poly-A tails (generateFakeSequences.py:11-13 style)
+    z = orc.gen_reads(seed=2, n_reads=2000, read_len=50, mode=2, genome_len=1 << 10)
+    top = max(set(z), key=z.count)
+    assert z.count(top) > 100                       # log-uniform ranks: heavy hitters

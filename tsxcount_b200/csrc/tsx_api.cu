@@ -1,0 +1,614 @@
+// tsx_api.cu — C ABI (include/tsxcount_cuda.h) over the sm_100a kernels.  No CPU fallback: every
+// compute entry point needs a CUDA device and reports TSXC_E_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/tsxcount_cuda.h"
+#include "tsx_gen.cuh"
+#include "tsx_kernels.cuh"
+
+using namespace tsx;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Staging {
+    uint64_t* d_packed = nullptr;  size_t cap_packed = 0;   // words
+    uint64_t* d_offsets = nullptr; size_t cap_offsets = 0;  // entries
+    uint32_t* d_ends = nullptr;    size_t cap_ends = 0;     // words
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool used = false;
+};
+
+}  // namespace
+
+struct tsxc_table {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy_stream = nullptr;  // H2D staging
+    Layout L{};
+    TableView tv{};
+    uint64_t* d_words = nullptr;
+    unsigned long long* d_ctr = nullptr;
+    Staging stage[2];
+    int next_stage = 0;
+    // device-variant scratch (ends bitmap for caller-resident reads)
+    uint32_t* d_ends = nullptr; size_t cap_ends = 0;
+    // k-mer / count staging for add_kmers / lookup / dump
+    uint64_t* d_keys = nullptr; size_t cap_keys = 0;      // words
+    uint64_t* d_counts = nullptr; size_t cap_counts = 0;  // entries
+    unsigned long long* d_nout = nullptr;
+    std::string err;
+    std::mutex mu;
+};
+
+namespace {
+
+int fail(tsxc_table* t, int code, const std::string& msg) {
+    if (t) t->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(t, e_ == cudaErrorMemoryAllocation ? TSXC_E_NOMEM : TSXC_E_CUDA,                 \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                             \
+    } while (0)
+
+template <typename T>
+int ensure(tsxc_table* t, T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return TSXC_OK;
+    if (*p) { CU(cudaStreamSynchronize(t->stream)); CU(cudaStreamSynchronize(t->copy_stream)); CU(cudaFree(*p)); *p = nullptr; *cap = 0; }
+    const size_t want = std::max(need, *cap + *cap / 2);
+    CU(cudaMalloc(p, want * sizeof(T)));
+    *cap = want;
+    return TSXC_OK;
+}
+
+int grid_for(const tsxc_table* t, uint64_t work_items, int per_sm = 8) {
+    const uint64_t blocks_needed = (work_items + kBlockThreads - 1) / kBlockThreads;
+    const uint64_t cap = (uint64_t)t->sms * per_sm;
+    return (int)std::max<uint64_t>(1, std::min(blocks_needed, cap));
+}
+
+#define TSX_DISPATCH(L, M)                                      \
+    do {                                                        \
+        if ((L).KW == 1 && (L).W == 1) { M(1, 1); }             \
+        else if ((L).KW == 1 && (L).W == 2) { M(1, 2); }        \
+        else if ((L).KW == 2 && (L).W == 2) { M(2, 2); }        \
+        else if ((L).KW == 2 && (L).W == 4) { M(2, 4); }        \
+        else if ((L).KW == 4 && (L).W == 4) { M(4, 4); }        \
+        else return fail(t, TSXC_E_UNSUPPORTED, "no kernel for this entry class"); \
+    } while (0)
+
+int status_from_flags(tsxc_table* t, uint64_t flags) {
+    if (flags & ERR_TABLE_FULL) return fail(t, TSXC_E_TABLE_FULL, "reprobe limit reached: table full (reference: exit(42))");
+    if (flags & ERR_SATURATED) return fail(t, TSXC_E_COUNT_SATURATED, "overflow counter saturated");
+    if (flags & ERR_SEND_OVERFLOW) return fail(t, TSXC_E_INVALID, "send buffer of a shard overflowed");
+    if (flags & ERR_WRONG_SHARD) return fail(t, TSXC_E_INVALID, "k-mer hash routed to the wrong shard");
+    return TSXC_OK;
+}
+
+int launch_count_reads(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint32_t* d_ends,
+                       uint64_t n_reads, uint64_t n_bases, cudaStream_t s) {
+    if (n_bases == 0 || n_reads == 0) return TSXC_OK;
+    const uint64_t n_words = (n_bases + 31) >> 5;
+    CU(cudaMemsetAsync(d_ends, 0, n_words * sizeof(uint32_t), s));
+    k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, d_ends);
+    const int grid = grid_for(t, n_words);
+    const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
+#define M(KW_, W_)                                                                                                    \
+    if (agg) k_count_reads<KW_, W_, true><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, n_words, n_bases);  \
+    else k_count_reads<KW_, W_, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, n_words, n_bases)
+    TSX_DISPATCH(t->L, M);
+#undef M
+    CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
+int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, uint32_t rank, uint32_t n_shards,
+                tsxc_table** out) {
+    tsxc_table* t = nullptr;  // for CU()/fail() before the handle exists
+    if (!out) return fail(t, TSXC_E_INVALID, "out == NULL");
+    *out = nullptr;
+    if (k < 1 || k > TSXC_MAX_K) return fail(t, TSXC_E_INVALID, "k out of range [1,128]");
+    if (2 * k <= l) return fail(t, TSXC_E_INVALID, "Invalid lengths for hashmap size and value of k");  // TSXHashMap.h:93
+    Layout L;
+    if (!make_layout(k, l, s, flags, rank, n_shards, &L)) return fail(t, TSXC_E_UNSUPPORTED, "(k, l, s, shards) fits no entry class");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(t, TSXC_E_CUDA, "no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(t, TSXC_E_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(t, TSXC_E_CUDA, "device is not sm_100 class");
+    CU(cudaSetDevice(device));
+    tsxc_table* h = new (std::nothrow) tsxc_table();
+    if (!h) return fail(t, TSXC_E_NOMEM, "host allocation failed");
+    t = h;
+    h->device = device;
+    h->sms = prop.multiProcessorCount;
+    h->L = L;
+    auto bail = [&](int code) { std::string m = h->err; tsxc_destroy(h); g_create_error = m; return code; };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        h->err = cudaGetErrorString(e);
+        return bail(TSXC_E_CUDA);
+    }
+    if ((e = cudaMalloc(&h->d_words, L.table_bytes)) != cudaSuccess) {
+        h->err = std::string("table allocation of ") + std::to_string(L.table_bytes) + " bytes failed: " + cudaGetErrorString(e);
+        cudaGetLastError();
+        return bail(TSXC_E_NOMEM);
+    }
+    if ((e = cudaMalloc(&h->d_ctr, CTR_COUNT * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_nout, sizeof(unsigned long long))) != cudaSuccess) {
+        h->err = cudaGetErrorString(e);
+        return bail(TSXC_E_NOMEM);
+    }
+    for (auto& st : h->stage) {
+        if ((e = cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming)) != cudaSuccess) {
+            h->err = cudaGetErrorString(e);
+            return bail(TSXC_E_CUDA);
+        }
+    }
+    h->tv = make_view(L, h->d_words, h->d_ctr);
+    int rc = tsxc_clear(h);
+    if (rc != TSXC_OK) return bail(rc);
+    *out = h;
+    return TSXC_OK;
+}
+
+static int add_keys_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, bool hashed) {
+    if (n == 0) return TSXC_OK;
+    const int grid = grid_for(t, n);
+    const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
+#define M(KW_, W_)                                                                                              \
+    if (hashed) { if (agg) k_add_kmers<KW_, W_, true, true><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n);  \
+                  else k_add_kmers<KW_, W_, true, false><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n); }   \
+    else { if (agg) k_add_kmers<KW_, W_, false, true><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n);        \
+           else k_add_kmers<KW_, W_, false, false><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n); }
+    TSX_DISPATCH(t->L, M);
+#undef M
+    CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
+
+// Dump in bucket ranges small enough for the staging buffers; `emit` consumes each chunk on the host.
+template <typename Emit>
+static int dump_chunks(tsxc_table* t, Emit&& emit) {
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->copy_stream));
+    CU(cudaStreamSynchronize(t->stream));
+    const Layout& L = t->L;
+    const uint64_t chunk_slots = std::min<uint64_t>(L.n_slots, 1ULL << 24);
+    const uint64_t chunk_buckets = std::max<uint64_t>(1, chunk_slots / L.SPB);
+    int rc;
+    if ((rc = ensure(t, &t->d_keys, &t->cap_keys, (size_t)chunk_slots * L.KW))) return rc;
+    if ((rc = ensure(t, &t->d_counts, &t->cap_counts, (size_t)chunk_slots))) return rc;
+    std::vector<uint64_t> hk, hc;
+    for (uint64_t b0 = 0; b0 < L.n_buckets; b0 += chunk_buckets) {
+        const uint64_t b1 = std::min(L.n_buckets, b0 + chunk_buckets);
+        CU(cudaMemsetAsync(t->d_nout, 0, sizeof(unsigned long long), t->stream));
+        const int grid = grid_for(t, (b1 - b0) * L.SPB);
+#define M(KW_, W_) k_dump<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, b0, b1, t->d_keys, t->d_counts, chunk_slots, t->d_nout)
+        TSX_DISPATCH(t->L, M);
+#undef M
+        CU(cudaGetLastError());
+        unsigned long long n = 0;
+        CU(cudaMemcpyAsync(&n, t->d_nout, sizeof n, cudaMemcpyDeviceToHost, t->stream));
+        CU(cudaStreamSynchronize(t->stream));
+        if (n == 0) continue;
+        hk.resize((size_t)n * L.KW); hc.resize((size_t)n);
+        CU(cudaMemcpy(hk.data(), t->d_keys, n * L.KW * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hc.data(), t->d_counts, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        rc = emit(hk.data(), hc.data(), (uint64_t)n);
+        if (rc) return rc;
+    }
+    return TSXC_OK;
+}
+
+
+}  // namespace
+
+extern "C" {
+
+uint32_t tsxc_key_words(uint32_t k) { return (k < 1 || k > TSXC_MAX_K) ? 0 : (k <= 32 ? 1 : (k <= 64 ? 2 : 4)); }
+int tsxc_abi_version(void) { return TSXC_ABI_VERSION; }
+
+int tsxc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major >= 10) ++ok;
+    }
+    return ok;
+}
+
+const char* tsxc_status_string(int s) {
+    switch (s) {
+        case TSXC_OK: return "ok";
+        case TSXC_E_INVALID: return "invalid argument";
+        case TSXC_E_CUDA: return "CUDA error / no usable device";
+        case TSXC_E_NOMEM: return "out of memory";
+        case TSXC_E_UNSUPPORTED: return "unsupported (k, l, s)";
+        case TSXC_E_COUNT_SATURATED: return "overflow counter saturated";
+        case TSXC_E_IO: return "I/O error";
+        case TSXC_E_TABLE_FULL: return "table full";
+        default: return "unknown status";
+    }
+}
+
+const char* tsxc_last_error(const tsxc_table* t) { return t ? t->err.c_str() : g_create_error.c_str(); }
+
+int tsxc_create(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, tsxc_table** out) {
+    return create_impl(k, l, s, device, flags, 0, 1, out);
+}
+int tsxc_create_shard(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, uint32_t shard_rank,
+                      uint32_t n_shards, tsxc_table** out) {
+    return create_impl(k, l, s, device, flags, shard_rank, n_shards, out);
+}
+
+int tsxc_destroy(tsxc_table* t) {
+    if (!t) return TSXC_OK;
+    cudaSetDevice(t->device);
+    if (t->stream) cudaStreamSynchronize(t->stream);
+    if (t->copy_stream) cudaStreamSynchronize(t->copy_stream);
+    for (auto& st : t->stage) {
+        cudaFree(st.d_packed); cudaFree(st.d_offsets); cudaFree(st.d_ends);
+        if (st.copied) cudaEventDestroy(st.copied);
+        if (st.done) cudaEventDestroy(st.done);
+    }
+    cudaFree(t->d_ends); cudaFree(t->d_keys); cudaFree(t->d_counts); cudaFree(t->d_nout);
+    cudaFree(t->d_ctr); cudaFree(t->d_words);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+    delete t;
+    return TSXC_OK;
+}
+
+int tsxc_clear(tsxc_table* t) {
+    if (!t) return TSXC_E_INVALID;
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    CU(cudaMemsetAsync(t->d_words, 0, t->L.table_bytes, t->stream));
+    CU(cudaMemsetAsync(t->d_ctr, 0, CTR_COUNT * sizeof(unsigned long long), t->stream));
+    t->err.clear();
+    return TSXC_OK;
+}
+
+void* tsxc_stream(tsxc_table* t) { return t ? (void*)t->stream : nullptr; }
+
+int tsxc_add_reads_device(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint64_t n_reads,
+                          uint64_t n_bases) {
+    if (!t || (!d_packed && n_bases) || !d_offsets) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    const uint64_t n_words = (n_bases + 31) >> 5;
+    int rc = ensure(t, &t->d_ends, &t->cap_ends, (size_t)n_words + 8);
+    if (rc) return rc;
+    return launch_count_reads(t, d_packed, d_offsets, t->d_ends, n_reads, n_bases, t->stream);
+}
+
+int tsxc_add_reads(tsxc_table* t, const uint64_t* packed, const uint64_t* offsets, uint64_t n_reads) {
+    if (!t || !offsets) return fail(t, TSXC_E_INVALID, "null argument");
+    if (n_reads == 0) return TSXC_OK;
+    if (offsets[0] != 0) return fail(t, TSXC_E_INVALID, "offsets[0] must be 0");
+    const uint64_t n_bases = offsets[n_reads];
+    if (n_bases == 0) return TSXC_OK;
+    if (!packed) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    const uint64_t n_words = (n_bases + 31) >> 5;
+    Staging& st = t->stage[t->next_stage];
+    t->next_stage ^= 1;
+    // the slot may still be read by the kernel of two calls ago
+    if (st.used) CU(cudaStreamWaitEvent(t->copy_stream, st.done, 0));
+    int rc;
+    if ((rc = ensure(t, &st.d_packed, &st.cap_packed, (size_t)n_words + 8))) return rc;
+    if ((rc = ensure(t, &st.d_offsets, &st.cap_offsets, (size_t)n_reads + 1))) return rc;
+    if ((rc = ensure(t, &st.d_ends, &st.cap_ends, (size_t)n_words + 8))) return rc;
+    CU(cudaMemcpyAsync(st.d_packed, packed, n_words * sizeof(uint64_t), cudaMemcpyHostToDevice, t->copy_stream));
+    CU(cudaMemcpyAsync(st.d_offsets, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, t->copy_stream));
+    CU(cudaEventRecord(st.copied, t->copy_stream));
+    CU(cudaStreamWaitEvent(t->stream, st.copied, 0));
+    rc = launch_count_reads(t, st.d_packed, st.d_offsets, st.d_ends, n_reads, n_bases, t->stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(st.done, t->stream));
+    st.used = true;
+    return TSXC_OK;
+}
+
+int tsxc_add_kmers_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n) {
+    if (!t || (!d_kmers && n)) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    return add_keys_device(t, d_kmers, n, false);
+}
+
+int tsxc_add_hashes_device(tsxc_table* t, const uint64_t* d_hashes, uint64_t n) {
+    if (!t || (!d_hashes && n)) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    return add_keys_device(t, d_hashes, n, true);
+}
+
+int tsxc_add_kmers(tsxc_table* t, const uint64_t* kmers, uint64_t n) {
+    if (!t || (!kmers && n)) return fail(t, TSXC_E_INVALID, "null argument");
+    if (n == 0) return TSXC_OK;
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    const size_t words = (size_t)n * t->L.KW;
+    // the staging buffer is shared with other calls: order against the compute stream
+    CU(cudaStreamSynchronize(t->stream));
+    int rc = ensure(t, &t->d_keys, &t->cap_keys, words);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(t->d_keys, kmers, words * sizeof(uint64_t), cudaMemcpyHostToDevice, t->stream));
+    return add_keys_device(t, t->d_keys, n, false);
+}
+
+int tsxc_sync(tsxc_table* t) {
+    if (!t) return TSXC_E_INVALID;
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->copy_stream));
+    CU(cudaStreamSynchronize(t->stream));
+    unsigned long long flags = 0;
+    CU(cudaMemcpy(&flags, t->d_ctr + CTR_ERRORS, sizeof flags, cudaMemcpyDeviceToHost));
+    return status_from_flags(t, flags);
+}
+
+int tsxc_lookup_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, uint64_t* d_counts_out) {
+    if (!t || ((!d_kmers || !d_counts_out) && n)) return fail(t, TSXC_E_INVALID, "null argument");
+    if (n == 0) return TSXC_OK;
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    const int grid = grid_for(t, n);
+#define M(KW_, W_) k_lookup<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n, d_counts_out)
+    TSX_DISPATCH(t->L, M);
+#undef M
+    CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
+int tsxc_lookup(tsxc_table* t, const uint64_t* kmers, uint64_t n, uint64_t* counts_out) {
+    if (!t || ((!kmers || !counts_out) && n)) return fail(t, TSXC_E_INVALID, "null argument");
+    if (n == 0) return TSXC_OK;
+    {
+        std::lock_guard<std::mutex> g(t->mu);
+        CU(cudaSetDevice(t->device));
+        CU(cudaStreamSynchronize(t->stream));
+        int rc;
+        if ((rc = ensure(t, &t->d_keys, &t->cap_keys, (size_t)n * t->L.KW))) return rc;
+        if ((rc = ensure(t, &t->d_counts, &t->cap_counts, (size_t)n))) return rc;
+        CU(cudaMemcpyAsync(t->d_keys, kmers, n * t->L.KW * sizeof(uint64_t), cudaMemcpyHostToDevice, t->stream));
+    }
+    int rc = tsxc_lookup_device(t, t->d_keys, n, t->d_counts);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaMemcpyAsync(counts_out, t->d_counts, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    return TSXC_OK;
+}
+
+int tsxc_stats(tsxc_table* t, tsxc_stats_t* out) {
+    if (!t || !out) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->copy_stream));
+    CU(cudaStreamSynchronize(t->stream));
+    unsigned long long c[CTR_COUNT];
+    CU(cudaMemcpy(c, t->d_ctr, sizeof c, cudaMemcpyDeviceToHost));
+    std::memset(out, 0, sizeof *out);
+    const Layout& L = t->L;
+    out->k = L.k; out->l = L.l; out->s = L.s_req;
+    out->key_words = L.KW; out->entry_words = L.W; out->value_bits = L.V; out->quotient_bits = L.Q;
+    out->reprobe_bits = L.R; out->slots_per_bucket = L.SPB;
+    out->n_shards = 1u << L.shard_bits; out->shard_rank = L.shard_rank;
+    out->n_slots = L.n_slots; out->table_bytes = L.table_bytes;
+    out->distinct = c[CTR_DISTINCT]; out->overflow_entries = c[CTR_OVERFLOW];
+    out->used_slots = c[CTR_DISTINCT] + c[CTR_OVERFLOW];
+    out->kmers_added = c[CTR_ADDED]; out->max_reprobe = c[CTR_MAXPROBE]; out->error_flags = c[CTR_ERRORS];
+    return TSXC_OK;
+}
+
+int tsxc_distinct(tsxc_table* t, uint64_t* out) {
+    tsxc_stats_t s;
+    int rc = tsxc_stats(t, &s);
+    if (rc == TSXC_OK && out) *out = s.distinct;
+    return rc;
+}
+
+int tsxc_dump(tsxc_table* t, uint64_t* kmers_out, uint64_t* counts_out, uint64_t capacity, uint64_t* n_out) {
+    if (!t || !n_out || ((!kmers_out || !counts_out) && capacity)) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    uint64_t total = 0;
+    const uint32_t KW = t->L.KW;
+    int rc = dump_chunks(t, [&](const uint64_t* k, const uint64_t* c, uint64_t n) {
+        const uint64_t room = total < capacity ? capacity - total : 0;
+        const uint64_t take = std::min(room, n);
+        if (take) {
+            std::memcpy(kmers_out + total * KW, k, take * KW * sizeof(uint64_t));
+            std::memcpy(counts_out + total, c, take * sizeof(uint64_t));
+        }
+        total += n;
+        return 0;
+    });
+    *n_out = total;
+    if (rc) return rc;
+    if (total > capacity) return fail(t, TSXC_E_INVALID, "dump truncated: capacity too small");
+    return TSXC_OK;
+}
+
+int tsxc_dump_file(tsxc_table* t, const char* path) {
+    if (!t || !path) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(t, TSXC_E_IO, std::string("cannot open ") + path);
+    const uint32_t KW = t->L.KW, k = t->L.k;
+    std::vector<char> buf;
+    int rc = dump_chunks(t, [&](const uint64_t* keys, const uint64_t* cnt, uint64_t n) {
+        static const char LUT[4] = {'A', 'C', 'G', 'T'};  // SequenceUtils.h:65-75
+        buf.clear();
+        buf.reserve((size_t)n * (k + 22));
+        char num[24];
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t* kw = keys + i * KW;
+            for (uint32_t b = 0; b < k; ++b) buf.push_back(LUT[(kw[(2 * b) >> 6] >> ((2 * b) & 63)) & 3]);
+            buf.push_back('\t');
+            int len = std::snprintf(num, sizeof num, "%llu\n", (unsigned long long)cnt[i]);
+            buf.insert(buf.end(), num, num + len);
+        }
+        return std::fwrite(buf.data(), 1, buf.size(), f) == buf.size() ? 0 : (int)TSXC_E_IO;
+    });
+    if (std::fclose(f) != 0 && rc == TSXC_OK) rc = TSXC_E_IO;
+    if (rc == TSXC_E_IO) return fail(t, rc, "write failed");
+    return rc;
+}
+
+int tsxc_route_reads_device(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint64_t n_reads,
+                            uint64_t n_bases, uint64_t* d_send, uint64_t capacity_per_shard,
+                            unsigned long long* d_send_counts) {
+    if (!t || !d_offsets || !d_send || !d_send_counts || (!d_packed && n_bases)) return fail(t, TSXC_E_INVALID, "null argument");
+    if (n_bases == 0 || n_reads == 0) return TSXC_OK;
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    const uint64_t n_words = (n_bases + 31) >> 5;
+    int rc = ensure(t, &t->d_ends, &t->cap_ends, (size_t)n_words + 8);
+    if (rc) return rc;
+    cudaStream_t s = t->stream;
+    CU(cudaMemsetAsync(t->d_ends, 0, n_words * sizeof(uint32_t), s));
+    k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, t->d_ends);
+    const int grid = grid_for(t, n_words);
+    switch (t->L.KW) {
+        case 1: k_route_reads<1, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, t->d_ends, n_words, n_bases, d_send, capacity_per_shard, d_send_counts); break;
+        case 2: k_route_reads<2, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, t->d_ends, n_words, n_bases, d_send, capacity_per_shard, d_send_counts); break;
+        default: k_route_reads<4, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, t->d_ends, n_words, n_bases, d_send, capacity_per_shard, d_send_counts); break;
+    }
+    CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
+int tsxc_gen_reads_device(const tsxc_gen_params* p, uint64_t first, uint64_t count, int device, void* stream,
+                          uint64_t* d_packed, uint64_t* d_offsets) {
+    tsxc_table* t = nullptr;
+    if (!p || !d_packed || !d_offsets || p->read_len == 0) return fail(t, TSXC_E_INVALID, "null argument");
+    if (p->mode > 3) return fail(t, TSXC_E_INVALID, "unknown generator mode");
+    GenParams gp{};
+    gp.seed = p->seed; gp.n_reads = p->n_reads; gp.read_len = p->read_len; gp.mode = p->mode;
+    gp.genome_len = p->genome_len; gp.sub_rate_q16 = p->sub_rate_q16;
+    if (p->mode == 2) {
+        while ((1ULL << gp.dict_log2) < p->genome_len) ++gp.dict_log2;
+        if ((1ULL << gp.dict_log2) != p->genome_len || gp.dict_log2 == 0) return fail(t, TSXC_E_INVALID, "dictionary size must be a power of two > 1");
+    }
+    if (p->mode == 3 && p->genome_len < p->read_len) return fail(t, TSXC_E_INVALID, "genome shorter than a read");
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const uint64_t n_words = (count * p->read_len + 31) >> 5;
+    const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((std::max(n_words, count + 1) + 255) / 256, (uint64_t)sms * 16));
+    k_gen_reads<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(gp, first, count, d_packed, d_offsets);
+    CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
+int tsxc_host_alloc(uint64_t bytes, void** out) {
+    tsxc_table* t = nullptr;
+    if (!out) return TSXC_E_INVALID;
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return TSXC_OK;
+}
+int tsxc_host_free(void* p) {
+    tsxc_table* t = nullptr;
+    if (p) CU(cudaFreeHost(p));
+    return TSXC_OK;
+}
+int tsxc_device_alloc(int device, uint64_t bytes, void** out) {
+    tsxc_table* t = nullptr;
+    if (!out) return TSXC_E_INVALID;
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(out, bytes ? bytes : 1));
+    return TSXC_OK;
+}
+int tsxc_device_free(int device, void* p) {
+    tsxc_table* t = nullptr;
+    CU(cudaSetDevice(device));
+    if (p) CU(cudaFree(p));
+    return TSXC_OK;
+}
+int tsxc_memcpy(int device, void* dst, const void* src, uint64_t bytes, int kind) {
+    tsxc_table* t = nullptr;
+    if (kind < 1 || kind > 3) return TSXC_E_INVALID;
+    CU(cudaSetDevice(device));
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : (kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    CU(cudaMemcpy(dst, src, bytes, k));
+    return TSXC_OK;
+}
+
+int tsxc_k0_random_rmw(tsxc_table* t, uint64_t table_bytes, uint64_t n_ops, int mode, float* ms_out) {
+    if (!t || !ms_out) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    uint64_t bytes = std::min<uint64_t>(table_bytes, t->L.table_bytes);
+    uint64_t words = 32;
+    while (words * 2 * 8 <= bytes) words *= 2;  // power of two
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, t->stream));
+    k_k0_random_rmw<<<t->sms * 8, kBlockThreads, 0, t->stream>>>(t->d_words, words - 1, n_ops, mode);
+    CU(cudaEventRecord(b, t->stream));
+    CU(cudaEventSynchronize(b));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(ms_out, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return TSXC_OK;
+}
+
+int tsxc_debug_hash(uint32_t k, const uint64_t* key, uint64_t* out) {
+    const uint32_t KW = tsxc_key_words(k);
+    if (!KW || !key || !out) return TSXC_E_INVALID;
+    const HashParams hp = make_hash_params(k);
+    if (KW == 1) { Key<1> x{{key[0]}}; auto h = hash_key<1>(x, hp); out[0] = h.w[0]; }
+    else if (KW == 2) { Key<2> x{{key[0], key[1]}}; auto h = hash_key<2>(x, hp); out[0] = h.w[0]; out[1] = h.w[1]; }
+    else { Key<4> x{{key[0], key[1], key[2], key[3]}}; auto h = hash_key<4>(x, hp); for (int j = 0; j < 4; ++j) out[j] = h.w[j]; }
+    return TSXC_OK;
+}
+
+int tsxc_debug_unhash(uint32_t k, const uint64_t* hash, uint64_t* out) {
+    const uint32_t KW = tsxc_key_words(k);
+    if (!KW || !hash || !out) return TSXC_E_INVALID;
+    const HashParams hp = make_hash_params(k);
+    if (KW == 1) { Key<1> x{{hash[0]}}; auto h = unhash_key<1>(x, hp); out[0] = h.w[0]; }
+    else if (KW == 2) { Key<2> x{{hash[0], hash[1]}}; auto h = unhash_key<2>(x, hp); out[0] = h.w[0]; out[1] = h.w[1]; }
+    else { Key<4> x{{hash[0], hash[1], hash[2], hash[3]}}; auto h = unhash_key<4>(x, hp); for (int j = 0; j < 4; ++j) out[j] = h.w[j]; }
+    return TSXC_OK;
+}
+
+int tsxc_debug_layout(uint32_t k, uint32_t l, uint32_t s, uint32_t flags, uint32_t n_shards, tsxc_stats_t* out) {
+    if (!out) return TSXC_E_INVALID;
+    if (k < 1 || k > TSXC_MAX_K || 2 * k <= l) return TSXC_E_INVALID;
+    Layout L;
+    if (!make_layout(k, l, s, flags, 0, n_shards ? n_shards : 1, &L)) return TSXC_E_UNSUPPORTED;
+    std::memset(out, 0, sizeof *out);
+    out->k = k; out->l = l; out->s = s;
+    out->key_words = L.KW; out->entry_words = L.W; out->value_bits = L.V; out->quotient_bits = L.Q;
+    out->reprobe_bits = L.R; out->slots_per_bucket = L.SPB; out->n_shards = 1u << L.shard_bits;
+    out->n_slots = L.n_slots; out->table_bytes = L.table_bytes;
+    return TSXC_OK;
+}
+
+}  // extern "C"

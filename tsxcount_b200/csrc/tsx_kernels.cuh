@@ -1,0 +1,319 @@
+// tsx_kernels.cuh — the sm_100a kernels of the counting path.
+//
+//   K1+K2  k_count_reads    packed reads -> forward k-mers -> hash -> insert (fused; no k-mer array in HBM)
+//   K2     k_add_kmers      batched addKmer on explicit k-mers / on pre-hashed k-mers
+//   K4     k_lookup         batched getKmerCount(kmer)
+//   K5     k_dump           table scan -> (k-mer, count) via the inverse hash
+//   K6     k_route_reads    extraction + hash + binning by owning shard (multi-GPU send side)
+//          k_mark_ends      read offsets -> "last base of a read" bitmap
+//
+// Reference semantics (paths relative to mjoppich/tsxCount):
+//   extraction  src/mains/testExecution.h:15-36   every forward substring seq[i:i+k]; none if len < k
+//   encoding    src/utils/SequenceUtils.h:86-123  base i -> bits [2i,2i+1]: a k-mer is a contiguous
+//               2k-bit window of the 2-bit packed read stream, so extraction is a funnel shift
+//   driver      src/mains/main.cpp:159-192        per read: createKMers -> fromSequence -> addKmer
+#pragma once
+
+#include <cstdint>
+
+#include "tsx_table.cuh"
+
+namespace tsx {
+
+constexpr int kBlockThreads = 256;
+
+// ---- read-boundary bitmap ---------------------------------------------------------------------
+// bit g of `ends` is set iff base g is the last base of a read.  A k-mer starting at g is valid iff
+// no end bit lies in [g, g+k-2] (it may end exactly on a boundary) and g+k <= n_bases.
+__global__ void __launch_bounds__(kBlockThreads) k_mark_ends(const uint64_t* __restrict__ offsets, uint64_t n_reads,
+                                                             uint32_t* __restrict__ ends) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        const uint64_t b = offsets[r], e = offsets[r + 1];
+        if (e > b) atomicOr(ends + ((e - 1) >> 5), 1u << ((e - 1) & 31));
+    }
+}
+
+// ---- warp-level window loader -----------------------------------------------------------------
+// Lane `lane` of a warp owns stream word base+lane; it needs NEXT further words to cover k-mers that
+// start in its word.  One coalesced load per lane plus NEXT tail words loaded by the first lanes;
+// neighbours come from shuffles instead of re-reading global memory.
+template <int NEXT, typename T>
+__device__ __forceinline__ void load_window(const T* __restrict__ src, uint64_t base, uint64_t n_words, unsigned lane,
+                                            T (&win)[NEXT + 1]) {
+    const unsigned full = 0xffffffffu;
+    const uint64_t t = base + lane;
+    const T cur = t < n_words ? __ldg(src + t) : T(0);
+    T tail = T(0);
+    if (lane < NEXT) {
+        const uint64_t u = base + 32 + lane;
+        tail = u < n_words ? __ldg(src + u) : T(0);
+    }
+    win[0] = cur;
+#pragma unroll
+    for (int j = 1; j <= NEXT; ++j) {
+        const T a = __shfl_down_sync(full, cur, j);
+        const T b = __shfl_sync(full, tail, (lane + j) & 31);
+        win[j] = (lane + j < 32) ? a : b;
+    }
+}
+
+// Enumerates the k-mers that start in one 32-base stream word and hands groups of identical k-mers
+// to `sink(key, count)` on one lane per group.
+//   - thread-local run aggregation: consecutive identical k-mers (homopolymer runs) are merged;
+//   - warp pre-aggregation: lanes holding the same k-mer in the same step are merged with
+//     __match_any_sync / __reduce_add_sync so a heavy hitter costs one table update per warp step.
+template <int KW, bool WARP_AGG, typename Sink>
+__device__ __forceinline__ void for_each_kmer_group(const uint64_t (&win)[KW + 1], uint32_t ends_cur, uint32_t dist_after,
+                                                    uint64_t word_index, uint64_t n_bases, uint32_t k,
+                                                    const HashParams& hp, Sink&& sink) {
+    const unsigned full = 0xffffffffu;
+    const uint64_t g0 = word_index << 5;
+    uint32_t dist = dist_after;  // distance from position g0+32 to the next read end at/after it
+    Key<KW> pend;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) pend.w[j] = 0;
+    uint32_t pend_cnt = 0;
+
+    for (int o = 31; o >= -1; --o) {
+        bool valid = false;
+        Key<KW> key;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) key.w[j] = 0;
+        if (o >= 0) {
+            dist = ((ends_cur >> o) & 1u) ? 0u : (dist == 0xffffffffu ? dist : dist + 1u);
+            valid = (dist >= k - 1) && (g0 + (uint64_t)o + k <= n_bases);
+            if (valid) {
+                const unsigned sh = 2u * (unsigned)o;
+#pragma unroll
+                for (int j = 0; j < KW; ++j) {
+                    key.w[j] = sh ? ((win[j] >> sh) | (win[j + 1] << (64 - sh))) : win[j];
+                }
+#pragma unroll
+                for (int j = 0; j < KW; ++j) key.w[j] &= word_mask<KW>(j, hp);
+            }
+        }
+        // run aggregation: emit the pending k-mer when the new one differs (or at the end, o == -1)
+        bool emit = false;
+        Key<KW> ekey = pend;
+        uint32_t ecnt = pend_cnt;
+        if (valid && pend_cnt && key_eq<KW>(key, pend)) {
+            ++pend_cnt;
+        } else {
+            emit = pend_cnt != 0;
+            pend = key;
+            pend_cnt = valid ? 1u : 0u;
+        }
+        const unsigned emask = __ballot_sync(full, emit);
+        if (emask == 0) continue;
+        if (emit) {
+            if (WARP_AGG) {
+                unsigned peers = __match_any_sync(emask, ekey.w[0]);
+#pragma unroll
+                for (int j = 1; j < KW; ++j) peers &= __match_any_sync(emask, ekey.w[j]);
+                const uint32_t total = __reduce_add_sync(peers, ecnt);
+                if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u)) sink(ekey, (uint64_t)total);
+            } else {
+                sink(ekey, (uint64_t)ecnt);
+            }
+        }
+    }
+}
+
+// distance from the first position after the lane's word to the next read end (0xffffffff: none in view)
+template <int NE>
+__device__ __forceinline__ uint32_t first_end_after(const uint32_t (&ewin)[NE + 1]) {
+    uint32_t d = 0xffffffffu;
+#pragma unroll
+    for (int j = NE; j >= 1; --j)
+        if (ewin[j]) d = 32u * (uint32_t)(j - 1) + (uint32_t)(__ffs(ewin[j]) - 1);
+    return d;
+}
+
+// ---- K1+K2 fused: count every k-mer of a packed read batch -------------------------------------
+template <int KW, int W, bool WARP_AGG>
+__global__ void __launch_bounds__(kBlockThreads) k_count_reads(const __grid_constant__ TableView tv, const uint64_t* __restrict__ packed,
+                                                               const uint32_t* __restrict__ ends, uint64_t n_words,
+                                                               uint64_t n_bases) {
+    constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);  // end-bitmap words of look-ahead: ceil((k-1)/32)
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    LocalStats st;
+    for (uint64_t base = warp * 32; base < n_words; base += n_warps * 32) {
+        uint64_t win[KW + 1];
+        uint32_t ewin[NE + 1];
+        load_window<KW, uint64_t>(packed, base, n_words, lane, win);
+        load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
+        const uint32_t dist_after = first_end_after<NE>(ewin);
+        for_each_kmer_group<KW, WARP_AGG>(win, ewin[0], dist_after, base + lane, n_bases, tv.L.k, tv.hp,
+                                          [&](const Key<KW>& key, uint64_t cnt) {
+                                              insert_hashed<KW, W>(tv, hash_key<KW>(key, tv.hp), cnt, st);
+                                          });
+    }
+    flush_stats(tv, st);
+}
+
+// ---- K2: batched addKmer -----------------------------------------------------------------------
+template <int KW, int W, bool HASHED, bool WARP_AGG>
+__global__ void __launch_bounds__(kBlockThreads) k_add_kmers(const __grid_constant__ TableView tv, const uint64_t* __restrict__ kmers, uint64_t n) {
+    const unsigned full = 0xffffffffu;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    LocalStats st;
+    const uint64_t n_round = (n + 31) & ~31ULL;  // keep warps converged for the collectives
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < n;
+        Key<KW> key;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) key.w[j] = valid ? __ldg(kmers + i * KW + j) : 0ULL;
+        const unsigned vmask = __ballot_sync(full, valid);
+        if (!valid) continue;
+        uint64_t cnt = 1;
+        bool lead = true;
+        if (WARP_AGG) {
+            unsigned peers = __match_any_sync(vmask, key.w[0]);
+#pragma unroll
+            for (int j = 1; j < KW; ++j) peers &= __match_any_sync(vmask, key.w[j]);
+            cnt = (uint64_t)__popc(peers);
+            lead = (unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u);
+        }
+        if (lead) {
+            if (!HASHED) {
+#pragma unroll
+                for (int j = 0; j < KW; ++j) key.w[j] &= word_mask<KW>(j, tv.hp);
+                insert_hashed<KW, W>(tv, hash_key<KW>(key, tv.hp), cnt, st);
+            } else {
+                insert_hashed<KW, W>(tv, key, cnt, st);
+            }
+        }
+    }
+    flush_stats(tv, st);
+}
+
+// ---- K4: batched lookup ------------------------------------------------------------------------
+template <int KW, int W>
+__global__ void __launch_bounds__(kBlockThreads) k_lookup(const __grid_constant__ TableView tv, const uint64_t* __restrict__ kmers, uint64_t n,
+                                                          uint64_t* __restrict__ counts) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Key<KW> key;
+        bool in_range = true;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+            key.w[j] = __ldg(kmers + i * KW + j);
+            const uint64_t m = word_mask<KW>(j, tv.hp);
+            in_range &= (key.w[j] & ~m) == 0;
+        }
+        counts[i] = in_range ? lookup_hashed<KW, W>(tv, hash_key<KW>(key, tv.hp)) : 0ULL;
+    }
+}
+
+// ---- K5: dump ----------------------------------------------------------------------------------
+// Scans buckets [b0, b1); every primary entry yields (k-mer, count).  Output positions are claimed
+// with one atomicAdd per warp.
+template <int KW, int W>
+__global__ void __launch_bounds__(kBlockThreads) k_dump(const __grid_constant__ TableView tv, uint64_t b0, uint64_t b1, uint64_t* __restrict__ kmers_out,
+                                                        uint64_t* __restrict__ counts_out, uint64_t capacity,
+                                                        unsigned long long* __restrict__ n_out) {
+    constexpr int SPB = 4 / W;
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_slots = (b1 - b0) * SPB;
+    const uint64_t n_round = (n_slots + 31) & ~31ULL;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool found = false;
+        Key<KW> key;
+        uint64_t cnt = 0;
+        if (i < n_slots) {
+            const uint64_t bucket = b0 + i / SPB;
+            const uint32_t sl = (uint32_t)(i % SPB);
+            const uint64_t* ep = tv.words + (bucket << 2) + sl * W;
+            uint64_t e[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) e[j] = __ldcg(ep + j);
+            const uint64_t h = e[W - 1];
+            if (h != 0 && !(h & tv.f_ovf)) {
+                found = true;
+                const Key<KW> H = hash_of_entry<KW, W>(tv, bucket, e);
+                key = unhash_key<KW>(H, tv.hp);
+                cnt = h >> tv.vshift;
+                if (h & tv.f_hasovf) {
+                    const uint32_t pi = (uint32_t)(h & tv.rmask);
+                    const uint64_t home = (bucket - tri(pi)) & tv.lbl_mask;
+                    cnt += overflow_lookup<KW, W>(tv, home, pi, sl) << tv.L.V;
+                }
+            }
+        }
+        const unsigned fm = __ballot_sync(full, found);
+        if (fm == 0) continue;
+        unsigned long long basepos = 0;
+        if (lane == (unsigned)(__ffs(fm) - 1)) basepos = atomicAdd(n_out, (unsigned long long)__popc(fm));
+        basepos = __shfl_sync(full, basepos, __ffs(fm) - 1);
+        if (found) {
+            const uint64_t pos = basepos + __popc(fm & ((1u << lane) - 1u));
+            if (pos < capacity) {
+#pragma unroll
+                for (int j = 0; j < KW; ++j) kmers_out[pos * KW + j] = key.w[j];
+                counts_out[pos] = cnt;
+            }
+        }
+    }
+}
+
+// ---- K6: route k-mers to their owning shard (multi-GPU send side) -------------------------------
+// Same extraction as k_count_reads; instead of inserting, the HASH of every k-mer occurrence (KW words;
+// the hash is bijective, so the receiver needs nothing else) is appended to the send buffer of the shard
+// that owns its bucket.  Homopolymer runs merged by the extractor are expanded again: the receiver
+// re-aggregates per warp while inserting.
+template <int KW, bool WARP_AGG>
+__global__ void __launch_bounds__(kBlockThreads) k_route_reads(const __grid_constant__ TableView tv, const uint64_t* __restrict__ packed,
+                                                               const uint32_t* __restrict__ ends, uint64_t n_words,
+                                                               uint64_t n_bases, uint64_t* __restrict__ send,
+                                                               uint64_t capacity, unsigned long long* __restrict__ send_counts) {
+    constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t errors = 0;
+    for (uint64_t base = warp * 32; base < n_words; base += n_warps * 32) {
+        uint64_t win[KW + 1];
+        uint32_t ewin[NE + 1];
+        load_window<KW, uint64_t>(packed, base, n_words, lane, win);
+        load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
+        const uint32_t dist_after = first_end_after<NE>(ewin);
+        for_each_kmer_group<KW, false>(win, ewin[0], dist_after, base + lane, n_bases, tv.L.k, tv.hp,
+                                       [&](const Key<KW>& key, uint64_t cnt) {
+                                           const Key<KW> H = hash_key<KW>(key, tv.hp);
+                                           const uint32_t owner = (uint32_t)((H.w[0] & tv.lbg_mask) >> tv.L.LBl);
+                                           const unsigned long long at = atomicAdd(send_counts + owner, (unsigned long long)cnt);
+                                           if (at + cnt > capacity) { errors |= ERR_SEND_OVERFLOW; return; }
+                                           uint64_t* dst = send + ((uint64_t)owner * capacity + at) * KW;
+                                           for (uint64_t c = 0; c < cnt; ++c)
+#pragma unroll
+                                               for (int j = 0; j < KW; ++j) dst[c * KW + j] = H.w[j];
+                                       });
+    }
+    if (errors) atomicOr(tv.ctr + CTR_ERRORS, (unsigned long long)errors);
+}
+
+// ---- K0: random 8-byte RMW roofline ------------------------------------------------------------
+__global__ void __launch_bounds__(kBlockThreads) k_k0_random_rmw(uint64_t* __restrict__ words, uint64_t n_words_mask,
+                                                                 uint64_t n_ops, int mode) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ops; i += stride) {
+        const uint64_t a = fmix64(i * kC1 + 0x1234567ULL) & n_words_mask;
+        if (mode == 0) {
+            atomicAdd((unsigned long long*)(words + a), 1ULL);            // RED, fire and forget
+        } else if (mode == 1) {
+            atomicCAS((unsigned long long*)(words + a), 0ULL, i | 1ULL);  // CAS with return
+        } else {
+            uint64_t w[4];
+            load_bucket(words + (a & ~3ULL), w);                          // sector load, then atomic on it
+            const uint64_t pick = (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x5a5a5a5a5a5a5a5aULL ? 1 : 0;
+            atomicAdd((unsigned long long*)(words + ((a & ~3ULL) | ((a + pick) & 3ULL))), 1ULL << 40);
+        }
+    }
+}
+
+}  // namespace tsx
