@@ -78,6 +78,9 @@ typedef struct tsxc_stats_t {
     uint64_t kmers_added;         /* sum of all increments accepted */
     uint64_t max_reprobe;         /* longest probe sequence seen by an insert */
     uint64_t error_flags;         /* sticky device-side error bits */
+    uint64_t kernel_launches;     /* kernels of this library launched on the handle since create/clear */
+    uint64_t main_kernel_launches;/* launches of the dominant (extract+insert / insert) kernels among them */
+    double   main_kernel_ms;      /* their summed device time (CUDA events on the handle's stream) */
 } tsxc_stats_t;
 
 /* Words per k-mer for this k: 1 (k<=32), 2 (k<=64), 4 (k<=128); 0 if k is out of range. */
@@ -105,6 +108,11 @@ int tsxc_destroy(tsxc_table* t);
 int tsxc_clear(tsxc_table* t);
 /* The CUDA stream (cudaStream_t) the handle queues work on, as an opaque pointer. */
 void* tsxc_stream(tsxc_table* t);
+
+/* Timing marks: record CUDA event `idx` (0..7) on the handle's stream / elapsed device time between two
+ * recorded marks after a tsxc_sync().  This is how bench.py times a step on the launching stream. */
+int tsxc_mark(tsxc_table* t, int idx);
+int tsxc_mark_elapsed_ms(tsxc_table* t, int idx_from, int idx_to, float* ms_out);
 
 /* ---- insert path ------------------------------------------------------------------------- */
 /* createKMers + fromSequence + addKmer for a whole batch of reads — main.cpp:159-192,
@@ -185,6 +193,12 @@ int tsxc_memcpy(int device, void* dst, const void* src, uint64_t bytes, int kind
  * atomicAdd on one of its words) on a scratch region of table_bytes in the handle's table memory
  * (contents are destroyed — call tsxc_clear afterwards).  Returns elapsed device milliseconds. */
 int tsxc_k0_random_rmw(tsxc_table* t, uint64_t table_bytes, uint64_t n_ops, int mode, float* ms_out);
+
+/* K0w: the same with every thread block confined to its own window of the footprint (disjoint windows while
+ * blocks*window <= footprint); separates address-translation reach from the DRAM random-access rate.
+ * mode 0 atomicAdd, 2 sector load + atomicAdd, 3 sector load only. */
+int tsxc_k0_windowed(tsxc_table* t, uint64_t footprint_bytes, uint64_t window_bytes, uint64_t n_ops, int mode,
+                     int blocks, int threads, float* ms_out);
 
 /* ---- debugging / tests ------------------------------------------------------------------- */
 /* The bijective hash and its inverse on the host (round-trip property of TSXHashMap::testHashFunction,

@@ -36,12 +36,16 @@ REFDATA = "/root/reference/data/small_t7.1000.fastq"
 # name, generator (mode, seed, n_reads, read_len, genome_len, sub_q16) or None for the bundled file,
 # k, l, s, [(mode, threads)...].  Domain limits of the reference binary: SURVEY.md §0.5 / §8(c).
 CASES = [
+    # the reference runs at ~300 k-mers/s/thread at k=31 and slower at k=63 (O(k^2) hash on heap big-ints),
+    # so the synthetic pins are a few 10^4 k-mers each
     ("c1_bundled_k14", None, 14, 26, 4, [("SERIAL", 1), ("OMP", 8)]),
-    ("c2_uniform_k31", (0, 0xC2, 1500, 150, 0, 0), 31, 22, 4, [("SERIAL", 1), ("OMP", 8)]),
-    ("c2_fakeseq_k31", (1, 0xC2, 1500, 150, 0, 0), 31, 22, 4, [("SERIAL", 1), ("OMP", 8)]),
-    ("c5_genome_k31", (3, 0xC5, 3000, 150, 20000, 328), 31, 22, 4, [("OMP", 8)]),
-    ("c3_flat_k63", (0, 0xC3, 800, 150, 0, 0), 63, 20, 4, [("SERIAL", 1), ("OMP", 8)]),
-    ("short_reads_k20", (0, 0x51, 4000, 24, 0, 0), 20, 18, 4, [("OMP", 8)]),
+    ("c2_uniform_k31", (0, 0xC2, 400, 150, 0, 0), 31, 22, 4, [("SERIAL", 1), ("OMP", 8)]),
+    # heavy-hitter poly-A k-mer with an overflow entry: SERIAL pins it; the reference's own OMP mode miscounts
+    # that k-mer under contention (total errors 1 at 8 threads) and is recorded for information only
+    ("c2_fakeseq_k31", (1, 0xC2, 300, 150, 0, 0), 31, 22, 4, [("SERIAL", 1), ("OMP", 8, "info")]),
+    ("c5_genome_k31", (3, 0xC5, 400, 150, 3000, 328), 31, 22, 4, [("OMP", 8)]),
+    ("c3_flat_k63", (0, 0xC3, 120, 150, 0, 0), 63, 20, 4, [("OMP", 8)]),
+    ("short_reads_k20", (0, 0x51, 1500, 24, 0, 0), 20, 18, 4, [("OMP", 8)]),
 ]
 
 
@@ -57,7 +61,7 @@ def run_ref(fastq, k, l, s, mode, threads):
     cmd = [REFBIN, f"--input={fastq}", f"--k={k}", f"--l={l}", f"--s={s}", f"--mode={mode}",
            f"--threads={threads}", "--check"]
     for attempt in range(4):  # the reference occasionally segfaults at start-up
-        p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=3000)
         if p.returncode == 0:
             break
     out = p.stdout
@@ -100,13 +104,15 @@ def main():
             if gen is None:
                 case["oracle_dump_identical_to_bundled_count"] = (
                     open(count, "rb").read() == open(REFDATA + f".{k}.count", "rb").read())
-            for mode, threads in runs:
+            for run in runs:
+                mode, threads = run[0], run[1]
                 r = run_ref(fastq, k, l, s, mode, threads)
+                r["informational"] = len(run) > 2
                 r["pinned"] = (r["returncode"] == 0 and r["total_errors"] == 0 and r["xor_kmer_count"] == 0
                                and r["reference_kmer_count"] == distinct and r["tsxcount_kmer_count"] == distinct)
                 print(name, r)
                 case["runs"].append(r)
-            case["pinned"] = all(r["pinned"] for r in case["runs"])
+            case["pinned"] = all(r["pinned"] for r in case["runs"] if not r["informational"])
             pins["cases"].append(case)
             # fixtures: FASTQ + count dump, gzip'ed
             for src in (fastq, count):

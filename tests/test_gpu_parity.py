@@ -109,7 +109,7 @@ CASES = [
     ("k128_fakeseq", dict(mode=1, seed=14), 1500, 150, 128, 17, 4, 0),
     ("c5_genome_k31", dict(mode=3, seed=0xC5, genome_len=50000, sub_rate_q16=328), 8000, 150, 31, 21, 4, 0),
     ("k14_genome_exact_s2", dict(mode=3, seed=15, genome_len=3000, sub_rate_q16=100), 4000, 100, 14, 16, 2, 1),
-    ("k5_tiny", dict(mode=0, seed=16), 500, 40, 5, 8, 3, 1),
+    ("k5_tiny", dict(mode=3, seed=16, genome_len=150), 500, 40, 5, 9, 3, 1),
 ]
 
 

@@ -39,6 +39,8 @@ def test_reference_binary_pins_are_green_and_fixtures_unchanged(tmp_path):
     for case in pins["cases"]:
         assert case["pinned"], case["name"]
         for r in case["runs"]:
+            if r.get("informational"):
+                continue
             assert r["total_errors"] == 0 and r["xor_kmer_count"] == 0
             assert r["reference_kmer_count"] == case["oracle_distinct"] == r["tsxcount_kmer_count"]
         # the committed fixtures are the files the reference binary saw, and the oracle still

@@ -33,6 +33,7 @@ class TsxcStats(C.Structure):
         ("n_slots", C.c_uint64), ("table_bytes", C.c_uint64), ("distinct", C.c_uint64),
         ("overflow_entries", C.c_uint64), ("used_slots", C.c_uint64), ("kmers_added", C.c_uint64),
         ("max_reprobe", C.c_uint64), ("error_flags", C.c_uint64),
+        ("kernel_launches", C.c_uint64), ("main_kernel_launches", C.c_uint64), ("main_kernel_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -62,6 +63,8 @@ PROTOTYPES = {
     "tsxc_destroy": (C.c_int, [_vp]),
     "tsxc_clear": (C.c_int, [_vp]),
     "tsxc_stream": (_vp, [_vp]),
+    "tsxc_mark": (C.c_int, [_vp, C.c_int]),
+    "tsxc_mark_elapsed_ms": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "tsxc_add_reads": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
     "tsxc_add_reads_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64]),
     "tsxc_add_kmers": (C.c_int, [_vp, _vp, C.c_uint64]),
@@ -78,6 +81,8 @@ PROTOTYPES = {
     "tsxc_pack_reads": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _u64p, _u64p]),
     "tsxc_gen_reads_device": (C.c_int, [C.POINTER(TsxcGenParams), C.c_uint64, C.c_uint64, C.c_int, _vp, _vp, _vp]),
     "tsxc_k0_random_rmw": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
+    "tsxc_k0_windowed": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_float)]),
     "tsxc_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_vp)]),
     "tsxc_host_free": (C.c_int, [_vp]),
     "tsxc_device_alloc": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(_vp)]),

@@ -47,6 +47,11 @@ struct tsxc_table {
     uint64_t* d_keys = nullptr; size_t cap_keys = 0;      // words
     uint64_t* d_counts = nullptr; size_t cap_counts = 0;  // entries
     unsigned long long* d_nout = nullptr;
+    // launch accounting (bench.py's gpu_launches / roofline come from here)
+    uint64_t n_launches = 0, n_main_launches = 0;
+    double main_ms = 0.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+    cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     std::mutex mu;
 };
@@ -56,6 +61,26 @@ namespace {
 int fail(tsxc_table* t, int code, const std::string& msg) {
     if (t) t->err = msg; else g_create_error = msg;
     return code;
+}
+
+// Event pair around a dominant-kernel launch; resolved lazily in collect_main_ms() after a sync.
+bool main_begin(tsxc_table* t, cudaStream_t s, std::pair<cudaEvent_t, cudaEvent_t>* ev) {
+    if (!t->ev_free.empty()) { *ev = t->ev_free.back(); t->ev_free.pop_back(); }
+    else if (cudaEventCreate(&ev->first) != cudaSuccess || cudaEventCreate(&ev->second) != cudaSuccess) return false;
+    return cudaEventRecord(ev->first, s) == cudaSuccess;
+}
+void main_end(tsxc_table* t, cudaStream_t s, const std::pair<cudaEvent_t, cudaEvent_t>& ev) {
+    cudaEventRecord(ev.second, s);
+    t->ev_pending.push_back(ev);
+    t->n_main_launches++;
+}
+void collect_main_ms(tsxc_table* t) {  // caller has synchronized the stream
+    for (auto& ev : t->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) t->main_ms += ms;
+        t->ev_free.push_back(ev);
+    }
+    t->ev_pending.clear();
 }
 
 #define CU(call)                                                                                         \
@@ -106,13 +131,18 @@ int launch_count_reads(tsxc_table* t, const uint64_t* d_packed, const uint64_t* 
     const uint64_t n_words = (n_bases + 31) >> 5;
     CU(cudaMemsetAsync(d_ends, 0, n_words * sizeof(uint32_t), s));
     k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, d_ends);
+    t->n_launches++;
     const int grid = grid_for(t, n_words);
     const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    const bool timed = main_begin(t, s, &ev);
 #define M(KW_, W_)                                                                                                    \
     if (agg) k_count_reads<KW_, W_, true><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, n_words, n_bases);  \
     else k_count_reads<KW_, W_, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, n_words, n_bases)
     TSX_DISPATCH(t->L, M);
 #undef M
+    t->n_launches++;
+    if (timed) main_end(t, s, ev);
     CU(cudaGetLastError());
     return TSXC_OK;
 }
@@ -174,6 +204,8 @@ static int add_keys_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, b
     if (n == 0) return TSXC_OK;
     const int grid = grid_for(t, n);
     const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    const bool timed = main_begin(t, t->stream, &ev);
 #define M(KW_, W_)                                                                                              \
     if (hashed) { if (agg) k_add_kmers<KW_, W_, true, true><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n);  \
                   else k_add_kmers<KW_, W_, true, false><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n); }   \
@@ -181,6 +213,8 @@ static int add_keys_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, b
            else k_add_kmers<KW_, W_, false, false><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n); }
     TSX_DISPATCH(t->L, M);
 #undef M
+    t->n_launches++;
+    if (timed) main_end(t, t->stream, ev);
     CU(cudaGetLastError());
     return TSXC_OK;
 }
@@ -206,6 +240,7 @@ static int dump_chunks(tsxc_table* t, Emit&& emit) {
 #define M(KW_, W_) k_dump<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, b0, b1, t->d_keys, t->d_counts, chunk_slots, t->d_nout)
         TSX_DISPATCH(t->L, M);
 #undef M
+        t->n_launches++;
         CU(cudaGetLastError());
         unsigned long long n = 0;
         CU(cudaMemcpyAsync(&n, t->d_nout, sizeof n, cudaMemcpyDeviceToHost, t->stream));
@@ -273,6 +308,9 @@ int tsxc_destroy(tsxc_table* t) {
         if (st.copied) cudaEventDestroy(st.copied);
         if (st.done) cudaEventDestroy(st.done);
     }
+    for (auto& ev : t->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto& ev : t->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto& m : t->marks) if (m) cudaEventDestroy(m);
     cudaFree(t->d_ends); cudaFree(t->d_keys); cudaFree(t->d_counts); cudaFree(t->d_nout);
     cudaFree(t->d_ctr); cudaFree(t->d_words);
     if (t->stream) cudaStreamDestroy(t->stream);
@@ -288,10 +326,29 @@ int tsxc_clear(tsxc_table* t) {
     CU(cudaMemsetAsync(t->d_words, 0, t->L.table_bytes, t->stream));
     CU(cudaMemsetAsync(t->d_ctr, 0, CTR_COUNT * sizeof(unsigned long long), t->stream));
     t->err.clear();
+    for (auto& ev : t->ev_pending) t->ev_free.push_back(ev);
+    t->ev_pending.clear();
+    t->n_launches = t->n_main_launches = 0; t->main_ms = 0.0;
     return TSXC_OK;
 }
 
 void* tsxc_stream(tsxc_table* t) { return t ? (void*)t->stream : nullptr; }
+
+int tsxc_mark(tsxc_table* t, int idx) {
+    if (!t || idx < 0 || idx >= 8) return fail(t, TSXC_E_INVALID, "bad mark index");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    if (!t->marks[idx]) CU(cudaEventCreate(&t->marks[idx]));
+    CU(cudaEventRecord(t->marks[idx], t->stream));
+    return TSXC_OK;
+}
+
+int tsxc_mark_elapsed_ms(tsxc_table* t, int a, int b, float* ms_out) {
+    if (!t || !ms_out || a < 0 || a >= 8 || b < 0 || b >= 8 || !t->marks[a] || !t->marks[b]) return fail(t, TSXC_E_INVALID, "bad mark index");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaEventElapsedTime(ms_out, t->marks[a], t->marks[b]));
+    return TSXC_OK;
+}
 
 int tsxc_add_reads_device(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint64_t n_reads,
                           uint64_t n_bases) {
@@ -381,6 +438,7 @@ int tsxc_lookup_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, uint6
 #define M(KW_, W_) k_lookup<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n, d_counts_out)
     TSX_DISPATCH(t->L, M);
 #undef M
+    t->n_launches++;
     CU(cudaGetLastError());
     return TSXC_OK;
 }
@@ -423,6 +481,8 @@ int tsxc_stats(tsxc_table* t, tsxc_stats_t* out) {
     out->distinct = c[CTR_DISTINCT]; out->overflow_entries = c[CTR_OVERFLOW];
     out->used_slots = c[CTR_DISTINCT] + c[CTR_OVERFLOW];
     out->kmers_added = c[CTR_ADDED]; out->max_reprobe = c[CTR_MAXPROBE]; out->error_flags = c[CTR_ERRORS];
+    collect_main_ms(t);
+    out->kernel_launches = t->n_launches; out->main_kernel_launches = t->n_main_launches; out->main_kernel_ms = t->main_ms;
     return TSXC_OK;
 }
 
@@ -494,6 +554,7 @@ int tsxc_route_reads_device(tsxc_table* t, const uint64_t* d_packed, const uint6
     CU(cudaMemsetAsync(t->d_ends, 0, n_words * sizeof(uint32_t), s));
     k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, t->d_ends);
     const int grid = grid_for(t, n_words);
+    t->n_launches += 2;
     switch (t->L.KW) {
         case 1: k_route_reads<1, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, t->d_ends, n_words, n_bases, d_send, capacity_per_shard, d_send_counts); break;
         case 2: k_route_reads<2, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, t->d_ends, n_words, n_bases, d_send, capacity_per_shard, d_send_counts); break;
@@ -570,6 +631,26 @@ int tsxc_k0_random_rmw(tsxc_table* t, uint64_t table_bytes, uint64_t n_ops, int 
     CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
     CU(cudaEventRecord(a, t->stream));
     k_k0_random_rmw<<<t->sms * 8, kBlockThreads, 0, t->stream>>>(t->d_words, words - 1, n_ops, mode);
+    CU(cudaEventRecord(b, t->stream));
+    CU(cudaEventSynchronize(b));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(ms_out, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return TSXC_OK;
+}
+
+int tsxc_k0_windowed(tsxc_table* t, uint64_t footprint_bytes, uint64_t window_bytes, uint64_t n_ops, int mode,
+                      int blocks, int threads, float* ms_out) {
+    if (!t || !ms_out || blocks < 1 || threads < 32 || threads > 1024) return fail(t, TSXC_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    uint64_t fw = 32, ww = 32;
+    while (fw * 2 * 8 <= std::min<uint64_t>(footprint_bytes, t->L.table_bytes)) fw *= 2;
+    while (ww * 2 * 8 <= window_bytes && ww * 2 <= fw) ww *= 2;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, t->stream));
+    k_k0_windowed<<<blocks, threads, 0, t->stream>>>(t->d_words, fw, ww, n_ops / blocks, mode);
     CU(cudaEventRecord(b, t->stream));
     CU(cudaEventSynchronize(b));
     CU(cudaGetLastError());

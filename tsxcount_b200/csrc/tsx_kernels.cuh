@@ -301,19 +301,54 @@ __global__ void __launch_bounds__(kBlockThreads) k_route_reads(const __grid_cons
 __global__ void __launch_bounds__(kBlockThreads) k_k0_random_rmw(uint64_t* __restrict__ words, uint64_t n_words_mask,
                                                                  uint64_t n_ops, int mode) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t sink = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ops; i += stride) {
         const uint64_t a = fmix64(i * kC1 + 0x1234567ULL) & n_words_mask;
         if (mode == 0) {
             atomicAdd((unsigned long long*)(words + a), 1ULL);            // RED, fire and forget
         } else if (mode == 1) {
             atomicCAS((unsigned long long*)(words + a), 0ULL, i | 1ULL);  // CAS with return
-        } else {
+        } else if (mode == 2) {
             uint64_t w[4];
             load_bucket(words + (a & ~3ULL), w);                          // sector load, then atomic on it
             const uint64_t pick = (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x5a5a5a5a5a5a5a5aULL ? 1 : 0;
             atomicAdd((unsigned long long*)(words + ((a & ~3ULL) | ((a + pick) & 3ULL))), 1ULL << 40);
+        } else if (mode == 3) {
+            uint64_t w[4];
+            load_bucket(words + (a & ~3ULL), w);                          // random 32-byte sector reads only
+            sink += w[0] ^ w[1] ^ w[2] ^ w[3];
+        } else {
+            __stcg(words + a, i);                                         // random 8-byte stores only
         }
     }
+    if (sink == 0x123456789ULL) words[0] = sink;
+}
+
+// K0w: like K0 but every block confines itself to its own window of the footprint (windows of different
+// blocks are disjoint while grid*window <= footprint).  Separates address-translation reach from DRAM
+// random-access rate: aggregate footprint stays far beyond L2 while each SM touches few pages.
+__global__ void k_k0_windowed(uint64_t* __restrict__ words, uint64_t footprint_words, uint64_t window_words,
+                              uint64_t ops_per_block, int mode) {
+    const uint64_t n_windows = footprint_words / window_words;
+    const uint64_t base = ((uint64_t)blockIdx.x % n_windows) * window_words;
+    const uint64_t wmask = window_words - 1;
+    uint64_t sink = 0;
+    for (uint64_t i = threadIdx.x; i < ops_per_block; i += blockDim.x) {
+        const uint64_t a = base + (fmix64((i + (uint64_t)blockIdx.x * ops_per_block) * kC1 + 0x1234567ULL) & wmask);
+        if (mode == 0) {
+            atomicAdd((unsigned long long*)(words + a), 1ULL);
+        } else if (mode == 3) {
+            uint64_t w[4];
+            load_bucket(words + (a & ~3ULL), w);
+            sink += w[0] ^ w[1] ^ w[2] ^ w[3];
+        } else {
+            uint64_t w[4];
+            load_bucket(words + (a & ~3ULL), w);
+            const uint64_t pick = (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x5a5a5a5a5a5a5a5aULL ? 1 : 0;
+            atomicAdd((unsigned long long*)(words + ((a & ~3ULL) | ((a + pick) & 3ULL))), 1ULL << 40);
+        }
+    }
+    if (sink == 0x123456789ULL) words[0] = sink;
 }
 
 }  // namespace tsx

@@ -59,6 +59,14 @@ class TSXHashMapCUDA:
     def sync(self):
         _lib.check(self._lib.tsxc_sync(self._h), self._h)
 
+    def mark(self, idx):
+        _lib.check(self._lib.tsxc_mark(self._h, idx), self._h)
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_float(0)
+        _lib.check(self._lib.tsxc_mark_elapsed_ms(self._h, a, b, C.byref(ms)), self._h)
+        return ms.value
+
     # -- reference getters (TSXHashMap.h:162-177) -------------------------------------------------
     def getK(self):
         return self.k
