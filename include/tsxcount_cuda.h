@@ -57,6 +57,9 @@ enum {
 #define TSXC_FLAG_EXACT_S 1u
 /* Disable warp-level pre-aggregation (__match_any_sync) — for measurements only. */
 #define TSXC_FLAG_NO_WARP_AGG 2u
+/* Always use the single fused extract+insert kernel, never the two-phase region-partitioned path that
+ * large tables take by default (DESIGN.md "TLB-aware insert") — for A/B measurements. */
+#define TSXC_FLAG_DIRECT 4u
 
 typedef struct tsxc_table tsxc_table; /* opaque */
 
@@ -81,6 +84,8 @@ typedef struct tsxc_stats_t {
     uint64_t kernel_launches;     /* kernels of this library launched on the handle since create/clear */
     uint64_t main_kernel_launches;/* launches of the dominant (extract+insert / insert) kernels among them */
     double   main_kernel_ms;      /* their summed device time (CUDA events on the handle's stream) */
+    double   partition_ms;        /* of which: phase A (extract+hash+bin) of the two-phase path */
+    double   insert_ms;           /* of which: phase B (insert from bins) of the two-phase path */
 } tsxc_stats_t;
 
 /* Words per k-mer for this k: 1 (k<=32), 2 (k<=64), 4 (k<=128); 0 if k is out of range. */

@@ -310,3 +310,63 @@ def test_sharded_route_and_insert(tsx, k, n_shards):
             lib.tsxc_device_free(0, p)
         for hm in shards:
             hm.close()
+
+
+# ---- the region-partitioned (two-phase) insert path -----------------------------------------------------
+@pytest.fixture
+def small_regions(monkeypatch):
+    """Tables larger than one region take the two-phase path; shrink the region so small tables do too."""
+    monkeypatch.setenv("TSXC_REGION_LOG2", "16")
+
+
+PART_CASES = [c for c in CASES if c[0] in (
+    "c2_uniform_k31", "c2_fakeseq_k31_exact_s4", "c2_fakeseq_k31_wide", "k32_small_table_class12", "c3_zipf_k63_exact_s4",
+    "k64_uniform", "k96_fakeseq", "c4_uniform_k127", "c4_zipf_k127_exact_s4", "c5_genome_k31")]
+
+
+@pytest.mark.parametrize("case", PART_CASES, ids=[c[0] for c in PART_CASES])
+def test_partitioned_path_parity(tsx, small_regions, case):
+    name, gen, n_reads, read_len, k, l, s, flags = case
+    seqs = orc.gen_reads(n_reads=n_reads, read_len=read_len, **gen)
+    st, oc = run_case(tsx, seqs, k, l, s, flags)
+    assert st["main_kernel_launches"] >= 2, "expected the partition + insert kernels"
+
+
+def test_partitioned_path_ragged_reads_and_repeats(tsx, small_regions):
+    rng = np.random.default_rng(5)
+    seqs = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(n))) for n in rng.integers(1, 400, size=1500)]
+    seqs += [b"A" * 3000, b"", b"ACGT" * 300]
+    oc = orc.count_seqs(seqs, 31)
+    with tsx.TSXHashMapCUDA(20, 4, 31, flags=tsx.TSXC_FLAG_EXACT_S) as hm:
+        hm.addSequences(seqs)
+        hm.addSequences(seqs)                        # second batch hits existing entries
+        assert hm.stats()["main_kernel_launches"] >= 4
+        assert hm.getKmerCount() == oc.n_distinct
+        assert np.array_equal(hm.getKmerCounts(oc.keys_kw(1)), 2 * oc.counts)
+
+
+def test_direct_flag_forces_single_kernel(tsx, small_regions):
+    seqs = orc.gen_reads(seed=3, n_reads=2000, read_len=150, mode=0)
+    st, oc = run_case(tsx, seqs, 31, 20, 0, flags=4)
+    assert st["main_kernel_launches"] == 1
+
+
+# ---- the committed fixtures the reference binary was run on -----------------------------------------------
+def test_reference_pinned_fixtures(tsx, tmp_path):
+    import json
+    pins = json.load(open(os.path.join(orc.GOLDEN, "ref_binary_pins.json")))
+    for case in pins["cases"]:
+        name, k = case["name"], case["k"]
+        fastq = orc.golden_path(f"{name}.fastq", tmp_path)
+        count = orc.golden_path(f"{name}.fastq.{k}.count", tmp_path)
+        want = {}
+        with open(count) as f:
+            for line in f:
+                kmer, c = line.rstrip("\n").split("\t")
+                want[kmer] = int(c)
+        with tsx.TSXHashMapCUDA(case["l"], case["s"], k, flags=tsx.TSXC_FLAG_EXACT_S) as hm:
+            hm.addFastq(fastq)
+            assert hm.getKmerCount() == case["oracle_distinct"] == len(want)
+            keys, counts = hm.getAllKmers()
+            got = {tsx.sequtils.to_sequence(kk, k): int(c) for kk, c in zip(keys, counts)}
+            assert got == want, name

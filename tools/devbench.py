@@ -64,7 +64,9 @@ def main():
         res.append(ms)
         print(json.dumps({"rep": rep, "ms": round(ms, 3), "gkmers_per_s": round(n_kmers / ms / 1e6, 3),
                           "distinct": st["distinct"], "load": round(st["used_slots"] / st["n_slots"], 4),
-                          "overflow_entries": st["overflow_entries"], "max_reprobe": st["max_reprobe"]}))
+                          "overflow_entries": st["overflow_entries"], "max_reprobe": st["max_reprobe"],
+                          "partition_ms": round(st["partition_ms"], 2), "insert_ms": round(st["insert_ms"], 2),
+                          "launches": st["kernel_launches"]}))
     if args.k0:
         for mode, name in ((0, "red_add"), (1, "cas"), (2, "sector_load+atomic")):
             hm.clear(); hm.sync()

@@ -22,6 +22,7 @@ TSXC_E_TABLE_FULL = 42
 TSXC_FLAG_NONE = 0
 TSXC_FLAG_EXACT_S = 1
 TSXC_FLAG_NO_WARP_AGG = 2
+TSXC_FLAG_DIRECT = 4
 
 
 class TsxcStats(C.Structure):
@@ -34,6 +35,7 @@ class TsxcStats(C.Structure):
         ("overflow_entries", C.c_uint64), ("used_slots", C.c_uint64), ("kmers_added", C.c_uint64),
         ("max_reprobe", C.c_uint64), ("error_flags", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("main_kernel_launches", C.c_uint64), ("main_kernel_ms", C.c_double),
+        ("partition_ms", C.c_double), ("insert_ms", C.c_double),
     ]
 
     def as_dict(self):

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -47,10 +48,17 @@ struct tsxc_table {
     uint64_t* d_keys = nullptr; size_t cap_keys = 0;      // words
     uint64_t* d_counts = nullptr; size_t cap_counts = 0;  // entries
     unsigned long long* d_nout = nullptr;
+    // region-partitioned insert (phase A bins)
+    uint64_t* d_part = nullptr; size_t cap_part = 0;          // words
+    unsigned long long* d_cursor = nullptr;                   // kMaxParts + 1 (last = ticket)
+    uint32_t pbits = 0;                                        // log2(#regions); 0 = direct path only
+    uint32_t region_log2 = 26;
     // launch accounting (bench.py's gpu_launches / roofline come from here)
     uint64_t n_launches = 0, n_main_launches = 0;
     double main_ms = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_part, ev_ins;  // per-phase pairs of the two-phase path
+    double part_ms = 0.0, ins_ms = 0.0;
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     std::mutex mu;
@@ -69,18 +77,23 @@ bool main_begin(tsxc_table* t, cudaStream_t s, std::pair<cudaEvent_t, cudaEvent_
     else if (cudaEventCreate(&ev->first) != cudaSuccess || cudaEventCreate(&ev->second) != cudaSuccess) return false;
     return cudaEventRecord(ev->first, s) == cudaSuccess;
 }
-void main_end(tsxc_table* t, cudaStream_t s, const std::pair<cudaEvent_t, cudaEvent_t>& ev) {
+void main_end(tsxc_table* t, cudaStream_t s, const std::pair<cudaEvent_t, cudaEvent_t>& ev, int launches = 1) {
     cudaEventRecord(ev.second, s);
     t->ev_pending.push_back(ev);
-    t->n_main_launches++;
+    t->n_main_launches += launches;
 }
 void collect_main_ms(tsxc_table* t) {  // caller has synchronized the stream
-    for (auto& ev : t->ev_pending) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) t->main_ms += ms;
-        t->ev_free.push_back(ev);
-    }
-    t->ev_pending.clear();
+    auto drain = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, double& acc) {
+        for (auto& ev : v) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) acc += ms;
+            t->ev_free.push_back(ev);
+        }
+        v.clear();
+    };
+    drain(t->ev_pending, t->main_ms);
+    drain(t->ev_part, t->part_ms);
+    drain(t->ev_ins, t->ins_ms);
 }
 
 #define CU(call)                                                                                         \
@@ -125,6 +138,53 @@ int status_from_flags(tsxc_table* t, uint64_t flags) {
     return TSXC_OK;
 }
 
+// Two-phase path for tables much larger than the per-SM translation reach (see tsx_kernels.cuh).
+int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words,
+                                   uint64_t n_bases, cudaStream_t s) {
+    const Layout& L = t->L;
+    const uint32_t P = 1u << t->pbits;
+    const uint64_t chunk_words = std::min<uint64_t>(n_words, (1ULL << 25) / L.KW);
+    uint64_t cap = (32 * chunk_words / P) + (32 * chunk_words / P) / 8 + 2048;
+    cap = (cap + 7) & ~7ULL;
+    int rc = ensure(t, &t->d_part, &t->cap_part, (size_t)P * cap * L.KW);
+    if (rc) return rc;
+    PartView pv{};
+    pv.buf = t->d_part; pv.cursor = t->d_cursor; pv.cap = cap;
+    pv.pshift = L.LBl - t->pbits; pv.pmask = P - 1; pv.P = P;
+    const uint32_t slices = (uint32_t)((cap + kSliceEntries - 1) / kSliceEntries);
+    const bool agg = !(L.flags & TSXC_FLAG_NO_WARP_AGG);
+    constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    const bool timed = main_begin(t, s, &ev);
+    int main_launches = 0;
+    for (uint64_t w0 = 0; w0 < n_words; w0 += chunk_words) {
+        const uint64_t w1 = std::min(n_words, w0 + chunk_words);
+        CU(cudaMemsetAsync(t->d_cursor, 0, (kMaxParts + 1) * sizeof(unsigned long long), s));
+        const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)t->sms * 4));
+        const int grid_b = t->sms * 8;
+        std::pair<cudaEvent_t, cudaEvent_t> eva, evb;
+        const bool ta = main_begin(t, s, &eva);
+#define M(KW_, W_)                                                                                                         \
+        if (agg) k_partition_reads<KW_, W_, true><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases); \
+        else k_partition_reads<KW_, W_, false><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases)
+        TSX_DISPATCH(t->L, M);
+#undef M
+        if (ta) { cudaEventRecord(eva.second, s); t->ev_part.push_back(eva); }
+        const bool tb = main_begin(t, s, &evb);
+#define M(KW_, W_)                                                                                                         \
+        if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, t->d_cursor + kMaxParts);  \
+        else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, t->d_cursor + kMaxParts)
+        TSX_DISPATCH(t->L, M);
+#undef M
+        if (tb) { cudaEventRecord(evb.second, s); t->ev_ins.push_back(evb); }
+        t->n_launches += 2;
+        main_launches += 2;
+    }
+    if (timed) main_end(t, s, ev, main_launches);
+    CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
 int launch_count_reads(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint32_t* d_ends,
                        uint64_t n_reads, uint64_t n_bases, cudaStream_t s) {
     if (n_bases == 0 || n_reads == 0) return TSXC_OK;
@@ -132,6 +192,9 @@ int launch_count_reads(tsxc_table* t, const uint64_t* d_packed, const uint64_t* 
     CU(cudaMemsetAsync(d_ends, 0, n_words * sizeof(uint32_t), s));
     k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, d_ends);
     t->n_launches++;
+    // the bins pay off once every region receives a few thousand k-mers per chunk
+    if (t->pbits > 0 && !(t->L.flags & TSXC_FLAG_DIRECT) && n_words >= (16ULL << t->pbits))
+        return launch_count_reads_partitioned(t, d_packed, d_ends, n_words, n_bases, s);
     const int grid = grid_for(t, n_words);
     const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -192,6 +255,24 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
             h->err = cudaGetErrorString(e);
             return bail(TSXC_E_CUDA);
         }
+    }
+    if ((e = cudaMalloc(&h->d_cursor, (kMaxParts + 1) * sizeof(unsigned long long))) != cudaSuccess) {
+        h->err = cudaGetErrorString(e);
+        return bail(TSXC_E_NOMEM);
+    }
+    if (const char* env = std::getenv("TSXC_L2_FETCH")) {  // experiment: L2 fetch granularity hint (32/64/128)
+        const int v = std::atoi(env);
+        if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+    }
+    if (const char* env = std::getenv("TSXC_REGION_LOG2")) {
+        const int v = std::atoi(env);
+        if (v >= 16 && v <= 40) h->region_log2 = (uint32_t)v;
+    }
+    {   // regions of 2^region_log2 bytes (default 64 MiB); a bucket is 32 bytes
+        const uint32_t table_log2 = L.LBl + 5;
+        h->pbits = table_log2 > h->region_log2 ? table_log2 - h->region_log2 : 0;
+        if (h->pbits > 12) h->pbits = 12;
+        if (h->pbits > L.LBl) h->pbits = L.LBl;
     }
     h->tv = make_view(L, h->d_words, h->d_ctr);
     int rc = tsxc_clear(h);
@@ -308,9 +389,11 @@ int tsxc_destroy(tsxc_table* t) {
         if (st.copied) cudaEventDestroy(st.copied);
         if (st.done) cudaEventDestroy(st.done);
     }
-    for (auto& ev : t->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto* v : {&t->ev_pending, &t->ev_part, &t->ev_ins})
+        for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& ev : t->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& m : t->marks) if (m) cudaEventDestroy(m);
+    cudaFree(t->d_part); cudaFree(t->d_cursor);
     cudaFree(t->d_ends); cudaFree(t->d_keys); cudaFree(t->d_counts); cudaFree(t->d_nout);
     cudaFree(t->d_ctr); cudaFree(t->d_words);
     if (t->stream) cudaStreamDestroy(t->stream);
@@ -326,9 +409,11 @@ int tsxc_clear(tsxc_table* t) {
     CU(cudaMemsetAsync(t->d_words, 0, t->L.table_bytes, t->stream));
     CU(cudaMemsetAsync(t->d_ctr, 0, CTR_COUNT * sizeof(unsigned long long), t->stream));
     t->err.clear();
-    for (auto& ev : t->ev_pending) t->ev_free.push_back(ev);
-    t->ev_pending.clear();
-    t->n_launches = t->n_main_launches = 0; t->main_ms = 0.0;
+    for (auto* v : {&t->ev_pending, &t->ev_part, &t->ev_ins}) {
+        for (auto& ev : *v) t->ev_free.push_back(ev);
+        v->clear();
+    }
+    t->n_launches = t->n_main_launches = 0; t->main_ms = t->part_ms = t->ins_ms = 0.0;
     return TSXC_OK;
 }
 
@@ -483,6 +568,7 @@ int tsxc_stats(tsxc_table* t, tsxc_stats_t* out) {
     out->kmers_added = c[CTR_ADDED]; out->max_reprobe = c[CTR_MAXPROBE]; out->error_flags = c[CTR_ERRORS];
     collect_main_ms(t);
     out->kernel_launches = t->n_launches; out->main_kernel_launches = t->n_main_launches; out->main_kernel_ms = t->main_ms;
+    out->partition_ms = t->part_ms; out->insert_ms = t->ins_ms;
     return TSXC_OK;
 }
 

@@ -75,6 +75,7 @@ __device__ __forceinline__ void for_each_kmer_group(const uint64_t (&win)[KW + 1
     for (int j = 0; j < KW; ++j) pend.w[j] = 0;
     uint32_t pend_cnt = 0;
 
+#pragma unroll 2
     for (int o = 31; o >= -1; --o) {
         bool valid = false;
         Key<KW> key;
@@ -104,18 +105,21 @@ __device__ __forceinline__ void for_each_kmer_group(const uint64_t (&win)[KW + 1
             pend = key;
             pend_cnt = valid ? 1u : 0u;
         }
-        const unsigned emask = __ballot_sync(full, emit);
-        if (emask == 0) continue;
-        if (emit) {
-            if (WARP_AGG) {
+        if (WARP_AGG) {
+            const unsigned emask = __ballot_sync(full, emit);
+            if (emask == 0) continue;
+            if (emit) {
                 unsigned peers = __match_any_sync(emask, ekey.w[0]);
 #pragma unroll
                 for (int j = 1; j < KW; ++j) peers &= __match_any_sync(emask, ekey.w[j]);
-                const uint32_t total = __reduce_add_sync(peers, ecnt);
+                // singleton groups (the common case) must not enter the reduction: with per-group masks
+                // REDUX is issued once per distinct mask, i.e. 32 times per step for all-distinct k-mers
+                uint32_t total = ecnt;
+                if (peers & (peers - 1)) total = __reduce_add_sync(peers, ecnt);
                 if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u)) sink(ekey, (uint64_t)total);
-            } else {
-                sink(ekey, (uint64_t)ecnt);
             }
+        } else {
+            if (emit) sink(ekey, (uint64_t)ecnt);
         }
     }
 }
@@ -295,6 +299,149 @@ __global__ void __launch_bounds__(kBlockThreads) k_route_reads(const __grid_cons
                                        });
     }
     if (errors) atomicOr(tv.ctr + CTR_ERRORS, (unsigned long long)errors);
+}
+
+// ---- partitioned insert (TLB-aware two-phase path) -----------------------------------------------
+// Measured on B200 (profiles/): uniformly random 8-byte RMWs over a 128 GiB table run at 9.8 G/s and a
+// dependent sector-load + atomic at 4 G/s, but the same accesses confined to a 64 MiB window per thread
+// block run at 19-22 G/s with the SAME aggregate footprint: the limiter of the naive scatter is address
+// translation (per-SM TLB reach), not DRAM.  So large tables are updated in two phases per chunk of reads:
+//   phase A  k_partition_reads   extract + hash, append the hash to the bin of the 64 MiB table region
+//                                that owns its home bucket (streaming writes, 8*KW bytes per k-mer);
+//   phase B  k_insert_partitions thread blocks drain one bin slice at a time, so every block probes
+//                                inside one region (translations stay resident), consecutive blocks
+//                                work on consecutive slices of the same region.
+// k-mer groups that the warp already aggregated (count >= 2: homopolymer runs, heavy hitters) and k-mers
+// whose bin is full bypass the bins and are inserted directly — bins never overflow, nothing is dropped.
+struct PartView {
+    uint64_t* buf;                 // P * cap * KW words
+    unsigned long long* cursor;    // P fill counters (may exceed cap: excess went the direct way)
+    uint64_t cap;                  // entries per bin
+    uint32_t pshift;               // bin = ((global bucket index) >> pshift) & pmask
+    uint32_t pmask;
+    uint32_t P;                    // number of bins
+    uint32_t pad;
+};
+
+constexpr int kPartTileIters = 16;                 // warp iterations per tile: 8 warps * 32 words * 16 = 4096 words
+constexpr int kMaxParts = 4096;
+
+template <int KW, int W, bool WARP_AGG>
+__global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_constant__ TableView tv,
+                                                                   const __grid_constant__ PartView pv,
+                                                                   const uint64_t* __restrict__ packed,
+                                                                   const uint32_t* __restrict__ ends, uint64_t w_begin,
+                                                                   uint64_t w_end, uint64_t n_words, uint64_t n_bases) {
+    constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
+    constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
+    __shared__ unsigned int hist[kMaxParts];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned wib = threadIdx.x >> 5;
+    LocalStats st;
+    for (uint64_t tile = w_begin + (uint64_t)blockIdx.x * kTileWords; tile < w_end; tile += (uint64_t)gridDim.x * kTileWords) {
+        const uint64_t tile_end = tile + kTileWords < w_end ? tile + kTileWords : w_end;
+        for (uint32_t p = threadIdx.x; p < pv.P; p += blockDim.x) hist[p] = 0;
+        __syncthreads();
+        // sweep 1: histogram of the tile's single k-mers over the bins
+        for (uint64_t base = tile + wib * 32; base < tile_end; base += (kBlockThreads / 32) * 32) {
+            uint64_t win[KW + 1];
+            uint32_t ewin[NE + 1];
+            load_window<KW, uint64_t>(packed, base, n_words, lane, win);
+            load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
+            const uint32_t active = (base + lane < tile_end) ? ewin[0] : 0u;
+            const uint64_t limit = (base + lane < tile_end) ? n_bases : 0;  // lanes past the chunk emit nothing
+            for_each_kmer_group<KW, false>(win, active, first_end_after<NE>(ewin), base + lane, limit, tv.L.k, tv.hp,
+                                              [&](const Key<KW>& key, uint64_t cnt) {
+                                                  if (cnt >= 2) return;
+                                                  const Key<KW> H = hash_key<KW>(key, tv.hp);
+                                                  atomicAdd(&hist[(uint32_t)((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask], 1u);
+                                              });
+        }
+        __syncthreads();
+        // reserve one contiguous run per non-empty bin; hist[] now holds the run's first position
+        for (uint32_t p = threadIdx.x; p < pv.P; p += blockDim.x) {
+            const unsigned int c = hist[p];
+            if (c) {
+                const unsigned long long at = atomicAdd(pv.cursor + p, (unsigned long long)c);
+                hist[p] = at >= 0xffffffffULL ? 0xffffffffu : (unsigned int)at;
+            }
+        }
+        __syncthreads();
+        // sweep 2: same enumeration, scatter the hashes (or insert directly)
+        for (uint64_t base = tile + wib * 32; base < tile_end; base += (kBlockThreads / 32) * 32) {
+            uint64_t win[KW + 1];
+            uint32_t ewin[NE + 1];
+            load_window<KW, uint64_t>(packed, base, n_words, lane, win);
+            load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
+            const uint32_t active = (base + lane < tile_end) ? ewin[0] : 0u;
+            const uint64_t limit = (base + lane < tile_end) ? n_bases : 0;
+            for_each_kmer_group<KW, false>(win, active, first_end_after<NE>(ewin), base + lane, limit, tv.L.k, tv.hp,
+                                              [&](const Key<KW>& key, uint64_t cnt) {
+                                                  const Key<KW> H = hash_key<KW>(key, tv.hp);
+                                                  if (cnt >= 2) { insert_hashed<KW, W>(tv, H, cnt, st); return; }
+                                                  const uint32_t p = (uint32_t)((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask;
+                                                  const uint64_t pos = atomicAdd(&hist[p], 1u);
+                                                  if (pos < pv.cap) {
+                                                      uint64_t* dst = pv.buf + ((uint64_t)p * pv.cap + pos) * KW;
+#pragma unroll
+                                                      for (int j = 0; j < KW; ++j) __stcg(dst + j, H.w[j]);
+                                                  } else {
+                                                      insert_hashed<KW, W>(tv, H, 1, st);
+                                                  }
+                                              });
+        }
+        __syncthreads();
+    }
+    flush_stats(tv, st);
+}
+
+// phase B: work item = (bin, slice of kSliceEntries entries); items are numbered bin-major and handed out
+// in order through `ticket`, so the blocks resident at any moment drain neighbouring slices.
+constexpr uint32_t kSliceEntries = 16384;
+
+template <int KW, int W, bool WARP_AGG>
+__global__ void __launch_bounds__(kBlockThreads) k_insert_partitions(const __grid_constant__ TableView tv,
+                                                                     const __grid_constant__ PartView pv,
+                                                                     uint32_t slices_per_bin,
+                                                                     unsigned long long* __restrict__ ticket) {
+    const unsigned full = 0xffffffffu;
+    __shared__ unsigned long long item_s;
+    LocalStats st;
+    const unsigned long long n_items = (unsigned long long)pv.P * slices_per_bin;
+    while (true) {
+        if (threadIdx.x == 0) item_s = atomicAdd(ticket, 1ULL);
+        __syncthreads();
+        const unsigned long long item = item_s;
+        __syncthreads();
+        if (item >= n_items) break;
+        const uint32_t p = (uint32_t)(item / slices_per_bin);
+        const uint64_t lo = (uint64_t)(item % slices_per_bin) * kSliceEntries;
+        unsigned long long n = __ldcg(pv.cursor + p);
+        if (n > pv.cap) n = pv.cap;
+        if (lo >= n) continue;
+        const uint64_t hi = lo + kSliceEntries < n ? lo + kSliceEntries : n;
+        const uint64_t* src = pv.buf + (uint64_t)p * pv.cap * KW;
+        for (uint64_t i0 = lo; i0 < hi; i0 += blockDim.x) {
+            const uint64_t i = i0 + threadIdx.x;
+            const bool valid = i < hi;
+            Key<KW> H;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) H.w[j] = valid ? __ldcs(src + i * KW + j) : 0ULL;
+            const unsigned vmask = __ballot_sync(full, valid);
+            if (!valid) continue;
+            uint64_t cnt = 1;
+            bool lead = true;
+            if (WARP_AGG) {
+                unsigned peers = __match_any_sync(vmask, H.w[0]);
+#pragma unroll
+                for (int j = 1; j < KW; ++j) peers &= __match_any_sync(vmask, H.w[j]);
+                cnt = (uint64_t)__popc(peers);
+                lead = (unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u);
+            }
+            if (lead) insert_hashed<KW, W>(tv, H, cnt, st);
+        }
+    }
+    flush_stats(tv, st);
 }
 
 // ---- K0: random 8-byte RMW roofline ------------------------------------------------------------
