@@ -35,11 +35,17 @@ for r in raw[2:]:
     for k in KEYS:
         if k in idx:
             print(f"  {k:75s} {r[idx[k]]:>18s} {units[idx[k]]}")
-    stalls = [h for h in hdr if "issue_stalled" in h and h.endswith("_per_warp_active.pct") and "not_issued" not in h]
-    vals = sorted(((float(r[idx[h]] or 0), h) for h in stalls), reverse=True)[:8]
-    print("  top stall reasons (% of warp-active cycles):")
-    for v, h in vals:
-        print(f"    {v:7.2f}  {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_warp_active.pct', '')}")
+    stalls = [h for h in hdr if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued")]
+    vals = []
+    for h in stalls:
+        try:
+            vals.append((float(r[idx[h]] or 0), h))
+        except ValueError:
+            pass
+    tot = sum(v for v, _ in vals) or 1.0
+    print("  warp stall reasons (share of pc samples):")
+    for v, h in sorted(vals, reverse=True)[:8]:
+        print(f"    {100 * v / tot:6.2f}%  {h.replace('smsp__pcsamp_warps_issue_stalled_', '')}")
 
 args = ["--page", "source", "--csv"]
 if kre:

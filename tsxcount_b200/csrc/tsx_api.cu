@@ -144,16 +144,21 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     const Layout& L = t->L;
     const uint32_t P = 1u << t->pbits;
     const uint64_t chunk_words = std::min<uint64_t>(n_words, (1ULL << 25) / L.KW);
-    uint64_t cap = (32 * chunk_words / P) + (32 * chunk_words / P) / 8 + 2048;
+    constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
+    const int grid_a_max = (int)std::max<uint64_t>(1, std::min<uint64_t>((chunk_words + kTileWords - 1) / kTileWords, (uint64_t)t->sms * 4));
+    // a private run holds ~4 tiles' worth of a bin's k-mers (a tile = 32*kTileWords positions)
+    uint32_t run = 32;
+    while (run < 8192 && run < 4 * 32 * kTileWords / P) run *= 2;
+    // mean + 12.5% + two private runs per block + slack
+    uint64_t cap = (32 * chunk_words / P) + (32 * chunk_words / P) / 8 + 2 * (uint64_t)grid_a_max * run + 2048;
     cap = (cap + 7) & ~7ULL;
     int rc = ensure(t, &t->d_part, &t->cap_part, (size_t)P * cap * L.KW);
     if (rc) return rc;
     PartView pv{};
     pv.buf = t->d_part; pv.cursor = t->d_cursor; pv.cap = cap;
-    pv.pshift = L.LBl - t->pbits; pv.pmask = P - 1; pv.P = P;
+    pv.pshift = L.LBl - t->pbits; pv.pmask = P - 1; pv.P = P; pv.run = run;
     const uint32_t slices = (uint32_t)((cap + kSliceEntries - 1) / kSliceEntries);
     const bool agg = !(L.flags & TSXC_FLAG_NO_WARP_AGG);
-    constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
     int main_launches = 0;
@@ -164,9 +169,7 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
         const int grid_b = t->sms * 8;
         std::pair<cudaEvent_t, cudaEvent_t> eva, evb;
         const bool ta = main_begin(t, s, &eva);
-#define M(KW_, W_)                                                                                                         \
-        if (agg) k_partition_reads<KW_, W_, true><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases); \
-        else k_partition_reads<KW_, W_, false><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases)
+#define M(KW_, W_) k_partition_reads<KW_, W_><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases)
         TSX_DISPATCH(t->L, M);
 #undef M
         if (ta) { cudaEventRecord(eva.second, s); t->ev_part.push_back(eva); }
@@ -271,7 +274,7 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
     {   // regions of 2^region_log2 bytes (default 64 MiB); a bucket is 32 bytes
         const uint32_t table_log2 = L.LBl + 5;
         h->pbits = table_log2 > h->region_log2 ? table_log2 - h->region_log2 : 0;
-        if (h->pbits > 12) h->pbits = 12;
+        if (h->pbits > 11) h->pbits = 11;   // kMaxParts bins
         if (h->pbits > L.LBl) h->pbits = L.LBl;
     }
     h->tv = make_view(L, h->d_words, h->d_ctr);

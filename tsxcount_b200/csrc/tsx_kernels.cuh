@@ -320,13 +320,21 @@ struct PartView {
     uint32_t pshift;               // bin = ((global bucket index) >> pshift) & pmask
     uint32_t pmask;
     uint32_t P;                    // number of bins
-    uint32_t pad;
+    uint32_t run;                  // entries per private run (phase A), a power of two
 };
 
-constexpr int kPartTileIters = 16;                 // warp iterations per tile: 8 warps * 32 words * 16 = 4096 words
-constexpr int kMaxParts = 4096;
+constexpr int kPartTileIters = 2;                  // warp iterations per tile: 8 warps * 32 words * 2 = 512 words
+constexpr int kMaxParts = 2048;
+constexpr uint64_t kHole = ~0ULL;                  // word 0 of an unused run entry; real hashes equal to it are never binned
 
-template <int KW, int W, bool WARP_AGG>
+// Phase A, single sweep.  Every block owns, per bin, TWO private runs of pv.run entries inside the bin (each
+// reserved with one global atomicAdd on the bin cursor): the current one and the next one.  A k-mer takes the
+// next free entry with one shared-memory atomicAdd on the bin's fill counter (fill < run -> current run,
+// fill < 2*run -> next run).  Runs are only rotated at the block-wide barrier between tiles, so the bases a
+// thread reads after its atomicAdd are always the ones its index refers to.  A tile brings ~run/4 k-mers per
+// bin, so both runs running out inside one tile is a tail event; those k-mers take single entries straight
+// from the global cursor.  Unused tails of the runs a block still owns at the end are filled with holes.
+template <int KW, int W>
 __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_constant__ TableView tv,
                                                                    const __grid_constant__ PartView pv,
                                                                    const uint64_t* __restrict__ packed,
@@ -334,63 +342,108 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
                                                                    uint64_t w_end, uint64_t n_words, uint64_t n_bases) {
     constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
     constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
-    __shared__ unsigned int hist[kMaxParts];
+    constexpr unsigned int kNoRun = 0xffffffffu;
+    __shared__ unsigned int run_cur[kMaxParts];    // base of the current run (entry index inside the bin)
+    __shared__ unsigned int run_next[kMaxParts];   // base of the next run
+    __shared__ unsigned int run_fill[kMaxParts];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
+    const uint32_t R = pv.run;
     LocalStats st;
+
+    auto reserve = [&](uint32_t p) -> unsigned int {   // one run, or kNoRun when the bin is (nearly) full
+        const unsigned long long nb = atomicAdd(pv.cursor + p, (unsigned long long)R);
+        if (nb + R <= pv.cap) return (unsigned int)nb;
+        for (unsigned long long j = nb; j < pv.cap; ++j) __stcg(pv.buf + ((uint64_t)p * pv.cap + j) * KW, kHole);
+        return kNoRun;
+    };
+    auto fill_holes = [&](uint32_t p, unsigned int base, unsigned int from) {
+        if (base == kNoRun) return;
+        uint64_t* dst = pv.buf + ((uint64_t)p * pv.cap + base) * KW;
+        for (unsigned int j = from; j < R; ++j) __stcg(dst + (uint64_t)j * KW, kHole);
+    };
+
+    for (uint32_t p = threadIdx.x; p < pv.P; p += blockDim.x) {
+        run_cur[p] = reserve(p); run_next[p] = reserve(p); run_fill[p] = 0;
+    }
+    __syncthreads();
+
+    // One k-mer per lane is kept "in flight": its shared-memory atomicAdd is issued when the k-mer is produced,
+    // the returned index is consumed (bases read, hash stored) only when the NEXT k-mer of the lane has issued
+    // its own atomic, so the ATOMS round trip overlaps a whole extraction + hash step.
+    Key<KW> pend_h;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) pend_h.w[j] = 0;
+    uint32_t pend_p = 0;
+    unsigned int pend_idx = 0;
+    bool pend = false;
+    auto complete = [&]() {
+        if (!pend) return;
+        pend = false;
+        const unsigned int rb = pend_idx < R ? run_cur[pend_p] : run_next[pend_p];
+        uint64_t pos;
+        if (pend_idx < 2 * R && rb != kNoRun) pos = (uint64_t)rb + (pend_idx < R ? pend_idx : pend_idx - R);
+        else pos = atomicAdd(pv.cursor + pend_p, 1ULL);   // both runs used up in one tile
+        if (pos < pv.cap) {
+            uint64_t* dst = pv.buf + ((uint64_t)pend_p * pv.cap + pos) * KW;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) __stcg(dst + j, pend_h.w[j]);
+        } else {
+            insert_hashed<KW, W>(tv, pend_h, 1, st);      // bin full: never dropped
+        }
+    };
+
     for (uint64_t tile = w_begin + (uint64_t)blockIdx.x * kTileWords; tile < w_end; tile += (uint64_t)gridDim.x * kTileWords) {
         const uint64_t tile_end = tile + kTileWords < w_end ? tile + kTileWords : w_end;
-        for (uint32_t p = threadIdx.x; p < pv.P; p += blockDim.x) hist[p] = 0;
-        __syncthreads();
-        // sweep 1: histogram of the tile's single k-mers over the bins
         for (uint64_t base = tile + wib * 32; base < tile_end; base += (kBlockThreads / 32) * 32) {
             uint64_t win[KW + 1];
             uint32_t ewin[NE + 1];
             load_window<KW, uint64_t>(packed, base, n_words, lane, win);
             load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
-            const uint32_t active = (base + lane < tile_end) ? ewin[0] : 0u;
             const uint64_t limit = (base + lane < tile_end) ? n_bases : 0;  // lanes past the chunk emit nothing
-            for_each_kmer_group<KW, false>(win, active, first_end_after<NE>(ewin), base + lane, limit, tv.L.k, tv.hp,
-                                              [&](const Key<KW>& key, uint64_t cnt) {
-                                                  if (cnt >= 2) return;
-                                                  const Key<KW> H = hash_key<KW>(key, tv.hp);
-                                                  atomicAdd(&hist[(uint32_t)((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask], 1u);
-                                              });
+            for_each_kmer_group<KW, false>(win, ewin[0], first_end_after<NE>(ewin), base + lane, limit, tv.L.k, tv.hp,
+                                           [&](const Key<KW>& key, uint64_t cnt) {
+                                               const Key<KW> H = hash_key<KW>(key, tv.hp);
+                                               if (cnt >= 2 || H.w[0] == kHole) { insert_hashed<KW, W>(tv, H, cnt, st); return; }
+                                               const uint32_t p = (uint32_t)((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask;
+                                               const unsigned int idx = atomicAdd(&run_fill[p], 1u);
+                                               complete();                 // the previous k-mer of this lane
+                                               pend_h = H; pend_p = p; pend_idx = idx; pend = true;
+                                           });
         }
+        complete();   // the runs must not rotate under an index that is still in flight
         __syncthreads();
-        // reserve one contiguous run per non-empty bin; hist[] now holds the run's first position
-        for (uint32_t p = threadIdx.x; p < pv.P; p += blockDim.x) {
-            const unsigned int c = hist[p];
-            if (c) {
-                const unsigned long long at = atomicAdd(pv.cursor + p, (unsigned long long)c);
-                hist[p] = at >= 0xffffffffULL ? 0xffffffffu : (unsigned int)at;
+        // rotate the runs whose current one was used up during this tile; the reservations of one thread are
+        // issued back to back (kMaxParts / kBlockThreads independent global atomics), then consumed
+        constexpr int kPer = kMaxParts / kBlockThreads;
+        unsigned long long nb[kPer];
+        bool rot[kPer];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const uint32_t p = threadIdx.x + i * kBlockThreads;
+            rot[i] = p < pv.P && run_fill[p] >= R;
+            nb[i] = rot[i] ? atomicAdd(pv.cursor + p, (unsigned long long)R) : 0ULL;
+        }
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            if (!rot[i]) continue;
+            const uint32_t p = threadIdx.x + i * kBlockThreads;
+            const unsigned int f = run_fill[p];
+            run_cur[p] = run_next[p];
+            run_fill[p] = (f < 2 * R ? f : 2 * R) - R;
+            if (nb[i] + R <= pv.cap) {
+                run_next[p] = (unsigned int)nb[i];
+            } else {
+                run_next[p] = kNoRun;
+                for (unsigned long long j = nb[i]; j < pv.cap; ++j) __stcg(pv.buf + ((uint64_t)p * pv.cap + j) * KW, kHole);
             }
         }
         __syncthreads();
-        // sweep 2: same enumeration, scatter the hashes (or insert directly)
-        for (uint64_t base = tile + wib * 32; base < tile_end; base += (kBlockThreads / 32) * 32) {
-            uint64_t win[KW + 1];
-            uint32_t ewin[NE + 1];
-            load_window<KW, uint64_t>(packed, base, n_words, lane, win);
-            load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
-            const uint32_t active = (base + lane < tile_end) ? ewin[0] : 0u;
-            const uint64_t limit = (base + lane < tile_end) ? n_bases : 0;
-            for_each_kmer_group<KW, false>(win, active, first_end_after<NE>(ewin), base + lane, limit, tv.L.k, tv.hp,
-                                              [&](const Key<KW>& key, uint64_t cnt) {
-                                                  const Key<KW> H = hash_key<KW>(key, tv.hp);
-                                                  if (cnt >= 2) { insert_hashed<KW, W>(tv, H, cnt, st); return; }
-                                                  const uint32_t p = (uint32_t)((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask;
-                                                  const uint64_t pos = atomicAdd(&hist[p], 1u);
-                                                  if (pos < pv.cap) {
-                                                      uint64_t* dst = pv.buf + ((uint64_t)p * pv.cap + pos) * KW;
-#pragma unroll
-                                                      for (int j = 0; j < KW; ++j) __stcg(dst + j, H.w[j]);
-                                                  } else {
-                                                      insert_hashed<KW, W>(tv, H, 1, st);
-                                                  }
-                                              });
-        }
-        __syncthreads();
+    }
+    for (uint32_t p = threadIdx.x; p < pv.P; p += blockDim.x) {
+        const unsigned int f = run_fill[p];
+        fill_holes(p, run_cur[p], f < R ? f : R);
+        fill_holes(p, run_next[p], f < R ? 0u : (f < 2 * R ? f - R : R));
     }
     flush_stats(tv, st);
 }
@@ -427,8 +480,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_insert_partitions(const __gri
             Key<KW> H;
 #pragma unroll
             for (int j = 0; j < KW; ++j) H.w[j] = valid ? __ldcs(src + i * KW + j) : 0ULL;
-            const unsigned vmask = __ballot_sync(full, valid);
-            if (!valid) continue;
+            const bool live = valid && H.w[0] != kHole;
+            const unsigned vmask = __ballot_sync(full, live);
+            if (!live) continue;
             uint64_t cnt = 1;
             bool lead = true;
             if (WARP_AGG) {
