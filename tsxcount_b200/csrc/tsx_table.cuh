@@ -374,6 +374,13 @@ __device__ __forceinline__ void insert_hashed(const TableView& tv, const Key<KW>
     st.errors |= ERR_TABLE_FULL;
 }
 
+// Out-of-line copy for kernels where inserting is the rare path (phase A of the two-phase insert): keeps the
+// probe loop out of their register budget.
+template <int KW, int W>
+__device__ __noinline__ void insert_hashed_cold(const TableView& tv, const Key<KW>& H, uint64_t count, LocalStats& st) {
+    insert_hashed<KW, W>(tv, H, count, st);
+}
+
 // Reference: findOverflowCounts, TSXHashMap.h:951-1039
 template <int KW, int W>
 __device__ __forceinline__ uint64_t overflow_lookup(const TableView& tv, uint64_t home, uint32_t i, uint32_t pslot) {
