@@ -25,7 +25,7 @@ cli: $(CLI)
 
 $(CLI): $(wildcard $(HOST)/*.cpp) $(wildcard $(HOST)/*.h) include/tsxcount_cuda.h $(LIB)
 	@mkdir -p $(BINDIR)
-	$(HOSTCXX) -O2 -std=c++17 -Wall -fopenmp -Iinclude -o $@ $(wildcard $(HOST)/*.cpp) -L$(LIBDIR) -ltsxcuda -lz -Wl,-rpath,'$$ORIGIN/../lib'
+	$(HOSTCXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(wildcard $(HOST)/*.cpp) -L$(LIBDIR) -ltsxcuda -lz -Wl,-rpath,'$$ORIGIN/../lib'
 
 oracle:
 	$(MAKE) -C oracle all

@@ -1,0 +1,89 @@
+"""The C++ host CLI (tsxcount_b200/host/main.cpp): the reference's option surface plus --mode=CUDA."""
+import os
+import subprocess
+
+import pytest
+
+import oracle_py as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "tsxcount_b200", "bin", "tsxcount")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cli_built():
+    if not os.path.exists(CLI):
+        subprocess.run(["make", "-C", ROOT, "cli"], check=True, capture_output=True)
+
+
+def test_cli_keeps_the_reference_option_surface():
+    out = subprocess.run([CLI, "--help"], capture_output=True, text=True).stdout
+    # src/mains/main.cpp:30-40 of the reference
+    for opt in ("--k=", "--s=", "--l=", "--input=", "--check", "--checkabort", "--threads", "--mode"):
+        assert opt in out, opt
+
+
+def test_cli_refuses_cpu_modes_and_has_no_fallback():
+    p = subprocess.run([CLI, "--input=x.fastq", "--mode=OMP"], capture_output=True, text=True)
+    assert p.returncode == 2 and "--mode=CUDA only" in p.stderr
+    import tsxcount_b200 as tsx
+    if tsx._lib.load().tsxc_device_count() == 0:
+        p = subprocess.run([CLI, "--input=x.fastq", "--mode=CUDA"], capture_output=True, text=True)
+        assert p.returncode == 1 and "no CPU fallback" in p.stderr
+        # the reference echoes its parameters on these streams (main.cpp:420-427)
+        assert "Running with parameters" in p.stdout and "K=14" in p.stderr and "L=26" in p.stderr and "StorageBits=4" in p.stderr
+
+
+@pytest.mark.gpu
+def test_cli_count_check_dump_on_bundled_example(tmp_path):
+    fastq = orc.golden_path("c1_bundled_k14.fastq", tmp_path)
+    golden = orc.golden_path("c1_bundled_k14.fastq.14.count", tmp_path)
+    dump = tmp_path / "out.count"
+    # the reference's documented call (README.md:61) with the new mode
+    p = subprocess.run([CLI, f"--input={fastq}", "--mode=CUDA", "--check", f"--dump={dump}"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "Added a total of 194697 different kmers" in p.stdout
+    assert "total errors0" in p.stdout
+    assert "Reference kmer count: 194697" in p.stdout and "tsxCount kmer count: 194697" in p.stdout
+    assert "queried (Xor) kmer count: 0" in p.stdout
+    assert "k=14 l=26 entry (key+value) bits=64 storage bits=4" in p.stderr
+    assert sorted(open(dump).read().splitlines()) == sorted(open(golden).read().splitlines())
+
+
+@pytest.mark.gpu
+def test_cli_check_detects_a_wrong_reference_and_checkabort_exits_200(tmp_path):
+    fastq = orc.golden_path("c2_fakeseq_k31.fastq", tmp_path)
+    good = orc.golden_path("c2_fakeseq_k31.fastq.31.count", tmp_path)
+    lines = open(good).read().splitlines()
+    kmer, cnt = lines[5].split("\t")
+    lines[5] = f"{kmer}\t{int(cnt) + 1}"
+    open(good, "w").write("\n".join(lines) + "\n")
+    args = [CLI, f"--input={fastq}", "--k=31", "--l=22", "--s=4", "--mode=CUDA", "--check"]
+    p = subprocess.run(args, capture_output=True, text=True)
+    assert p.returncode == 1 and "total errors1" in p.stdout and "Should be" in p.stdout
+    p = subprocess.run(args + ["--checkabort"], capture_output=True, text=True)
+    assert p.returncode == 200                      # src/mains/main.cpp:285-291
+
+
+@pytest.mark.gpu
+def test_cli_table_full_exits_42(tmp_path):
+    fastq = orc.golden_path("c2_uniform_k31.fastq", tmp_path)
+    p = subprocess.run([CLI, f"--input={fastq}", "--k=31", "--l=8", "--mode=CUDA"], capture_output=True, text=True)
+    assert p.returncode == 42                       # src/tsxcount/TSXHashMap.h:340-343
+
+
+@pytest.mark.gpu
+def test_cli_gz_input_and_n_bases(tmp_path):
+    import gzip
+    seqs = [b"ACGTACGTNACGTACGTACGT", b"ACGTACGTACGTACGTACGTAAAA"]
+    fq = tmp_path / "n.fastq.gz"
+    with gzip.open(fq, "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b"@r%d\n%s\n+\n%s\n\n" % (i, s, b"&" * len(s)))
+    dump = tmp_path / "n.count"
+    p = subprocess.run([CLI, f"--input={fq}", "--k=8", "--l=10", "--mode=CUDA", f"--dump={dump}"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    oc = orc.count_seqs(seqs, 8)
+    got = dict(l.split("\t") for l in open(dump).read().splitlines())
+    assert len(got) == oc.n_distinct and sum(int(v) for v in got.values()) == oc.n_total
+    assert "Non-ACGT bases: 1" in p.stderr

@@ -1,0 +1,231 @@
+// tsxcount — command-line front end with the reference's CLI surface and a new --mode=CUDA.
+//
+// Mirrors src/mains/main.cpp of mjoppich/tsxCount:
+//   options           :30-40   --k/-k --s/-s --l/-l --input/-i --check/-c --checkabort/-a --threads/-t --mode/-m
+//   defaults          :409-413 k=14 l=26 s=4
+//   parameter echo    :420-427 (same lines on the same streams)
+//   count phase       :104-222 ("Added a total of N different kmers")
+//   --check           :224-396 (<input>.<k>.count, KMER<TAB>COUNT lines; "total errorsN" and the three counts;
+//                               --checkabort -> exit(200), :285-291)
+//   statistics        :479     print_stats()
+// New: --mode=CUDA (the only mode this binary implements — the CPU modes are the reference's own),
+//      --dump=FILE (KMER<TAB>COUNT, format of count_kmers.py:32-34), --device=N, --widevalue (use every
+//      spare bit of the entry for the value field instead of exactly s bits).
+// The count phase streams FASTQ through FastxReader -> tsxc_pack_reads -> pinned buffers -> tsxc_add_reads
+// (double-buffered: parsing/packing of batch b+1 overlaps the GPU work on batch b).
+#include <argp.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "FastxReader.h"
+#include "TSXHashMapCUDA.h"
+
+const char* argp_program_version = "tsxCount-b200 1.0";
+static char doc[] = "Count k-mers on a B200 (drop-in --mode=CUDA for tsxCount's hash-map insert path).";
+static char args_doc[] = "[FILENAME]...";
+static struct argp_option options[] = {
+    {"k", 'k', "K", 0, "parameter k"},
+    {"s", 's', "STORAGE", 0, "parameter s"},
+    {"l", 'l', "L", 0, "parameter l"},
+    {"input", 'i', "INPUT_FASTA", 0, "input string"},
+    {"check", 'c', 0, OPTION_ARG_OPTIONAL, "check counts"},
+    {"checkabort", 'a', 0, OPTION_ARG_OPTIONAL, "abort if check count raises error"},
+    {"threads", 't', "THREADS", OPTION_ARG_OPTIONAL, "Number of host threads (accepted for compatibility)."},
+    {"mode", 'm', "MODE", OPTION_ARG_OPTIONAL, "counting mode (CUDA)"},
+    {"dump", 'd', "FILE", 0, "write KMER<TAB>COUNT lines"},
+    {"device", 'g', "N", 0, "CUDA device index"},
+    {"widevalue", 'w', 0, 0, "widen the value field to every spare entry bit (default: exactly s bits)"},
+    {0}};
+
+struct arguments {
+    uint16_t k = 14, l = 26, storagebits = 4;   // main.cpp:409-413
+    int threads = 1;
+    std::string input_path, dump_path, mode = "CUDA";
+    bool check = false, checkabort = false, wide = false;
+    int device = 0;
+};
+
+static error_t parse_opt(int key, char* arg, struct argp_state* state) {
+    arguments* a = (arguments*)state->input;
+    switch (key) {
+        case 'k': a->k = (uint16_t)atoi(arg); break;
+        case 'l': a->l = (uint16_t)atoi(arg); break;
+        case 's': a->storagebits = (uint16_t)atoi(arg); break;
+        case 't': if (arg) a->threads = atoi(arg); break;
+        case 'i': a->input_path = arg ? arg : ""; break;
+        case 'c': a->check = true; break;
+        case 'a': a->checkabort = true; break;
+        case 'm': if (arg) { a->mode = arg; std::transform(a->mode.begin(), a->mode.end(), a->mode.begin(), ::toupper); } break;
+        case 'd': a->dump_path = arg ? arg : ""; break;
+        case 'g': a->device = atoi(arg); break;
+        case 'w': a->wide = true; break;
+        case ARGP_KEY_ARG: return 0;
+        default: return ARGP_ERR_UNKNOWN;
+    }
+    return 0;
+}
+static struct argp argp_parser = {options, parse_opt, args_doc, doc, 0, 0, 0};
+
+namespace {
+
+struct PinnedBatch {
+    uint64_t* packed = nullptr; size_t packed_cap = 0;   // words
+    uint64_t* offsets = nullptr; size_t off_cap = 0;     // entries
+    void ensure(size_t words, size_t offs) {
+        if (words > packed_cap) { if (packed) tsxc_host_free(packed); void* p; if (tsxc_host_alloc(words * 8, &p)) throw TSXException("pinned alloc"); packed = (uint64_t*)p; packed_cap = words; }
+        if (offs > off_cap) { if (offsets) tsxc_host_free(offsets); void* p; if (tsxc_host_alloc(offs * 8, &p)) throw TSXException("pinned alloc"); offsets = (uint64_t*)p; off_cap = offs; }
+    }
+    ~PinnedBatch() { if (packed) tsxc_host_free(packed); if (offsets) tsxc_host_free(offsets); }
+};
+
+// k-mer text -> KW words (SequenceUtils.h:86-123); false for non-ACGT
+bool encode_kmer(const std::string& s, uint32_t kw, uint64_t* out) {
+    for (uint32_t j = 0; j < kw; ++j) out[j] = 0;
+    for (size_t i = 0; i < s.size(); ++i) {
+        uint64_t c;
+        switch (s[i]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; default: return false; }
+        out[(2 * i) >> 6] |= c << ((2 * i) & 63);
+    }
+    return true;
+}
+
+void countKMers(TSXHashMapCUDA& map, const arguments& args) {
+    FastxReader reader(args.input_path);
+    const size_t kBatchReads = 1 << 18;
+    PinnedBatch pin[2];
+    std::string bases;
+    std::vector<uint64_t> offsets;
+    uint64_t n_reads_total = 0, n_bad_total = 0;
+    int cur = 0;
+    size_t n;
+    while ((n = reader.nextBatch(kBatchReads, bases, offsets)) > 0) {
+        PinnedBatch& pb = pin[cur];
+        // the previous use of this pinned pair (two batches ago) must have been consumed
+        if (n_reads_total >= 2 * kBatchReads) map.sync();
+        size_t bad_upper = 0;
+        for (char c : bases) bad_upper += !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+        pb.ensure(bases.size() / 32 + 2, n + bad_upper + 2);
+        uint64_t nseg = 0, nbad = 0;
+        if (tsxc_pack_reads(bases.data(), offsets.data(), n, pb.packed, pb.offsets, pb.off_cap, &nseg, &nbad) != TSXC_OK)
+            throw TSXException("tsxc_pack_reads failed");
+        map.addReads(pb.packed, pb.offsets, nseg);
+        n_reads_total += n;
+        n_bad_total += nbad;
+        cur ^= 1;
+    }
+    map.sync();
+    std::cerr << "Reads: " << n_reads_total << std::endl;
+    if (n_bad_total)
+        std::cerr << "Non-ACGT bases: " << n_bad_total << " (k-mers spanning them are skipped; the reference substitutes random bits)" << std::endl;
+    std::cout << "Added a total of " << map.getKmerCount() << " different kmers" << std::endl;   // main.cpp:222
+}
+
+int checkCounts(TSXHashMapCUDA& map, const arguments& args) {
+    const std::string ref = args.input_path + "." + std::to_string(args.k) + ".count";         // main.cpp:226
+    std::cout << "Checking kmer counts against manual hashmap ..." << std::endl;
+    std::cerr << "Loading reference file: " << ref << std::endl;
+    std::ifstream file(ref);
+    uint64_t total_errors = 0, ref_count = 0, found = 0;
+    const uint32_t kw = map.keyWords();
+    if (file.is_open()) {
+        const size_t kChunk = 100000;                                                           // main.cpp:262
+        std::vector<uint64_t> keys, want, got;
+        std::vector<std::string> names;
+        std::string line;
+        auto flush = [&]() {
+            if (want.empty()) return;
+            std::cout << "Going to check " << want.size() << " kmers" << std::endl;
+            got.resize(want.size());
+            map.getKmerCounts(keys.data(), want.size(), got.data());
+            for (size_t i = 0; i < want.size(); ++i) {
+                if (got[i] != 0) ++found;
+                if (got[i] != want[i]) {                                                        // testExecution.h:50-92
+                    std::cout << "kmer: ( " << names[i] << " ): " << got[i] << " Should be " << want[i] << std::endl;
+                    ++total_errors;
+                    if (args.checkabort) exit(200);                                             // main.cpp:285-291
+                }
+            }
+            std::cout << "Checked " << want.size() << " kmers" << std::endl;
+            ref_count += want.size();
+            keys.clear(); want.clear(); names.clear();
+        };
+        while (std::getline(file, line)) {
+            const size_t tab = line.find('\t');
+            if (tab == std::string::npos) continue;
+            const std::string kmer = line.substr(0, tab);
+            const uint64_t cnt = (uint64_t)std::atoll(line.c_str() + tab + 1);
+            keys.resize(keys.size() + kw);
+            if (kmer.size() != args.k || !encode_kmer(kmer, kw, keys.data() + keys.size() - kw)) {
+                keys.resize(keys.size() - kw);
+                std::cout << "kmer: ( " << kmer << " ) cannot be encoded" << std::endl;
+                ++total_errors; ++ref_count;
+                continue;
+            }
+            want.push_back(cnt);
+            names.push_back(kmer);
+            if (want.size() >= kChunk) flush();
+        }
+        flush();
+    }
+    const uint64_t distinct = map.getKmerCount();
+    std::cout << "total errors" << total_errors << std::endl;                                  // main.cpp:367
+    std::cout << "Kmer count check completed." << std::endl;
+    std::cout << "Reference kmer count: " << ref_count << std::endl;                            // main.cpp:373-375
+    std::cout << "queried kmer count: " << found << std::endl;
+    std::cout << "tsxCount kmer count: " << distinct << std::endl;
+    // the reference XORs the queried start positions with its k-mer-start bitmap (:378-384): non-zero means the
+    // table holds k-mers the reference file does not list
+    std::cout << "queried (Xor) kmer count: " << (distinct > found ? distinct - found : found - distinct) << std::endl;
+    return total_errors == 0 && distinct == found ? 0 : 1;
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+    arguments args;
+    argp_parse(&argp_parser, argc, argv, 0, NULL, &args);
+
+    std::cout << "Running with parameters " << std::endl;                                       // main.cpp:420-427
+    std::cerr << "K=" << (int)args.k << std::endl;
+    std::cerr << "L=" << (int)args.l << std::endl;
+    std::cerr << "StorageBits=" << (int)args.storagebits << std::endl;
+    std::cerr << "Check=" << (args.check ? "Yes" : "No") << std::endl;
+    std::cerr << "Input=" << args.input_path << std::endl;
+    std::cerr << "Threads=" << args.threads << std::endl;
+    std::cerr << "Mode=" << args.mode << std::endl;
+
+    if (args.mode != "CUDA") {
+        std::cerr << "Mode " << args.mode << " is one of the reference's CPU serialization backends; this binary implements "
+                  << "--mode=CUDA only (there is no CPU fallback)." << std::endl;
+        return 2;
+    }
+    try {
+        std::cerr << "Creating TSXHashMap CUDA" << std::endl;
+        TSXHashMapCUDA map((uint8_t)args.l, args.storagebits, args.k, args.device, args.wide ? TSXC_FLAG_NONE : TSXC_FLAG_EXACT_S);
+        const auto t0 = std::chrono::steady_clock::now();
+        countKMers(map, args);
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const tsxc_stats_t st = map.stats();
+        std::cerr << "Counted " << st.kmers_added << " kmers in " << secs << " s (" << (secs > 0 ? st.kmers_added / secs / 1e6 : 0.0)
+                  << " M kmers/s incl. parsing)" << std::endl;
+        int rc = 0;
+        if (args.check) rc = checkCounts(map, args);
+        if (!args.dump_path.empty()) map.dump(args.dump_path);
+        map.print_stats();                                                                      // main.cpp:479
+        std::cerr << "adds: " << st.kmers_added << std::endl;
+        std::cerr << "overflow entries: " << st.overflow_entries << std::endl;
+        return rc;
+    } catch (const TSXException& e) {
+        std::cerr << "TSXException: " << e.what() << std::endl;
+        return 1;
+    } catch (const std::exception& e) {
+        std::cerr << "error: " << e.what() << std::endl;
+        return 1;
+    }
+}
