@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batch-reads", type=int, default=4_000_000)
+    ap.add_argument("--force-sharded", action="store_true", help="run the routed multi-GPU data path even with one rank")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -203,9 +204,12 @@ def main():
     lib = tsx._lib.load()
     if lib.tsxc_device_count() < 1:
         raise SystemExit("bench.py needs a B200: tsxcount_b200 has no CPU fallback")
-    if world > 1:
+    if world > 1 or args.force_sharded:
         from tsxcount_b200 import multigpu
-        return multigpu.bench_main(args, wl, rank, world, local_rank)
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29577")
+        return multigpu.bench_main(args, wl, rank, world, local_rank, log)
 
     dev = local_rank
     k, l = wl["k"], wl["l"]

@@ -149,14 +149,43 @@ int tsxc_dump_file(tsxc_table* t, const char* path);
 int tsxc_stats(tsxc_table* t, tsxc_stats_t* out);
 
 /* ---- multi-GPU routing (hash-sharded table) ------------------------------- */
-/* Extract + hash every k-mer of a read batch and append its hash (KW words) to the send buffer of the
- * owning shard: d_send + owner*capacity*KW words; d_send_counts[owner] is advanced atomically.  The handle
- * only supplies (k, l, n_shards, hash); its table is not touched.  Overflowing a send buffer sets a
- * sticky error (TSXC_E_INVALID at the next sync). */
-int tsxc_route_reads_device(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint64_t n_reads,
-                            uint64_t n_bases, uint64_t* d_send, uint64_t capacity_per_shard,
-                            unsigned long long* d_send_counts);
-/* Insert n already-hashed k-mers (as produced by tsxc_route_reads_device) owned by this shard. */
+/* Data path of one chunk of reads on a box of n_shards GPUs (one process per GPU, each holding one shard):
+ *   sender    tsxc_route_chunk   extract + hash, bin every k-mer by (owning shard, table region of that shard)
+ *   exchange  the caller moves block `o` of the bins / cursors / spill lists to shard o (all-to-all over NVLink;
+ *             torch.distributed/NCCL in tsxcount_b200/multigpu.py, or peer copies)
+ *   receiver  tsxc_insert_routed inserts the received bins region by region (the same phase B the single-GPU
+ *             path uses), tsxc_add_hash_counts_device inserts the received spill records.
+ * (No reference counterpart: the reference is one process on one shared table, src/mains/main.cpp:132-218.) */
+typedef struct tsxc_route_layout_t {
+    uint32_t n_shards;
+    uint32_t bins_per_shard;      /* table regions per shard */
+    uint32_t key_words;           /* KW: words per hash */
+    uint32_t spill_record_words;  /* KW + 1: hash + count */
+    uint64_t chunk_words;         /* packed stream words one tsxc_route_chunk call may cover */
+    uint64_t bin_cap;             /* entries per bin */
+    uint64_t block_words;         /* 64-bit words of the bins destined to ONE shard: bins_per_shard*bin_cap*KW */
+    uint64_t spill_cap;           /* records per destination spill list */
+} tsxc_route_layout_t;
+/* Buffer geometry for chunks of at most max_chunk_words packed words (0 = library default). */
+int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, tsxc_route_layout_t* out);
+/* Build the read-boundary bitmap of a read batch (kept inside the handle until the next prepare). */
+int tsxc_route_prepare(tsxc_table* t, const uint64_t* d_offsets, uint64_t n_reads, uint64_t n_bases);
+/* Route packed words [w_begin, w_end) of the prepared batch.  d_bins: n_shards*block_words words,
+ * d_cursors: n_shards*bins_per_shard fill counters, d_spill: n_shards*spill_cap records,
+ * d_spill_n: n_shards counters.  Cursors and spill counters are zeroed first.  Nothing is inserted. */
+int tsxc_route_chunk(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64_t* d_packed, uint64_t n_bases,
+                     uint64_t w_begin, uint64_t w_end, uint64_t* d_bins, unsigned long long* d_cursors,
+                     uint64_t* d_spill, unsigned long long* d_spill_n);
+/* Waits for the routing kernels; *overflowed = 1 if a spill list ran out of room (the flag is cleared):
+ * the caller repeats the chunk in smaller pieces. */
+int tsxc_route_overflowed(tsxc_table* t, int* overflowed);
+/* Insert the bins received from n_sources senders: d_bins holds n_sources blocks of block_words words,
+ * d_cursors n_sources*bins_per_shard fill counters (the sender's block for THIS shard). */
+int tsxc_insert_routed(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64_t* d_bins,
+                       const unsigned long long* d_cursors, uint32_t n_sources);
+/* Insert n (hash, count) records of KW+1 words (received spill lists). */
+int tsxc_add_hash_counts_device(tsxc_table* t, const uint64_t* d_records, uint64_t n);
+/* Insert n already-hashed k-mers (KW words each) owned by this shard. */
 int tsxc_add_hashes_device(tsxc_table* t, const uint64_t* d_hashes, uint64_t n);
 
 /* ---- host-side packing (replaces TSXSeqUtils::fromSequence on the feeder side) ----------- */

@@ -259,17 +259,21 @@ def test_device_generator_matches_oracle(tsx, mode, genome, sub):
 
 
 # ---- hash-sharded table on one GPU (the multi-GPU data path without the exchange) -------------------
-@pytest.mark.parametrize("k,n_shards", [(31, 2), (31, 8), (63, 4), (127, 2)])
-def test_sharded_route_and_insert(tsx, k, n_shards):
+@pytest.mark.parametrize("k,n_shards,mode", [(31, 2, 1), (31, 8, 0), (63, 4, 2), (127, 2, 1)])
+def test_sharded_route_and_insert(tsx, k, n_shards, mode, monkeypatch):
+    """All shards live on one GPU; block o of the sender's bins is handed to shard o directly."""
+    monkeypatch.setenv("TSXC_REGION_LOG2", "16")     # several table regions per shard even for small tables
     lib = tsx._lib.load()
-    seqs = orc.gen_reads(seed=31, n_reads=3000, read_len=150, mode=1)
+    seqs = orc.gen_reads(seed=31, n_reads=3000, read_len=150, mode=mode, genome_len=1 << 8 if mode == 2 else 0)
     oc = orc.count_seqs(seqs, k)
     ascii_, offsets = tsx.sequtils.concat_reads(seqs)
     packed, seg, _ = tsx.sequtils.pack_reads(ascii_, offsets)
     n_bases = int(seg[-1])
+    n_words = (n_bases + 31) // 32
     shards = [tsx.TSXHashMapCUDA(20, 4, k, shard_rank=r, n_shards=n_shards) for r in range(n_shards)]
     kw = shards[0].kw
-    cap = oc.n_total  # worst case: everything to one shard
+    lay = shards[0].routeLayout(1 << 12)             # small chunks: several route calls
+    assert lay.n_shards == n_shards and lay.bins_per_shard >= 2
     bufs = {}
 
     def dalloc(name, nbytes):
@@ -281,27 +285,38 @@ def test_sharded_route_and_insert(tsx, k, n_shards):
     try:
         d_packed = dalloc("packed", packed.nbytes)
         d_off = dalloc("off", seg.nbytes)
-        d_send = dalloc("send", n_shards * cap * kw * 8)
-        d_cnt = dalloc("cnt", n_shards * 8)
+        d_bins = dalloc("bins", n_shards * lay.block_words * 8)
+        d_cur = dalloc("cur", n_shards * lay.bins_per_shard * 8)
+        d_spill = dalloc("spill", n_shards * lay.spill_cap * (kw + 1) * 8)
+        d_spn = dalloc("spn", n_shards * 8)
         tsx._lib.check(lib.tsxc_memcpy(0, d_packed, packed.ctypes.data, packed.nbytes, 1))
         tsx._lib.check(lib.tsxc_memcpy(0, d_off, seg.ctypes.data, seg.nbytes, 1))
-        zero = np.zeros(n_shards, dtype=np.uint64)
-        tsx._lib.check(lib.tsxc_memcpy(0, d_cnt, zero.ctypes.data, zero.nbytes, 1))
-        shards[0].routeReadsDevice(d_packed, d_off, len(seg) - 1, n_bases, d_send, cap, d_cnt)
-        shards[0].sync()
-        cnt = np.zeros(n_shards, dtype=np.uint64)
-        tsx._lib.check(lib.tsxc_memcpy(0, cnt.ctypes.data, d_cnt, cnt.nbytes, 2))
-        assert int(cnt.sum()) == oc.n_total
+        sender = shards[0]
+        sender.routePrepare(d_off, len(seg) - 1, n_bases)
+        n_spilled = 0
+        for w0 in range(0, n_words, lay.chunk_words):
+            w1 = min(n_words, w0 + lay.chunk_words)
+            sender.routeChunk(lay, d_packed, n_bases, w0, w1, d_bins, d_cur, d_spill, d_spn)
+            assert not sender.routeOverflowed()
+            spn = np.zeros(n_shards, dtype=np.uint64)
+            tsx._lib.check(lib.tsxc_memcpy(0, spn.ctypes.data, d_spn, spn.nbytes, 2))
+            for r, hm in enumerate(shards):
+                hm.insertRouted(lay, C.c_void_p(d_bins.value + r * lay.block_words * 8),
+                                C.c_void_p(d_cur.value + r * lay.bins_per_shard * 8), 1)
+                hm.addHashCountsDevice(C.c_void_p(d_spill.value + r * lay.spill_cap * (kw + 1) * 8), int(spn[r]))
+                hm.sync()
+            n_spilled += int(spn.sum())
+        if mode == 1 and k <= 31:
+            assert n_spilled > 0                     # poly-A runs are pre-aggregated and travel as (hash, count)
         got = {}
-        for r, hm in enumerate(shards):
-            hm.addHashesDevice(C.c_void_p(d_send.value + r * cap * kw * 8), int(cnt[r]))
-            hm.sync()
+        for hm in shards:
             keys, counts = hm.getAllKmers()
             for key, c in zip(keys.tolist(), counts.tolist()):
                 assert tuple(key) not in got, "k-mer present in two shards"
                 got[tuple(key)] = int(c)
         assert got == oc.as_dict(kw)
         assert sum(hm.getKmerCount() for hm in shards) == oc.n_distinct
+        assert sum(hm.stats()["kmers_added"] for hm in shards) == oc.n_total
         # a shard answers 0 for k-mers it does not own; the per-shard answers sum to the oracle's
         total = sum(hm.getKmerCounts(oc.keys_kw(kw)) for hm in shards)
         assert np.array_equal(total, oc.counts)
@@ -310,6 +325,50 @@ def test_sharded_route_and_insert(tsx, k, n_shards):
             lib.tsxc_device_free(0, p)
         for hm in shards:
             hm.close()
+
+
+def test_route_spill_overflow_is_reported_not_dropped(tsx):
+    """A chunk whose pre-aggregated groups exceed the spill list raises the flag; halving the chunk succeeds."""
+    lib = tsx._lib.load()
+    seqs = [b"A" * 40 + b"C" * 40 + b"G" * 40 + b"T" * 40] * 4000     # every word ends several homopolymer runs
+    oc = orc.count_seqs(seqs, 21)
+    ascii_, offsets = tsx.sequtils.concat_reads(seqs)
+    packed, seg, _ = tsx.sequtils.pack_reads(ascii_, offsets)
+    n_bases = int(seg[-1]); n_words = (n_bases + 31) // 32
+    with tsx.TSXHashMapCUDA(16, 4, 21, shard_rank=0, n_shards=1) as hm:
+        lay = hm.routeLayout(n_words + 32)
+        lay.spill_cap = 64                            # force the overflow
+        ptrs = []
+
+        def dalloc(nbytes):
+            p = C.c_void_p(); tsx._lib.check(lib.tsxc_device_alloc(0, nbytes, C.byref(p))); ptrs.append(p); return p
+        try:
+            d_packed, d_off = dalloc(packed.nbytes), dalloc(seg.nbytes)
+            d_bins, d_cur = dalloc(lay.block_words * 8), dalloc(lay.bins_per_shard * 8)
+            d_spill, d_spn = dalloc(lay.spill_cap * 2 * 8), dalloc(8)
+            tsx._lib.check(lib.tsxc_memcpy(0, d_packed, packed.ctypes.data, packed.nbytes, 1))
+            tsx._lib.check(lib.tsxc_memcpy(0, d_off, seg.ctypes.data, seg.nbytes, 1))
+            hm.routePrepare(d_off, len(seg) - 1, n_bases)
+            hm.routeChunk(lay, d_packed, n_bases, 0, n_words, d_bins, d_cur, d_spill, d_spn)
+            assert hm.routeOverflowed() and not hm.routeOverflowed()     # reported once, then cleared
+            assert hm.getKmerCount() == 0                                 # routing never inserts
+            todo = [(0, n_words)]
+            while todo:
+                w0, w1 = todo.pop()
+                hm.routeChunk(lay, d_packed, n_bases, w0, w1, d_bins, d_cur, d_spill, d_spn)
+                if hm.routeOverflowed():
+                    mid = (w0 + w1) // 2
+                    todo += [(w0, mid), (mid, w1)]
+                    continue
+                spn = np.zeros(1, dtype=np.uint64)
+                tsx._lib.check(lib.tsxc_memcpy(0, spn.ctypes.data, d_spn, 8, 2))
+                hm.insertRouted(lay, d_bins, d_cur, 1)
+                hm.addHashCountsDevice(d_spill, int(spn[0]))
+                hm.sync()
+            check_against_oracle(tsx, hm, oc)
+        finally:
+            for p in ptrs:
+                lib.tsxc_device_free(0, p)
 
 
 # ---- the region-partitioned (two-phase) insert path -----------------------------------------------------

@@ -49,6 +49,14 @@ class TsxcGenParams(C.Structure):
     ]
 
 
+class TsxcRouteLayout(C.Structure):
+    _fields_ = [
+        ("n_shards", C.c_uint32), ("bins_per_shard", C.c_uint32), ("key_words", C.c_uint32),
+        ("spill_record_words", C.c_uint32), ("chunk_words", C.c_uint64), ("bin_cap", C.c_uint64),
+        ("block_words", C.c_uint64), ("spill_cap", C.c_uint64),
+    ]
+
+
 _u64p = C.POINTER(C.c_uint64)
 _vp = C.c_void_p
 
@@ -78,7 +86,12 @@ PROTOTYPES = {
     "tsxc_dump": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _u64p]),
     "tsxc_dump_file": (C.c_int, [_vp, C.c_char_p]),
     "tsxc_stats": (C.c_int, [_vp, C.POINTER(TsxcStats)]),
-    "tsxc_route_reads_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]),
+    "tsxc_route_layout": (C.c_int, [_vp, C.c_uint64, C.POINTER(TsxcRouteLayout)]),
+    "tsxc_route_prepare": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64]),
+    "tsxc_route_chunk": (C.c_int, [_vp, C.POINTER(TsxcRouteLayout), _vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
+    "tsxc_route_overflowed": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "tsxc_insert_routed": (C.c_int, [_vp, C.POINTER(TsxcRouteLayout), _vp, _vp, C.c_uint32]),
+    "tsxc_add_hash_counts_device": (C.c_int, [_vp, _vp, C.c_uint64]),
     "tsxc_add_hashes_device": (C.c_int, [_vp, _vp, C.c_uint64]),
     "tsxc_pack_reads": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _u64p, _u64p]),
     "tsxc_gen_reads_device": (C.c_int, [C.POINTER(TsxcGenParams), C.c_uint64, C.c_uint64, C.c_int, _vp, _vp, _vp]),

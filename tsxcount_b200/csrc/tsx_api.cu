@@ -169,7 +169,7 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
         const int grid_b = t->sms * 8;
         std::pair<cudaEvent_t, cudaEvent_t> eva, evb;
         const bool ta = main_begin(t, s, &eva);
-#define M(KW_, W_) k_partition_reads<KW_, W_><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases)
+#define M(KW_, W_) k_partition_reads<KW_, W_, false><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases)
         TSX_DISPATCH(t->L, M);
 #undef M
         if (ta) { cudaEventRecord(eva.second, s); t->ev_part.push_back(eva); }
@@ -274,7 +274,7 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
     {   // regions of 2^region_log2 bytes (default 64 MiB); a bucket is 32 bytes
         const uint32_t table_log2 = L.LBl + 5;
         h->pbits = table_log2 > h->region_log2 ? table_log2 - h->region_log2 : 0;
-        if (h->pbits > 11) h->pbits = 11;   // kMaxParts bins
+        if (h->pbits > 12) h->pbits = 12;   // kMaxParts bins
         if (h->pbits > L.LBl) h->pbits = L.LBl;
     }
     h->tv = make_view(L, h->d_words, h->d_ctr);
@@ -629,26 +629,135 @@ int tsxc_dump_file(tsxc_table* t, const char* path) {
     return rc;
 }
 
-int tsxc_route_reads_device(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint64_t n_reads,
-                            uint64_t n_bases, uint64_t* d_send, uint64_t capacity_per_shard,
-                            unsigned long long* d_send_counts) {
-    if (!t || !d_offsets || !d_send || !d_send_counts || (!d_packed && n_bases)) return fail(t, TSXC_E_INVALID, "null argument");
-    if (n_bases == 0 || n_reads == 0) return TSXC_OK;
+int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, tsxc_route_layout_t* out) {
+    if (!t || !out) return fail(t, TSXC_E_INVALID, "null argument");
+    const Layout& L = t->L;
+    const uint32_t n_shards = 1u << L.shard_bits;
+    // regions of 2^region_log2 bytes inside the shard, limited so that all shards' bins fit one partition kernel
+    uint32_t pb = t->pbits;
+    while (pb > 0 && ((uint64_t)n_shards << pb) > (uint64_t)kMaxParts) --pb;
+    if (n_shards > (uint32_t)kMaxParts) return fail(t, TSXC_E_UNSUPPORTED, "too many shards");
+    const uint64_t chunk_words = max_chunk_words ? max_chunk_words : (1ULL << 23) / L.KW;
+    const uint32_t P = n_shards << pb;
+    constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
+    const uint64_t grid_a_max = std::max<uint64_t>(1, std::min<uint64_t>((chunk_words + kTileWords - 1) / kTileWords, (uint64_t)t->sms * 4));
+    uint32_t run = 32;
+    while (run < 8192 && run < 4 * 32 * kTileWords / P) run *= 2;
+    uint64_t cap = (32 * chunk_words / P) + (32 * chunk_words / P) / 8 + 2 * grid_a_max * run + 2048;
+    cap = (cap + 7) & ~7ULL;
+    std::memset(out, 0, sizeof *out);
+    out->n_shards = n_shards; out->bins_per_shard = 1u << pb; out->key_words = L.KW; out->spill_record_words = L.KW + 1;
+    out->chunk_words = chunk_words; out->bin_cap = cap; out->block_words = ((uint64_t)1 << pb) * cap * L.KW;
+    out->spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 16 / n_shards * 2);
+    return TSXC_OK;
+}
+
+int tsxc_route_prepare(tsxc_table* t, const uint64_t* d_offsets, uint64_t n_reads, uint64_t n_bases) {
+    if (!t || !d_offsets) return fail(t, TSXC_E_INVALID, "null argument");
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
     const uint64_t n_words = (n_bases + 31) >> 5;
     int rc = ensure(t, &t->d_ends, &t->cap_ends, (size_t)n_words + 8);
     if (rc) return rc;
-    cudaStream_t s = t->stream;
-    CU(cudaMemsetAsync(t->d_ends, 0, n_words * sizeof(uint32_t), s));
-    k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, t->d_ends);
-    const int grid = grid_for(t, n_words);
-    t->n_launches += 2;
-    switch (t->L.KW) {
-        case 1: k_route_reads<1, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, t->d_ends, n_words, n_bases, d_send, capacity_per_shard, d_send_counts); break;
-        case 2: k_route_reads<2, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, t->d_ends, n_words, n_bases, d_send, capacity_per_shard, d_send_counts); break;
-        default: k_route_reads<4, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, t->d_ends, n_words, n_bases, d_send, capacity_per_shard, d_send_counts); break;
+    CU(cudaMemsetAsync(t->d_ends, 0, (n_words + 8) * sizeof(uint32_t), t->stream));
+    if (n_reads) {
+        k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, t->stream>>>(d_offsets, n_reads, t->d_ends);
+        t->n_launches++;
     }
+    CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
+int tsxc_route_chunk(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64_t* d_packed, uint64_t n_bases,
+                     uint64_t w_begin, uint64_t w_end, uint64_t* d_bins, unsigned long long* d_cursors,
+                     uint64_t* d_spill, unsigned long long* d_spill_n) {
+    if (!t || !lay || !d_bins || !d_cursors || !d_spill || !d_spill_n || (!d_packed && w_end > w_begin))
+        return fail(t, TSXC_E_INVALID, "null argument");
+    if (w_end < w_begin || w_end - w_begin > lay->chunk_words) return fail(t, TSXC_E_INVALID, "chunk larger than the layout allows");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    const Layout& L = t->L;
+    const uint64_t n_words = (n_bases + 31) >> 5;
+    const uint32_t P = lay->n_shards * lay->bins_per_shard;
+    uint32_t pb = 0;
+    while ((1u << pb) < lay->bins_per_shard) ++pb;
+    cudaStream_t s = t->stream;
+    CU(cudaMemsetAsync(d_cursors, 0, (size_t)P * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(d_spill_n, 0, (size_t)lay->n_shards * sizeof(unsigned long long), s));
+    if (w_end == w_begin) return TSXC_OK;
+    constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
+    PartView pv{};
+    pv.buf = d_bins; pv.cursor = d_cursors; pv.cap = lay->bin_cap;
+    pv.pshift = L.LBl - pb; pv.pmask = P - 1; pv.P = P;
+    uint32_t run = 32;
+    while (run < 8192 && run < 4 * 32 * kTileWords / P) run *= 2;
+    pv.run = run;
+    pv.spill = d_spill; pv.spill_n = d_spill_n; pv.spill_cap = lay->spill_cap; pv.bins_per_shard_log2 = pb;
+    const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w_end - w_begin + kTileWords - 1) / kTileWords, (uint64_t)t->sms * 4));
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    const bool timed = main_begin(t, s, &ev);
+#define M(KW_, W_) k_partition_reads<KW_, W_, true><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases)
+    TSX_DISPATCH(t->L, M);
+#undef M
+    t->n_launches++;
+    if (timed) { cudaEventRecord(ev.second, s); t->ev_part.push_back(ev); t->n_main_launches++; }
+    CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
+int tsxc_route_overflowed(tsxc_table* t, int* overflowed) {
+    if (!t || !overflowed) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->stream));
+    unsigned long long flags = 0;
+    CU(cudaMemcpy(&flags, t->d_ctr + CTR_ERRORS, sizeof flags, cudaMemcpyDeviceToHost));
+    *overflowed = (flags & ERR_SEND_OVERFLOW) ? 1 : 0;
+    if (*overflowed) {
+        flags &= ~(unsigned long long)ERR_SEND_OVERFLOW;
+        CU(cudaMemcpy(t->d_ctr + CTR_ERRORS, &flags, sizeof flags, cudaMemcpyHostToDevice));
+    }
+    return TSXC_OK;
+}
+
+int tsxc_insert_routed(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64_t* d_bins,
+                       const unsigned long long* d_cursors, uint32_t n_sources) {
+    if (!t || !lay || !d_bins || !d_cursors) return fail(t, TSXC_E_INVALID, "null argument");
+    if (n_sources == 0) return TSXC_OK;
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    cudaStream_t s = t->stream;
+    PartView pv{};
+    pv.buf = const_cast<uint64_t*>(d_bins); pv.cursor = const_cast<unsigned long long*>(d_cursors);
+    pv.cap = lay->bin_cap; pv.P = n_sources * lay->bins_per_shard;
+    const uint32_t slices = (uint32_t)((lay->bin_cap + kSliceEntries - 1) / kSliceEntries);
+    unsigned long long* ticket = t->d_cursor + kMaxParts;
+    CU(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s));
+    const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
+    const int grid_b = t->sms * 8;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    const bool timed = main_begin(t, s, &ev);
+#define M(KW_, W_)                                                                                        \
+    if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket); \
+    else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket)
+    TSX_DISPATCH(t->L, M);
+#undef M
+    t->n_launches++;
+    if (timed) { cudaEventRecord(ev.second, s); t->ev_ins.push_back(ev); t->n_main_launches++; }
+    CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
+int tsxc_add_hash_counts_device(tsxc_table* t, const uint64_t* d_records, uint64_t n) {
+    if (!t || (!d_records && n)) return fail(t, TSXC_E_INVALID, "null argument");
+    if (n == 0) return TSXC_OK;
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    const int grid = grid_for(t, n);
+#define M(KW_, W_) k_add_hash_counts<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_records, n)
+    TSX_DISPATCH(t->L, M);
+#undef M
+    t->n_launches++;
     CU(cudaGetLastError());
     return TSXC_OK;
 }

@@ -4,7 +4,8 @@
 //   K2     k_add_kmers      batched addKmer on explicit k-mers / on pre-hashed k-mers
 //   K4     k_lookup         batched getKmerCount(kmer)
 //   K5     k_dump           table scan -> (k-mer, count) via the inverse hash
-//   K6     k_route_reads    extraction + hash + binning by owning shard (multi-GPU send side)
+//   K6     k_partition_reads<ROUTE>  extraction + hash + binning by owning shard and table region (multi-GPU
+//                              send side); k_insert_partitions / k_add_hash_counts on the receiving shard
 //          k_mark_ends      read offsets -> "last base of a read" bitmap
 //
 // Reference semantics (paths relative to mjoppich/tsxCount):
@@ -265,42 +266,6 @@ __global__ void __launch_bounds__(kBlockThreads) k_dump(const __grid_constant__ 
     }
 }
 
-// ---- K6: route k-mers to their owning shard (multi-GPU send side) -------------------------------
-// Same extraction as k_count_reads; instead of inserting, the HASH of every k-mer occurrence (KW words;
-// the hash is bijective, so the receiver needs nothing else) is appended to the send buffer of the shard
-// that owns its bucket.  Homopolymer runs merged by the extractor are expanded again: the receiver
-// re-aggregates per warp while inserting.
-template <int KW, bool WARP_AGG>
-__global__ void __launch_bounds__(kBlockThreads) k_route_reads(const __grid_constant__ TableView tv, const uint64_t* __restrict__ packed,
-                                                               const uint32_t* __restrict__ ends, uint64_t n_words,
-                                                               uint64_t n_bases, uint64_t* __restrict__ send,
-                                                               uint64_t capacity, unsigned long long* __restrict__ send_counts) {
-    constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
-    const unsigned lane = threadIdx.x & 31u;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    uint32_t errors = 0;
-    for (uint64_t base = warp * 32; base < n_words; base += n_warps * 32) {
-        uint64_t win[KW + 1];
-        uint32_t ewin[NE + 1];
-        load_window<KW, uint64_t>(packed, base, n_words, lane, win);
-        load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
-        const uint32_t dist_after = first_end_after<NE>(ewin);
-        for_each_kmer_group<KW, false>(win, ewin[0], dist_after, base + lane, n_bases, tv.L.k, tv.hp,
-                                       [&](const Key<KW>& key, uint64_t cnt) {
-                                           const Key<KW> H = hash_key<KW>(key, tv.hp);
-                                           const uint32_t owner = (uint32_t)((H.w[0] & tv.lbg_mask) >> tv.L.LBl);
-                                           const unsigned long long at = atomicAdd(send_counts + owner, (unsigned long long)cnt);
-                                           if (at + cnt > capacity) { errors |= ERR_SEND_OVERFLOW; return; }
-                                           uint64_t* dst = send + ((uint64_t)owner * capacity + at) * KW;
-                                           for (uint64_t c = 0; c < cnt; ++c)
-#pragma unroll
-                                               for (int j = 0; j < KW; ++j) dst[c * KW + j] = H.w[j];
-                                       });
-    }
-    if (errors) atomicOr(tv.ctr + CTR_ERRORS, (unsigned long long)errors);
-}
-
 // ---- partitioned insert (TLB-aware two-phase path) -----------------------------------------------
 // Measured on B200 (profiles/): uniformly random 8-byte RMWs over a 128 GiB table run at 9.8 G/s and a
 // dependent sector-load + atomic at 4 G/s, but the same accesses confined to a 64 MiB window per thread
@@ -321,10 +286,17 @@ struct PartView {
     uint32_t pmask;
     uint32_t P;                    // number of bins
     uint32_t run;                  // entries per private run (phase A), a power of two
+    // routing mode (multi-GPU send side): bins are grouped by owning shard, bins_per_shard each; k-mers that
+    // cannot be binned (pre-aggregated groups, full bins) become (hash, count) records in the owner's spill list
+    uint64_t* spill;               // n_shards * spill_cap records of KW+1 words
+    unsigned long long* spill_n;   // n_shards counters
+    uint64_t spill_cap;
+    uint32_t bins_per_shard_log2;
+    uint32_t pad;
 };
 
 constexpr int kPartTileIters = 2;                  // warp iterations per tile: 8 warps * 32 words * 2 = 512 words
-constexpr int kMaxParts = 2048;
+constexpr int kMaxParts = 4096;
 constexpr uint64_t kHole = ~0ULL;                  // word 0 of an unused run entry; real hashes equal to it are never binned
 
 // Phase A, single sweep.  Every block owns, per bin, TWO private runs of pv.run entries inside the bin (each
@@ -334,7 +306,7 @@ constexpr uint64_t kHole = ~0ULL;                  // word 0 of an unused run en
 // thread reads after its atomicAdd are always the ones its index refers to.  A tile brings ~run/4 k-mers per
 // bin, so both runs running out inside one tile is a tail event; those k-mers take single entries straight
 // from the global cursor.  Unused tails of the runs a block still owns at the end are filled with holes.
-template <int KW, int W>
+template <int KW, int W, bool ROUTE>
 __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_constant__ TableView tv,
                                                                    const __grid_constant__ PartView pv,
                                                                    const uint64_t* __restrict__ packed,
@@ -351,6 +323,19 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
     const uint32_t R = pv.run;
     LocalStats st;
 
+    // k-mers that do not go through a bin.  Single GPU: inserted on the spot.  Routing: the table of the owner
+    // lives on another GPU, so they become (hash, count) records of the owner's spill list; a full spill list
+    // raises ERR_SEND_OVERFLOW and the host repeats the chunk in smaller pieces (nothing has been inserted yet).
+    auto cold = [&](const Key<KW>& H, uint64_t cnt) {
+        if (!ROUTE) { insert_hashed<KW, W>(tv, H, cnt, st); return; }
+        const uint32_t owner = (uint32_t)(((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask) >> pv.bins_per_shard_log2;
+        const unsigned long long at = atomicAdd(pv.spill_n + owner, 1ULL);
+        if (at >= pv.spill_cap) { st.errors |= ERR_SEND_OVERFLOW; return; }
+        uint64_t* dst = pv.spill + ((uint64_t)owner * pv.spill_cap + at) * (KW + 1);
+#pragma unroll
+        for (int j = 0; j < KW; ++j) dst[j] = H.w[j];
+        dst[KW] = cnt;
+    };
     auto reserve = [&](uint32_t p) -> unsigned int {   // one run, or kNoRun when the bin is (nearly) full
         const unsigned long long nb = atomicAdd(pv.cursor + p, (unsigned long long)R);
         if (nb + R <= pv.cap) return (unsigned int)nb;
@@ -389,7 +374,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
 #pragma unroll
             for (int j = 0; j < KW; ++j) __stcg(dst + j, pend_h.w[j]);
         } else {
-            insert_hashed<KW, W>(tv, pend_h, 1, st);      // bin full: never dropped
+            cold(pend_h, 1);                              // bin full: never dropped
         }
     };
 
@@ -404,7 +389,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
             for_each_kmer_group<KW, false>(win, ewin[0], first_end_after<NE>(ewin), base + lane, limit, tv.L.k, tv.hp,
                                            [&](const Key<KW>& key, uint64_t cnt) {
                                                const Key<KW> H = hash_key<KW>(key, tv.hp);
-                                               if (cnt >= 2 || H.w[0] == kHole) { insert_hashed<KW, W>(tv, H, cnt, st); return; }
+                                               if (cnt >= 2 || H.w[0] == kHole) { cold(H, cnt); return; }
                                                const uint32_t p = (uint32_t)((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask;
                                                const unsigned int idx = atomicAdd(&run_fill[p], 1u);
                                                complete();                 // the previous k-mer of this lane
@@ -494,6 +479,21 @@ __global__ void __launch_bounds__(kBlockThreads) k_insert_partitions(const __gri
             }
             if (lead) insert_hashed<KW, W>(tv, H, cnt, st);
         }
+    }
+    flush_stats(tv, st);
+}
+
+// (hash, count) records: the spill lists of the routing path
+template <int KW, int W>
+__global__ void __launch_bounds__(kBlockThreads) k_add_hash_counts(const __grid_constant__ TableView tv,
+                                                                   const uint64_t* __restrict__ rec, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    LocalStats st;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Key<KW> H;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) H.w[j] = __ldg(rec + i * (KW + 1) + j);
+        insert_hashed<KW, W>(tv, H, __ldg(rec + i * (KW + 1) + KW), st);
     }
     flush_stats(tv, st);
 }

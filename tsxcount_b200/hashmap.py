@@ -120,9 +120,29 @@ class TSXHashMapCUDA:
     def addHashesDevice(self, d_hashes, n):
         _lib.check(self._lib.tsxc_add_hashes_device(self._h, d_hashes, n), self._h)
 
-    def routeReadsDevice(self, d_packed, d_offsets, n_reads, n_bases, d_send, capacity, d_send_counts):
-        _lib.check(self._lib.tsxc_route_reads_device(self._h, d_packed, d_offsets, n_reads, n_bases, d_send, capacity,
-                                                     d_send_counts), self._h)
+    # -- multi-GPU routing (see include/tsxcount_cuda.h "multi-GPU routing") ------------------------
+    def routeLayout(self, max_chunk_words=0):
+        lay = _lib.TsxcRouteLayout()
+        _lib.check(self._lib.tsxc_route_layout(self._h, max_chunk_words, C.byref(lay)), self._h)
+        return lay
+
+    def routePrepare(self, d_offsets, n_reads, n_bases):
+        _lib.check(self._lib.tsxc_route_prepare(self._h, d_offsets, n_reads, n_bases), self._h)
+
+    def routeChunk(self, lay, d_packed, n_bases, w_begin, w_end, d_bins, d_cursors, d_spill, d_spill_n):
+        _lib.check(self._lib.tsxc_route_chunk(self._h, C.byref(lay), d_packed, n_bases, w_begin, w_end, d_bins,
+                                              d_cursors, d_spill, d_spill_n), self._h)
+
+    def routeOverflowed(self):
+        flag = C.c_int(0)
+        _lib.check(self._lib.tsxc_route_overflowed(self._h, C.byref(flag)), self._h)
+        return bool(flag.value)
+
+    def insertRouted(self, lay, d_bins, d_cursors, n_sources):
+        _lib.check(self._lib.tsxc_insert_routed(self._h, C.byref(lay), d_bins, d_cursors, n_sources), self._h)
+
+    def addHashCountsDevice(self, d_records, n):
+        _lib.check(self._lib.tsxc_add_hash_counts_device(self._h, d_records, n), self._h)
 
     # -- query path -------------------------------------------------------------------------------
     def getKmerCount(self, kmer=None):
