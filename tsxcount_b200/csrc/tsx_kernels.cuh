@@ -356,23 +356,26 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
     // One k-mer per lane is kept "in flight": its shared-memory atomicAdd is issued when the k-mer is produced,
     // the returned index is consumed (bases read, hash stored) only when the NEXT k-mer of the lane has issued
     // its own atomic, so the ATOMS round trip overlaps a whole extraction + hash step.
+    const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
     Key<KW> pend_h;
 #pragma unroll
     for (int j = 0; j < KW; ++j) pend_h.w[j] = 0;
     uint32_t pend_p = 0;
-    unsigned int pend_idx = 0;
+    unsigned int pend_idx = 0, pend_cur = 0, pend_next = 0;
     bool pend = false;
     auto complete = [&]() {
         if (!pend) return;
         pend = false;
-        const unsigned int rb = pend_idx < R ? run_cur[pend_p] : run_next[pend_p];
+        const unsigned int rb = pend_idx < R ? pend_cur : pend_next;
         uint64_t pos;
         if (pend_idx < 2 * R && rb != kNoRun) pos = (uint64_t)rb + (pend_idx < R ? pend_idx : pend_idx - R);
         else pos = atomicAdd(pv.cursor + pend_p, 1ULL);   // both runs used up in one tile
         if (pos < pv.cap) {
             uint64_t* dst = pv.buf + ((uint64_t)pend_p * pv.cap + pos) * KW;
+            const bool last = KW >= 4 || ((pos * KW) & 3) == (4 - KW);   // entry that completes its 32-byte sector
+            const uint64_t pol = last ? pol_first : pol_last;
 #pragma unroll
-            for (int j = 0; j < KW; ++j) __stcg(dst + j, pend_h.w[j]);
+            for (int j = 0; j < KW; ++j) st_bin(dst + j, pend_h.w[j], pol);
         } else {
             cold(pend_h, 1);                              // bin full: never dropped
         }
@@ -392,8 +395,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
                                                if (cnt >= 2 || H.w[0] == kHole) { cold(H, cnt); return; }
                                                const uint32_t p = (uint32_t)((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask;
                                                const unsigned int idx = atomicAdd(&run_fill[p], 1u);
+                                               const unsigned int rc = run_cur[p], rn = run_next[p];   // stable until the barrier
                                                complete();                 // the previous k-mer of this lane
-                                               pend_h = H; pend_p = p; pend_idx = idx; pend = true;
+                                               pend_h = H; pend_p = p; pend_idx = idx; pend_cur = rc; pend_next = rn; pend = true;
                                            });
         }
         complete();   // the runs must not rotate under an index that is still in flight

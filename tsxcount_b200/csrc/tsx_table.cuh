@@ -157,6 +157,24 @@ __device__ __forceinline__ void load_bucket(const uint64_t* b, uint64_t (&w)[4])
     w[0] = a.x; w[1] = a.y; w[2] = c.x; w[3] = c.y;
 }
 
+// Stores into the bins of the two-phase path.  The write frontier (one partially filled 32-byte sector per
+// (block, bin)) must survive in L2 until its last entry arrives, otherwise DRAM sees read-fills and repeated
+// partial write-backs (ncu: 20 B written + 9.5 B read per 8-byte hash).  Entries that do not complete a sector
+// are stored evict_last, the completing one evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_bin(uint64_t* p, uint64_t v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(policy) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_bucket_l2(const uint64_t* b) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(b));
 }
