@@ -272,16 +272,22 @@ def main():
     peak, peak_src = read_peaks()
     main_launches = st["main_kernel_launches"]
     achieved = algo_bytes / (statistics.mean(main_ms) * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]
+        # ncu dram__bytes_read+write per k-mer of the dominant kernels (captured on the 1/16-scale configuration,
+        # same region count) x the k-mers the dominant launches of one step process
+        traffic = prof["dram_bytes_per_kmer"] * n_kmers
+        traffic_src = prof["source"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": "k_count_reads (fused extract+hash+insert)" if main_launches == 1 else "partition+insert kernels",
-                "algorithmic_bytes_per_kmer": 2 * E + in_bytes_per_kmer}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "per": f"step = {main_launches} launches of the dominant kernels (algorithmic bytes and traffic are per step)",
+                "kernel": "k_count_reads (fused extract+hash+insert)" if main_launches == 1
+                else "k_partition_reads + k_insert_partitions (two-phase insert, one pair per chunk of reads)",
+                "algorithmic_bytes_per_kmer": 2 * E + in_bytes_per_kmer,
+                "phase_ms": {"partition": st["partition_ms"], "insert": st["insert_ms"]}}
     # K0: the random 8-byte RMW rate on a table of the same size, measured live
     k0 = {}
     for mode, name in ((0, "atomic_add"), (2, "sector_load_plus_atomic")):

@@ -52,7 +52,7 @@ struct tsxc_table {
     uint64_t* d_part = nullptr; size_t cap_part = 0;          // words
     unsigned long long* d_cursor = nullptr;                   // kMaxParts + 1 (last = ticket)
     uint32_t pbits = 0;                                        // log2(#regions); 0 = direct path only
-    uint32_t region_log2 = 26;
+    uint32_t region_log2 = 28;
     // launch accounting (bench.py's gpu_launches / roofline come from here)
     uint64_t n_launches = 0, n_main_launches = 0;
     double main_ms = 0.0;
@@ -147,7 +147,7 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
     const int grid_a_max = (int)std::max<uint64_t>(1, std::min<uint64_t>((chunk_words + kTileWords - 1) / kTileWords, (uint64_t)t->sms * 4));
     // a private run holds ~4 tiles' worth of a bin's k-mers (a tile = 32*kTileWords positions)
-    uint32_t run = 32;
+    uint32_t run = 8;
     while (run < 8192 && run < 4 * 32 * kTileWords / P) run *= 2;
     // mean + 12.5% + two private runs per block + slack
     uint64_t cap = (32 * chunk_words / P) + (32 * chunk_words / P) / 8 + 2 * (uint64_t)grid_a_max * run + 2048;
@@ -271,7 +271,7 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
         const int v = std::atoi(env);
         if (v >= 16 && v <= 40) h->region_log2 = (uint32_t)v;
     }
-    {   // regions of 2^region_log2 bytes (default 64 MiB); a bucket is 32 bytes
+    {   // regions of 2^region_log2 bytes (default 256 MiB); a bucket is 32 bytes
         const uint32_t table_log2 = L.LBl + 5;
         h->pbits = table_log2 > h->region_log2 ? table_log2 - h->region_log2 : 0;
         if (h->pbits > 12) h->pbits = 12;   // kMaxParts bins
@@ -637,11 +637,11 @@ int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, tsxc_route_layout
     uint32_t pb = t->pbits;
     while (pb > 0 && ((uint64_t)n_shards << pb) > (uint64_t)kMaxParts) --pb;
     if (n_shards > (uint32_t)kMaxParts) return fail(t, TSXC_E_UNSUPPORTED, "too many shards");
-    const uint64_t chunk_words = max_chunk_words ? max_chunk_words : (1ULL << 23) / L.KW;
+    const uint64_t chunk_words = max_chunk_words ? max_chunk_words : (1ULL << 24) / L.KW;
     const uint32_t P = n_shards << pb;
     constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
     const uint64_t grid_a_max = std::max<uint64_t>(1, std::min<uint64_t>((chunk_words + kTileWords - 1) / kTileWords, (uint64_t)t->sms * 4));
-    uint32_t run = 32;
+    uint32_t run = 8;
     while (run < 8192 && run < 4 * 32 * kTileWords / P) run *= 2;
     uint64_t cap = (32 * chunk_words / P) + (32 * chunk_words / P) / 8 + 2 * grid_a_max * run + 2048;
     cap = (cap + 7) & ~7ULL;
@@ -689,11 +689,13 @@ int tsxc_route_chunk(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64
     PartView pv{};
     pv.buf = d_bins; pv.cursor = d_cursors; pv.cap = lay->bin_cap;
     pv.pshift = L.LBl - pb; pv.pmask = P - 1; pv.P = P;
-    uint32_t run = 32;
+    uint32_t run = 8;
     while (run < 8192 && run < 4 * 32 * kTileWords / P) run *= 2;
     pv.run = run;
     pv.spill = d_spill; pv.spill_n = d_spill_n; pv.spill_cap = lay->spill_cap; pv.bins_per_shard_log2 = pb;
-    const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w_end - w_begin + kTileWords - 1) / kTileWords, (uint64_t)t->sms * 4));
+    int per_sm = 4;
+    if (const char* env = std::getenv("TSXC_ROUTE_GRID")) { const int v = std::atoi(env); if (v >= 1 && v <= 8) per_sm = v; }
+    const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w_end - w_begin + kTileWords - 1) / kTileWords, (uint64_t)t->sms * per_sm));
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
 #define M(KW_, W_) k_partition_reads<KW_, W_, true><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases)
