@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -53,6 +54,7 @@ struct tsxc_table {
     unsigned long long* d_cursor = nullptr;                   // kMaxParts + 1 (last = ticket)
     uint32_t pbits = 0;                                        // log2(#regions); 0 = direct path only
     uint32_t region_log2 = 28;
+    int part_blocks_per_sm = 3, route_blocks_per_sm = 3;   // resident blocks of k_partition_reads (occupancy query)
     // launch accounting (bench.py's gpu_launches / roofline come from here)
     uint64_t n_launches = 0, n_main_launches = 0;
     double main_ms = 0.0;
@@ -138,25 +140,50 @@ int status_from_flags(tsxc_table* t, uint64_t flags) {
     return TSXC_OK;
 }
 
+// Geometry of phase A for P bins and chunks of chunk_words packed words.
+//   tile   : words a block handles between two run-rotation barriers; longer tiles for many bins, where the
+//            barrier (8 warps waiting for the slowest) otherwise shows up as 20 % of the stall samples
+//   run    : entries per private run; two runs must cover one tile's arrivals of a bin: mean m = 32*tile/P
+//            (every position valid), Poisson tail m + 6*sqrt(m)
+//   grid   : 8 blocks per SM for few bins, 4 for many (measured: 3 are resident, a finer grid-stride still
+//            balances better: 183-186 ms vs 196 ms at 4 and 217 ms at 3 per SM on config 2; every extra block
+//            costs 1.5 runs of holes per bin)
+//   cap    : bin capacity = mean + 12.5 % + the hole tails of every block (1.5 runs each) + slack
+struct PartGeom { uint32_t tile_words, run; int grid; uint64_t cap; };
+
+PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, int blocks_per_sm) {
+    PartGeom g{};
+    uint32_t iters = P >= 4096 ? 4 : 2;
+    if (const char* e = std::getenv("TSXC_PART_ITERS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) iters = (uint32_t)v; }
+    blocks_per_sm = P <= 1024 ? 8 : 4;
+    if (const char* e = std::getenv("TSXC_PART_GRID")) { const int v = std::atoi(e); if (v >= 1 && v <= 16) blocks_per_sm = v; }
+    g.tile_words = (kBlockThreads / 32) * 32 * iters;
+    const double m = 32.0 * g.tile_words / P;
+    g.run = (uint32_t)std::ceil((m + 6.0 * std::sqrt(m)) / 2.0);
+    g.run = (g.run + 3) & ~3u;           // whole 32-byte sectors
+    if (g.run < 8) g.run = 8;
+    if (const char* e = std::getenv("TSXC_PART_RUN")) { const int v = std::atoi(e); if (v >= 4 && v <= 65536) g.run = (uint32_t)v; }
+    const uint64_t tiles = (chunk_words + g.tile_words - 1) / g.tile_words;
+    g.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)t->sms * blocks_per_sm));
+    const uint64_t mean = 32 * chunk_words / P;
+    g.cap = mean + mean / 8 + 2ULL * (uint64_t)g.grid * g.run + 2048;
+    g.cap = (g.cap + 7) & ~7ULL;
+    return g;
+}
+
 // Two-phase path for tables much larger than the per-SM translation reach (see tsx_kernels.cuh).
 int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words,
                                    uint64_t n_bases, cudaStream_t s) {
     const Layout& L = t->L;
     const uint32_t P = 1u << t->pbits;
     const uint64_t chunk_words = std::min<uint64_t>(n_words, (1ULL << 25) / L.KW);
-    constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
-    const int grid_a_max = (int)std::max<uint64_t>(1, std::min<uint64_t>((chunk_words + kTileWords - 1) / kTileWords, (uint64_t)t->sms * 4));
-    // a private run holds ~4 tiles' worth of a bin's k-mers (a tile = 32*kTileWords positions)
-    uint32_t run = 8;
-    while (run < 8192 && run < 4 * 32 * kTileWords / P) run *= 2;
-    // mean + 12.5% + two private runs per block + slack
-    uint64_t cap = (32 * chunk_words / P) + (32 * chunk_words / P) / 8 + 2 * (uint64_t)grid_a_max * run + 2048;
-    cap = (cap + 7) & ~7ULL;
+    const PartGeom geo = part_geometry(t, P, chunk_words, t->part_blocks_per_sm);
+    const uint64_t cap = geo.cap;
     int rc = ensure(t, &t->d_part, &t->cap_part, (size_t)P * cap * L.KW);
     if (rc) return rc;
     PartView pv{};
     pv.buf = t->d_part; pv.cursor = t->d_cursor; pv.cap = cap;
-    pv.pshift = L.LBl - t->pbits; pv.pmask = P - 1; pv.P = P; pv.run = run;
+    pv.pshift = L.LBl - t->pbits; pv.pmask = P - 1; pv.P = P; pv.run = geo.run; pv.tile_words = geo.tile_words;
     const uint32_t slices = (uint32_t)((cap + kSliceEntries - 1) / kSliceEntries);
     const bool agg = !(L.flags & TSXC_FLAG_NO_WARP_AGG);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -165,7 +192,7 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     for (uint64_t w0 = 0; w0 < n_words; w0 += chunk_words) {
         const uint64_t w1 = std::min(n_words, w0 + chunk_words);
         CU(cudaMemsetAsync(t->d_cursor, 0, (kMaxParts + 1) * sizeof(unsigned long long), s));
-        const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)t->sms * 4));
+        const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w1 - w0 + geo.tile_words - 1) / geo.tile_words, (uint64_t)geo.grid));
         const int grid_b = t->sms * 8;
         std::pair<cudaEvent_t, cudaEvent_t> eva, evb;
         const bool ta = main_begin(t, s, &eva);
@@ -276,6 +303,16 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
         h->pbits = table_log2 > h->region_log2 ? table_log2 - h->region_log2 : 0;
         if (h->pbits > 12) h->pbits = 12;   // kMaxParts bins
         if (h->pbits > L.LBl) h->pbits = L.LBl;
+    }
+    {
+        int a = 0, b = 0;
+#define M(KW_, W_)                                                                                                   \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_partition_reads<KW_, W_, false>, kBlockThreads, 0);          \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_partition_reads<KW_, W_, true>, kBlockThreads, 0)
+        TSX_DISPATCH(L, M);
+#undef M
+        if (a > 0) h->part_blocks_per_sm = a;
+        if (b > 0) h->route_blocks_per_sm = b;
     }
     h->tv = make_view(L, h->d_words, h->d_ctr);
     int rc = tsxc_clear(h);
@@ -639,12 +676,7 @@ int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, tsxc_route_layout
     if (n_shards > (uint32_t)kMaxParts) return fail(t, TSXC_E_UNSUPPORTED, "too many shards");
     const uint64_t chunk_words = max_chunk_words ? max_chunk_words : (1ULL << 24) / L.KW;
     const uint32_t P = n_shards << pb;
-    constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
-    const uint64_t grid_a_max = std::max<uint64_t>(1, std::min<uint64_t>((chunk_words + kTileWords - 1) / kTileWords, (uint64_t)t->sms * 4));
-    uint32_t run = 8;
-    while (run < 8192 && run < 4 * 32 * kTileWords / P) run *= 2;
-    uint64_t cap = (32 * chunk_words / P) + (32 * chunk_words / P) / 8 + 2 * grid_a_max * run + 2048;
-    cap = (cap + 7) & ~7ULL;
+    const uint64_t cap = part_geometry(t, P, chunk_words, t->route_blocks_per_sm).cap;
     std::memset(out, 0, sizeof *out);
     out->n_shards = n_shards; out->bins_per_shard = 1u << pb; out->key_words = L.KW; out->spill_record_words = L.KW + 1;
     out->chunk_words = chunk_words; out->bin_cap = cap; out->block_words = ((uint64_t)1 << pb) * cap * L.KW;
@@ -685,17 +717,13 @@ int tsxc_route_chunk(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64
     CU(cudaMemsetAsync(d_cursors, 0, (size_t)P * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(d_spill_n, 0, (size_t)lay->n_shards * sizeof(unsigned long long), s));
     if (w_end == w_begin) return TSXC_OK;
-    constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
+    const PartGeom geo = part_geometry(t, P, lay->chunk_words, t->route_blocks_per_sm);
     PartView pv{};
     pv.buf = d_bins; pv.cursor = d_cursors; pv.cap = lay->bin_cap;
     pv.pshift = L.LBl - pb; pv.pmask = P - 1; pv.P = P;
-    uint32_t run = 8;
-    while (run < 8192 && run < 4 * 32 * kTileWords / P) run *= 2;
-    pv.run = run;
+    pv.run = geo.run; pv.tile_words = geo.tile_words;
     pv.spill = d_spill; pv.spill_n = d_spill_n; pv.spill_cap = lay->spill_cap; pv.bins_per_shard_log2 = pb;
-    int per_sm = 4;
-    if (const char* env = std::getenv("TSXC_ROUTE_GRID")) { const int v = std::atoi(env); if (v >= 1 && v <= 8) per_sm = v; }
-    const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w_end - w_begin + kTileWords - 1) / kTileWords, (uint64_t)t->sms * per_sm));
+    const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w_end - w_begin + geo.tile_words - 1) / geo.tile_words, (uint64_t)geo.grid));
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
 #define M(KW_, W_) k_partition_reads<KW_, W_, true><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases)

@@ -292,10 +292,9 @@ struct PartView {
     unsigned long long* spill_n;   // n_shards counters
     uint64_t spill_cap;
     uint32_t bins_per_shard_log2;
-    uint32_t pad;
+    uint32_t tile_words;           // packed words a block handles between two run-rotation barriers
 };
 
-constexpr int kPartTileIters = 2;                  // warp iterations per tile: 8 warps * 32 words * 2 = 512 words
 constexpr int kMaxParts = 4096;
 constexpr uint64_t kHole = ~0ULL;                  // word 0 of an unused run entry; real hashes equal to it are never binned
 
@@ -313,7 +312,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
                                                                    const uint32_t* __restrict__ ends, uint64_t w_begin,
                                                                    uint64_t w_end, uint64_t n_words, uint64_t n_bases) {
     constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
-    constexpr uint64_t kTileWords = (uint64_t)(kBlockThreads / 32) * 32 * kPartTileIters;
+    const uint64_t kTileWords = pv.tile_words;
     constexpr unsigned int kNoRun = 0xffffffffu;
     __shared__ unsigned int run_cur[kMaxParts];    // base of the current run (entry index inside the bin)
     __shared__ unsigned int run_next[kMaxParts];   // base of the next run
