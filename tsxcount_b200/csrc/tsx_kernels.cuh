@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
     const uint32_t R = pv.run;
+    const bool hole_possible = KW > 1 || tv.hp.nbits == 64;   // for 2k < 64 no hash has all 64 bits set
     LocalStats st;
 
     // k-mers that do not go through a bin.  Single GPU: inserted on the spot.  Routing: the table of the owner
@@ -355,7 +356,6 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
     // One k-mer per lane is kept "in flight": its shared-memory atomicAdd is issued when the k-mer is produced,
     // the returned index is consumed (bases read, hash stored) only when the NEXT k-mer of the lane has issued
     // its own atomic, so the ATOMS round trip overlaps a whole extraction + hash step.
-    const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
     Key<KW> pend_h;
 #pragma unroll
     for (int j = 0; j < KW; ++j) pend_h.w[j] = 0;
@@ -371,10 +371,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
         else pos = atomicAdd(pv.cursor + pend_p, 1ULL);   // both runs used up in one tile
         if (pos < pv.cap) {
             uint64_t* dst = pv.buf + ((uint64_t)pend_p * pv.cap + pos) * KW;
-            const bool last = KW >= 4 || ((pos * KW) & 3) == (4 - KW);   // entry that completes its 32-byte sector
-            const uint64_t pol = last ? pol_first : pol_last;
 #pragma unroll
-            for (int j = 0; j < KW; ++j) st_bin(dst + j, pend_h.w[j], pol);
+            for (int j = 0; j < KW; ++j) __stcg(dst + j, pend_h.w[j]);
         } else {
             cold(pend_h, 1);                              // bin full: never dropped
         }
@@ -391,7 +389,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
             for_each_kmer_group<KW, false>(win, ewin[0], first_end_after<NE>(ewin), base + lane, limit, tv.L.k, tv.hp,
                                            [&](const Key<KW>& key, uint64_t cnt) {
                                                const Key<KW> H = hash_key<KW>(key, tv.hp);
-                                               if (cnt >= 2 || H.w[0] == kHole) { cold(H, cnt); return; }
+                                               if (cnt >= 2 || (hole_possible && H.w[0] == kHole)) { cold(H, cnt); return; }
                                                const uint32_t p = (uint32_t)((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask;
                                                const unsigned int idx = atomicAdd(&run_fill[p], 1u);
                                                const unsigned int rc = run_cur[p], rn = run_next[p];   // stable until the barrier

@@ -100,7 +100,7 @@ inline bool make_layout(uint32_t k, uint32_t l, uint32_t s, uint32_t flags, uint
         const uint32_t body_cap = 64 * (W - 1);
         const uint32_t qh_min = Q > body_cap ? Q - body_cap : 0;
         const uint32_t fixed = 3 + R;
-        const uint32_t v_need = s > 0 ? s : 8;
+        const uint32_t v_need = s > 0 ? s : 4;
         if (qh_min + fixed + v_need > 64) continue;
         uint32_t V;
         if (exact) {
@@ -155,24 +155,6 @@ __device__ __forceinline__ void load_bucket(const uint64_t* b, uint64_t (&w)[4])
     const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(b));
     const ulonglong2 c = __ldcg(reinterpret_cast<const ulonglong2*>(b) + 1);
     w[0] = a.x; w[1] = a.y; w[2] = c.x; w[3] = c.y;
-}
-
-// Stores into the bins of the two-phase path.  The write frontier (one partially filled 32-byte sector per
-// (block, bin)) must survive in L2 until its last entry arrives, otherwise DRAM sees read-fills and repeated
-// partial write-backs (ncu: 20 B written + 9.5 B read per 8-byte hash).  Entries that do not complete a sector
-// are stored evict_last, the completing one evict_first.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void st_bin(uint64_t* p, uint64_t v, uint64_t policy) {
-    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(policy) : "memory");
 }
 
 __device__ __forceinline__ void prefetch_bucket_l2(const uint64_t* b) {
