@@ -166,8 +166,11 @@ typedef struct tsxc_route_layout_t {
     uint64_t block_words;         /* 64-bit words of the bins destined to ONE shard: bins_per_shard*bin_cap*KW */
     uint64_t spill_cap;           /* records per destination spill list */
 } tsxc_route_layout_t;
-/* Buffer geometry for chunks of at most max_chunk_words packed words (0 = library default). */
-int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, tsxc_route_layout_t* out);
+/* Buffer geometry for chunks of at most max_chunk_words packed words (0 = library default).
+ * kmers_per_position_q16: expected k-mers per base position in 1/65536 units, e.g. (len-k+1)/len for reads of one
+ * length (0 = 65536: every position starts a k-mer).  It only sizes the bins: an underestimate sends the excess
+ * through the spill lists and, if those fill up, makes tsxc_route_overflowed report the chunk for splitting. */
+int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, uint32_t kmers_per_position_q16, tsxc_route_layout_t* out);
 /* Build the read-boundary bitmap of a read batch (kept inside the handle until the next prepare). */
 int tsxc_route_prepare(tsxc_table* t, const uint64_t* d_offsets, uint64_t n_reads, uint64_t n_bases);
 /* Route packed words [w_begin, w_end) of the prepared batch.  d_bins: n_shards*block_words words,

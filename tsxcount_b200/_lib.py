@@ -86,7 +86,7 @@ PROTOTYPES = {
     "tsxc_dump": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _u64p]),
     "tsxc_dump_file": (C.c_int, [_vp, C.c_char_p]),
     "tsxc_stats": (C.c_int, [_vp, C.POINTER(TsxcStats)]),
-    "tsxc_route_layout": (C.c_int, [_vp, C.c_uint64, C.POINTER(TsxcRouteLayout)]),
+    "tsxc_route_layout": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.POINTER(TsxcRouteLayout)]),
     "tsxc_route_prepare": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64]),
     "tsxc_route_chunk": (C.c_int, [_vp, C.POINTER(TsxcRouteLayout), _vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
     "tsxc_route_overflowed": (C.c_int, [_vp, C.POINTER(C.c_int)]),

@@ -51,6 +51,7 @@ struct tsxc_table {
     unsigned long long* d_nout = nullptr;
     // region-partitioned insert (phase A bins)
     uint64_t* d_part = nullptr; size_t cap_part = 0;          // words
+    uint64_t* d_spill = nullptr; size_t cap_spill = 0;        // words: (hash, count) records of the single-GPU two-phase path
     unsigned long long* d_cursor = nullptr;                   // kMaxParts + 1 (last = ticket)
     uint32_t pbits = 0;                                        // log2(#regions); 0 = direct path only
     uint32_t region_log2 = 28;
@@ -151,7 +152,7 @@ int status_from_flags(tsxc_table* t, uint64_t flags) {
 //   cap    : bin capacity = mean + 12.5 % + the hole tails of every block (1.5 runs each) + slack
 struct PartGeom { uint32_t tile_words, run; int grid; uint64_t cap; };
 
-PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, int blocks_per_sm) {
+PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, int blocks_per_sm, double kmers_per_position = 1.0) {
     PartGeom g{};
     uint32_t iters = P >= 4096 ? 4 : 2;
     if (const char* e = std::getenv("TSXC_PART_ITERS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) iters = (uint32_t)v; }
@@ -165,7 +166,7 @@ PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, in
     if (const char* e = std::getenv("TSXC_PART_RUN")) { const int v = std::atoi(e); if (v >= 4 && v <= 65536) g.run = (uint32_t)v; }
     const uint64_t tiles = (chunk_words + g.tile_words - 1) / g.tile_words;
     g.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)t->sms * blocks_per_sm));
-    const uint64_t mean = 32 * chunk_words / P;
+    const uint64_t mean = (uint64_t)(32.0 * chunk_words * kmers_per_position / P) + 1;
     g.cap = mean + mean / 8 + 2ULL * (uint64_t)g.grid * g.run + 2048;
     g.cap = (g.cap + 7) & ~7ULL;
     return g;
@@ -179,11 +180,20 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     const uint64_t chunk_words = std::min<uint64_t>(n_words, (1ULL << 25) / L.KW);
     const PartGeom geo = part_geometry(t, P, chunk_words, t->part_blocks_per_sm);
     const uint64_t cap = geo.cap;
+    // spill list: one record per 8 positions is far more than homopolymer runs and bin tails ever need; inputs
+    // that exceed it (a handful of k-mers making up most of a chunk) are redone by the fused kernel below
+    const uint64_t spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 8);
     int rc = ensure(t, &t->d_part, &t->cap_part, (size_t)P * cap * L.KW);
     if (rc) return rc;
+    if ((rc = ensure(t, &t->d_spill, &t->cap_spill, (size_t)spill_cap * (L.KW + 1)))) return rc;
+    unsigned long long* ticket = t->d_cursor + kMaxParts;
+    unsigned long long* spill_n = t->d_cursor + kMaxParts + 1;
+    unsigned int* overflow = reinterpret_cast<unsigned int*>(t->d_cursor + kMaxParts + 2);
     PartView pv{};
     pv.buf = t->d_part; pv.cursor = t->d_cursor; pv.cap = cap;
     pv.pshift = L.LBl - t->pbits; pv.pmask = P - 1; pv.P = P; pv.run = geo.run; pv.tile_words = geo.tile_words;
+    pv.spill = t->d_spill; pv.spill_n = spill_n; pv.spill_cap = spill_cap; pv.bins_per_shard_log2 = t->pbits;
+    pv.overflow = overflow;
     const uint32_t slices = (uint32_t)((cap + kSliceEntries - 1) / kSliceEntries);
     const bool agg = !(L.flags & TSXC_FLAG_NO_WARP_AGG);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -191,24 +201,32 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     int main_launches = 0;
     for (uint64_t w0 = 0; w0 < n_words; w0 += chunk_words) {
         const uint64_t w1 = std::min(n_words, w0 + chunk_words);
-        CU(cudaMemsetAsync(t->d_cursor, 0, (kMaxParts + 1) * sizeof(unsigned long long), s));
+        CU(cudaMemsetAsync(t->d_cursor, 0, (kMaxParts + 8) * sizeof(unsigned long long), s));
         const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w1 - w0 + geo.tile_words - 1) / geo.tile_words, (uint64_t)geo.grid));
         const int grid_b = t->sms * 8;
         std::pair<cudaEvent_t, cudaEvent_t> eva, evb;
+        // phase A: bins + spill records, nothing inserted
         const bool ta = main_begin(t, s, &eva);
-#define M(KW_, W_) k_partition_reads<KW_, W_, false><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases)
-        TSX_DISPATCH(t->L, M);
-#undef M
+        switch (L.KW) {
+            case 1: k_partition_reads<1><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases); break;
+            case 2: k_partition_reads<2><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases); break;
+            default: k_partition_reads<4><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases); break;
+        }
         if (ta) { cudaEventRecord(eva.second, s); t->ev_part.push_back(eva); }
+        // phase B: bins, then the spill records; both skip when the chunk overflowed its spill list ...
         const bool tb = main_begin(t, s, &evb);
 #define M(KW_, W_)                                                                                                         \
-        if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, t->d_cursor + kMaxParts);  \
-        else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, t->d_cursor + kMaxParts)
+        if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket, overflow);  \
+        else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket, overflow);    \
+        k_add_hash_counts<KW_, W_><<<t->sms * 2, kBlockThreads, 0, s>>>(t->tv, t->d_spill, spill_cap, spill_n, overflow);  \
+        /* ... in which case the fused kernel redoes the whole chunk (it exits at once otherwise) */                       \
+        if (agg) k_count_reads<KW_, W_, true><<<t->sms * 8, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, w0, w1, n_words, n_bases, overflow); \
+        else k_count_reads<KW_, W_, false><<<t->sms * 8, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, w0, w1, n_words, n_bases, overflow)
         TSX_DISPATCH(t->L, M);
 #undef M
         if (tb) { cudaEventRecord(evb.second, s); t->ev_ins.push_back(evb); }
-        t->n_launches += 2;
-        main_launches += 2;
+        t->n_launches += 4;
+        main_launches += 4;
     }
     if (timed) main_end(t, s, ev, main_launches);
     CU(cudaGetLastError());
@@ -230,8 +248,8 @@ int launch_count_reads(tsxc_table* t, const uint64_t* d_packed, const uint64_t* 
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
 #define M(KW_, W_)                                                                                                    \
-    if (agg) k_count_reads<KW_, W_, true><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, n_words, n_bases);  \
-    else k_count_reads<KW_, W_, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, n_words, n_bases)
+    if (agg) k_count_reads<KW_, W_, true><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, 0, n_words, n_words, n_bases, nullptr);  \
+    else k_count_reads<KW_, W_, false><<<grid, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, 0, n_words, n_words, n_bases, nullptr)
     TSX_DISPATCH(t->L, M);
 #undef M
     t->n_launches++;
@@ -286,7 +304,7 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
             return bail(TSXC_E_CUDA);
         }
     }
-    if ((e = cudaMalloc(&h->d_cursor, (kMaxParts + 1) * sizeof(unsigned long long))) != cudaSuccess) {
+    if ((e = cudaMalloc(&h->d_cursor, (kMaxParts + 8) * sizeof(unsigned long long))) != cudaSuccess) {
         h->err = cudaGetErrorString(e);
         return bail(TSXC_E_NOMEM);
     }
@@ -303,16 +321,6 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
         h->pbits = table_log2 > h->region_log2 ? table_log2 - h->region_log2 : 0;
         if (h->pbits > 12) h->pbits = 12;   // kMaxParts bins
         if (h->pbits > L.LBl) h->pbits = L.LBl;
-    }
-    {
-        int a = 0, b = 0;
-#define M(KW_, W_)                                                                                                   \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_partition_reads<KW_, W_, false>, kBlockThreads, 0);          \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_partition_reads<KW_, W_, true>, kBlockThreads, 0)
-        TSX_DISPATCH(L, M);
-#undef M
-        if (a > 0) h->part_blocks_per_sm = a;
-        if (b > 0) h->route_blocks_per_sm = b;
     }
     h->tv = make_view(L, h->d_words, h->d_ctr);
     int rc = tsxc_clear(h);
@@ -433,7 +441,7 @@ int tsxc_destroy(tsxc_table* t) {
         for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& ev : t->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& m : t->marks) if (m) cudaEventDestroy(m);
-    cudaFree(t->d_part); cudaFree(t->d_cursor);
+    cudaFree(t->d_part); cudaFree(t->d_spill); cudaFree(t->d_cursor);
     cudaFree(t->d_ends); cudaFree(t->d_keys); cudaFree(t->d_counts); cudaFree(t->d_nout);
     cudaFree(t->d_ctr); cudaFree(t->d_words);
     if (t->stream) cudaStreamDestroy(t->stream);
@@ -666,7 +674,7 @@ int tsxc_dump_file(tsxc_table* t, const char* path) {
     return rc;
 }
 
-int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, tsxc_route_layout_t* out) {
+int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, uint32_t kmers_per_position_q16, tsxc_route_layout_t* out) {
     if (!t || !out) return fail(t, TSXC_E_INVALID, "null argument");
     const Layout& L = t->L;
     const uint32_t n_shards = 1u << L.shard_bits;
@@ -676,7 +684,8 @@ int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, tsxc_route_layout
     if (n_shards > (uint32_t)kMaxParts) return fail(t, TSXC_E_UNSUPPORTED, "too many shards");
     const uint64_t chunk_words = max_chunk_words ? max_chunk_words : (1ULL << 24) / L.KW;
     const uint32_t P = n_shards << pb;
-    const uint64_t cap = part_geometry(t, P, chunk_words, t->route_blocks_per_sm).cap;
+    const double frac = kmers_per_position_q16 ? std::min(1.0, kmers_per_position_q16 / 65536.0) : 1.0;
+    const uint64_t cap = part_geometry(t, P, chunk_words, t->route_blocks_per_sm, frac).cap;
     std::memset(out, 0, sizeof *out);
     out->n_shards = n_shards; out->bins_per_shard = 1u << pb; out->key_words = L.KW; out->spill_record_words = L.KW + 1;
     out->chunk_words = chunk_words; out->bin_cap = cap; out->block_words = ((uint64_t)1 << pb) * cap * L.KW;
@@ -723,12 +732,15 @@ int tsxc_route_chunk(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64
     pv.pshift = L.LBl - pb; pv.pmask = P - 1; pv.P = P;
     pv.run = geo.run; pv.tile_words = geo.tile_words;
     pv.spill = d_spill; pv.spill_n = d_spill_n; pv.spill_cap = lay->spill_cap; pv.bins_per_shard_log2 = pb;
+    pv.overflow = reinterpret_cast<unsigned int*>(t->d_cursor + kMaxParts + 3);   // host path reads ERR_SEND_OVERFLOW instead
     const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w_end - w_begin + geo.tile_words - 1) / geo.tile_words, (uint64_t)geo.grid));
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
-#define M(KW_, W_) k_partition_reads<KW_, W_, true><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases)
-    TSX_DISPATCH(t->L, M);
-#undef M
+    switch (L.KW) {
+        case 1: k_partition_reads<1><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases); break;
+        case 2: k_partition_reads<2><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases); break;
+        default: k_partition_reads<4><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases); break;
+    }
     t->n_launches++;
     if (timed) { cudaEventRecord(ev.second, s); t->ev_part.push_back(ev); t->n_main_launches++; }
     CU(cudaGetLastError());
@@ -768,8 +780,8 @@ int tsxc_insert_routed(tsxc_table* t, const tsxc_route_layout_t* lay, const uint
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
 #define M(KW_, W_)                                                                                        \
-    if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket); \
-    else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket)
+    if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket, nullptr); \
+    else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket, nullptr)
     TSX_DISPATCH(t->L, M);
 #undef M
     t->n_launches++;
@@ -784,7 +796,7 @@ int tsxc_add_hash_counts_device(tsxc_table* t, const uint64_t* d_records, uint64
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
     const int grid = grid_for(t, n);
-#define M(KW_, W_) k_add_hash_counts<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_records, n)
+#define M(KW_, W_) k_add_hash_counts<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_records, n, nullptr, nullptr)
     TSX_DISPATCH(t->L, M);
 #undef M
     t->n_launches++;

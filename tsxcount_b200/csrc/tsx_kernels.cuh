@@ -136,22 +136,27 @@ __device__ __forceinline__ uint32_t first_end_after(const uint32_t (&ewin)[NE + 
 }
 
 // ---- K1+K2 fused: count every k-mer of a packed read batch -------------------------------------
+// Words [w_begin, w_end) of the batch.  only_if != nullptr: the launch is the fallback of a two-phase chunk and
+// does nothing unless *only_if is set (see launch_count_reads_partitioned).
 template <int KW, int W, bool WARP_AGG>
 __global__ void __launch_bounds__(kBlockThreads) k_count_reads(const __grid_constant__ TableView tv, const uint64_t* __restrict__ packed,
-                                                               const uint32_t* __restrict__ ends, uint64_t n_words,
-                                                               uint64_t n_bases) {
+                                                               const uint32_t* __restrict__ ends, uint64_t w_begin, uint64_t w_end,
+                                                               uint64_t n_words, uint64_t n_bases,
+                                                               const unsigned int* __restrict__ only_if) {
     constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);  // end-bitmap words of look-ahead: ceil((k-1)/32)
+    if (only_if && __ldcg(only_if) == 0) return;
     const unsigned lane = threadIdx.x & 31u;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     LocalStats st;
-    for (uint64_t base = warp * 32; base < n_words; base += n_warps * 32) {
+    for (uint64_t base = w_begin + warp * 32; base < w_end; base += n_warps * 32) {
         uint64_t win[KW + 1];
         uint32_t ewin[NE + 1];
         load_window<KW, uint64_t>(packed, base, n_words, lane, win);
         load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
         const uint32_t dist_after = first_end_after<NE>(ewin);
-        for_each_kmer_group<KW, WARP_AGG>(win, ewin[0], dist_after, base + lane, n_bases, tv.L.k, tv.hp,
+        const uint64_t limit = (base + lane < w_end) ? n_bases : 0;   // lanes past the range emit nothing
+        for_each_kmer_group<KW, WARP_AGG>(win, ewin[0], dist_after, base + lane, limit, tv.L.k, tv.hp,
                                           [&](const Key<KW>& key, uint64_t cnt) {
                                               insert_hashed<KW, W>(tv, hash_key<KW>(key, tv.hp), cnt, st);
                                           });
@@ -293,6 +298,7 @@ struct PartView {
     uint64_t spill_cap;
     uint32_t bins_per_shard_log2;
     uint32_t tile_words;           // packed words a block handles between two run-rotation barriers
+    unsigned int* overflow;        // set to 1 when a spill list ran out of room: the chunk's bins are incomplete
 };
 
 constexpr int kMaxParts = 4096;
@@ -305,7 +311,7 @@ constexpr uint64_t kHole = ~0ULL;                  // word 0 of an unused run en
 // thread reads after its atomicAdd are always the ones its index refers to.  A tile brings ~run/4 k-mers per
 // bin, so both runs running out inside one tile is a tail event; those k-mers take single entries straight
 // from the global cursor.  Unused tails of the runs a block still owns at the end are filled with holes.
-template <int KW, int W, bool ROUTE>
+template <int KW>
 __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_constant__ TableView tv,
                                                                    const __grid_constant__ PartView pv,
                                                                    const uint64_t* __restrict__ packed,
@@ -314,8 +320,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
     constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
     const uint64_t kTileWords = pv.tile_words;
     constexpr unsigned int kNoRun = 0xffffffffu;
-    __shared__ unsigned int run_cur[kMaxParts];    // base of the current run (entry index inside the bin)
-    __shared__ unsigned int run_next[kMaxParts];   // base of the next run
+    // bases of the current (.x) and the next (.y) run of every bin as one 8-byte word: one LDS per k-mer; the
+    // kernel is bound by the shared-memory pipe (ATOMS + LDS + the global store), not by occupancy
+    __shared__ uint2 run_base[kMaxParts];
     __shared__ unsigned int run_fill[kMaxParts];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
@@ -323,14 +330,14 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
     const bool hole_possible = KW > 1 || tv.hp.nbits == 64;   // for 2k < 64 no hash has all 64 bits set
     LocalStats st;
 
-    // k-mers that do not go through a bin.  Single GPU: inserted on the spot.  Routing: the table of the owner
-    // lives on another GPU, so they become (hash, count) records of the owner's spill list; a full spill list
-    // raises ERR_SEND_OVERFLOW and the host repeats the chunk in smaller pieces (nothing has been inserted yet).
+    // k-mers that do not go through a bin (groups the extractor already aggregated, k-mers whose bin is full, a
+    // hash equal to the hole marker) become (hash, count) records of the owner's spill list.  The kernel never
+    // touches the table: if a spill list runs out of room it raises pv.overflow (and ERR_SEND_OVERFLOW) and the
+    // chunk is redone — by the fused kernel on a single GPU, in smaller pieces by the multi-GPU host loop.
     auto cold = [&](const Key<KW>& H, uint64_t cnt) {
-        if (!ROUTE) { insert_hashed<KW, W>(tv, H, cnt, st); return; }
         const uint32_t owner = (uint32_t)(((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask) >> pv.bins_per_shard_log2;
         const unsigned long long at = atomicAdd(pv.spill_n + owner, 1ULL);
-        if (at >= pv.spill_cap) { st.errors |= ERR_SEND_OVERFLOW; return; }
+        if (at >= pv.spill_cap) { st.errors |= ERR_SEND_OVERFLOW; *pv.overflow = 1u; return; }
         uint64_t* dst = pv.spill + ((uint64_t)owner * pv.spill_cap + at) * (KW + 1);
 #pragma unroll
         for (int j = 0; j < KW; ++j) dst[j] = H.w[j];
@@ -349,7 +356,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
     };
 
     for (uint32_t p = threadIdx.x; p < pv.P; p += blockDim.x) {
-        run_cur[p] = reserve(p); run_next[p] = reserve(p); run_fill[p] = 0;
+        const unsigned int c = reserve(p), n = reserve(p);
+        run_base[p] = make_uint2(c, n); run_fill[p] = 0;
     }
     __syncthreads();
 
@@ -392,46 +400,46 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
                                                if (cnt >= 2 || (hole_possible && H.w[0] == kHole)) { cold(H, cnt); return; }
                                                const uint32_t p = (uint32_t)((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask;
                                                const unsigned int idx = atomicAdd(&run_fill[p], 1u);
-                                               const unsigned int rc = run_cur[p], rn = run_next[p];   // stable until the barrier
+                                               const uint2 rb2 = run_base[p];                          // stable until the barrier
+                                               const unsigned int rc = rb2.x, rn = rb2.y;
                                                complete();                 // the previous k-mer of this lane
                                                pend_h = H; pend_p = p; pend_idx = idx; pend_cur = rc; pend_next = rn; pend = true;
                                            });
         }
         complete();   // the runs must not rotate under an index that is still in flight
         __syncthreads();
-        // rotate the runs whose current one was used up during this tile; the reservations of one thread are
-        // issued back to back (kMaxParts / kBlockThreads independent global atomics), then consumed
-        constexpr int kPer = kMaxParts / kBlockThreads;
-        unsigned long long nb[kPer];
-        bool rot[kPer];
+        // rotate the runs whose current one was used up during this tile; a thread issues its reservations four
+        // at a time (independent global atomics), then consumes them
+        constexpr int kBatch = 4;
+        for (uint32_t p0 = threadIdx.x; p0 < pv.P; p0 += kBatch * kBlockThreads) {
+            unsigned long long nb[kBatch];
+            bool rot[kBatch];
 #pragma unroll
-        for (int i = 0; i < kPer; ++i) {
-            const uint32_t p = threadIdx.x + i * kBlockThreads;
-            rot[i] = p < pv.P && run_fill[p] >= R;
-            nb[i] = rot[i] ? atomicAdd(pv.cursor + p, (unsigned long long)R) : 0ULL;
-        }
+            for (int i = 0; i < kBatch; ++i) {
+                const uint32_t p = p0 + i * kBlockThreads;
+                rot[i] = p < pv.P && run_fill[p] >= R;
+                nb[i] = rot[i] ? atomicAdd(pv.cursor + p, (unsigned long long)R) : 0ULL;
+            }
 #pragma unroll
-        for (int i = 0; i < kPer; ++i) {
-            if (!rot[i]) continue;
-            const uint32_t p = threadIdx.x + i * kBlockThreads;
-            const unsigned int f = run_fill[p];
-            run_cur[p] = run_next[p];
-            run_fill[p] = (f < 2 * R ? f : 2 * R) - R;
-            if (nb[i] + R <= pv.cap) {
-                run_next[p] = (unsigned int)nb[i];
-            } else {
-                run_next[p] = kNoRun;
-                for (unsigned long long j = nb[i]; j < pv.cap; ++j) __stcg(pv.buf + ((uint64_t)p * pv.cap + j) * KW, kHole);
+            for (int i = 0; i < kBatch; ++i) {
+                if (!rot[i]) continue;
+                const uint32_t p = p0 + i * kBlockThreads;
+                const unsigned int f = run_fill[p];
+                run_fill[p] = (f < 2 * R ? f : 2 * R) - R;
+                unsigned int fresh = kNoRun;
+                if (nb[i] + R <= pv.cap) fresh = (unsigned int)nb[i];
+                else for (unsigned long long j = nb[i]; j < pv.cap; ++j) __stcg(pv.buf + ((uint64_t)p * pv.cap + j) * KW, kHole);
+                run_base[p] = make_uint2(run_base[p].y, fresh);
             }
         }
         __syncthreads();
     }
     for (uint32_t p = threadIdx.x; p < pv.P; p += blockDim.x) {
         const unsigned int f = run_fill[p];
-        fill_holes(p, run_cur[p], f < R ? f : R);
-        fill_holes(p, run_next[p], f < R ? 0u : (f < 2 * R ? f - R : R));
+        fill_holes(p, run_base[p].x, f < R ? f : R);
+        fill_holes(p, run_base[p].y, f < R ? 0u : (f < 2 * R ? f - R : R));
     }
-    flush_stats(tv, st);
+    if (st.errors) atomicOr(tv.ctr + CTR_ERRORS, (unsigned long long)st.errors);
 }
 
 // phase B: work item = (bin, slice of kSliceEntries entries); items are numbered bin-major and handed out
@@ -442,9 +450,11 @@ template <int KW, int W, bool WARP_AGG>
 __global__ void __launch_bounds__(kBlockThreads) k_insert_partitions(const __grid_constant__ TableView tv,
                                                                      const __grid_constant__ PartView pv,
                                                                      uint32_t slices_per_bin,
-                                                                     unsigned long long* __restrict__ ticket) {
+                                                                     unsigned long long* __restrict__ ticket,
+                                                                     const unsigned int* __restrict__ skip_if) {
     const unsigned full = 0xffffffffu;
     __shared__ unsigned long long item_s;
+    if (skip_if && __ldcg(skip_if) != 0) return;     // the chunk overflowed its spill list and is being redone
     LocalStats st;
     const unsigned long long n_items = (unsigned long long)pv.P * slices_per_bin;
     while (true) {
@@ -485,9 +495,14 @@ __global__ void __launch_bounds__(kBlockThreads) k_insert_partitions(const __gri
 }
 
 // (hash, count) records: the spill lists of the routing path
+// n_dev != nullptr: the record count lives on the device (min(*n_dev, n) records are read)
 template <int KW, int W>
 __global__ void __launch_bounds__(kBlockThreads) k_add_hash_counts(const __grid_constant__ TableView tv,
-                                                                   const uint64_t* __restrict__ rec, uint64_t n) {
+                                                                   const uint64_t* __restrict__ rec, uint64_t n,
+                                                                   const unsigned long long* __restrict__ n_dev,
+                                                                   const unsigned int* __restrict__ skip_if) {
+    if (skip_if && __ldcg(skip_if) != 0) return;
+    if (n_dev) { const unsigned long long m = __ldcg(n_dev); if (m < n) n = m; }
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     LocalStats st;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {

@@ -121,9 +121,10 @@ class TSXHashMapCUDA:
         _lib.check(self._lib.tsxc_add_hashes_device(self._h, d_hashes, n), self._h)
 
     # -- multi-GPU routing (see include/tsxcount_cuda.h "multi-GPU routing") ------------------------
-    def routeLayout(self, max_chunk_words=0):
+    def routeLayout(self, max_chunk_words=0, kmers_per_position=1.0):
         lay = _lib.TsxcRouteLayout()
-        _lib.check(self._lib.tsxc_route_layout(self._h, max_chunk_words, C.byref(lay)), self._h)
+        q16 = max(1, min(65536, int(round(kmers_per_position * 65536))))
+        _lib.check(self._lib.tsxc_route_layout(self._h, max_chunk_words, q16, C.byref(lay)), self._h)
         return lay
 
     def routePrepare(self, d_offsets, n_reads, n_bases):

@@ -28,11 +28,11 @@ from .hashmap import TSXHashMapCUDA
 class CudaBackend:
     """Device buffers are torch tensors; kernels run on the handle's own stream."""
 
-    def __init__(self, k, l_global, s, rank, world, device, flags=0, max_chunk_words=0):
+    def __init__(self, k, l_global, s, rank, world, device, flags=0, max_chunk_words=0, kmers_per_position=1.0):
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         self.hm = TSXHashMapCUDA(l_global, s, k, device=device, flags=flags, shard_rank=rank, n_shards=world)
-        self.lay = self.hm.routeLayout(max_chunk_words)
+        self.lay = self.hm.routeLayout(max_chunk_words, kmers_per_position)
         self.kw = self.lay.key_words
         self.stream = torch.cuda.ExternalStream(self.hm._lib.tsxc_stream(self.hm.handle), device=self.device)
         self.comm_stream = torch.cuda.Stream(device=self.device)
@@ -222,7 +222,9 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None):
     gp = _lib.TsxcGenParams(wl["seed"], n_reads * world, read_len, wl["mode"], wl["genome"], wl["sub"], 0)
     _lib.check(lib.tsxc_gen_reads_device(C.byref(gp), rank * n_reads, n_reads, local_rank, None, d_packed.data_ptr(), d_off.data_ptr()))
     torch.cuda.synchronize()
-    be = CudaBackend(k, l_global, 0, rank, world, local_rank)
+    # bins are sized for the k-mers a read of this length yields (+2 %); anything beyond goes through the spill path
+    be = CudaBackend(k, l_global, 0, rank, world, local_rank,
+                     kmers_per_position=min(1.0, 1.02 * max(0, read_len - k + 1) / read_len))
     sc = ShardedCounter(be, rank, world)
     layout = be.hm.stats()
 
