@@ -429,3 +429,17 @@ def test_reference_pinned_fixtures(tsx, tmp_path):
             keys, counts = hm.getAllKmers()
             got = {tsx.sequtils.to_sequence(kk, k): int(c) for kk, c in zip(keys, counts)}
             assert got == want, name
+
+
+def test_two_phase_spill_overflow_falls_back_to_the_fused_kernel(tsx, small_regions):
+    """24 distinct 12-mers over 128 bins: every bin that receives a k-mer overflows, the spill list overflows too;
+    the chunk must then be redone by the fused kernel on the device - same counts, no error."""
+    seqs = [(b"A" * 13 + b"C" * 13) * 200] * 300
+    oc = orc.count_seqs(seqs, 12)
+    assert oc.n_distinct == 24
+    with tsx.TSXHashMapCUDA(20, 4, 12, flags=tsx.TSXC_FLAG_EXACT_S) as hm:
+        hm.addSequences(seqs)
+        assert hm.stats()["main_kernel_launches"] >= 4     # partition, insert, spill drain, fused fallback
+        check_against_oracle(tsx, hm, oc)
+        hm.addSequences(seqs[:50])                         # and the table stays usable afterwards
+        assert hm.getKmerCount() == 24

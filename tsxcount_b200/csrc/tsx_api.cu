@@ -732,7 +732,8 @@ int tsxc_route_chunk(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64
     pv.pshift = L.LBl - pb; pv.pmask = P - 1; pv.P = P;
     pv.run = geo.run; pv.tile_words = geo.tile_words;
     pv.spill = d_spill; pv.spill_n = d_spill_n; pv.spill_cap = lay->spill_cap; pv.bins_per_shard_log2 = pb;
-    pv.overflow = reinterpret_cast<unsigned int*>(t->d_cursor + kMaxParts + 3);   // host path reads ERR_SEND_OVERFLOW instead
+    pv.overflow = reinterpret_cast<unsigned int*>(t->d_cursor + kMaxParts + 3);   // read back by tsxc_route_overflowed
+    CU(cudaMemsetAsync(pv.overflow, 0, sizeof(unsigned long long), s));
     const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w_end - w_begin + geo.tile_words - 1) / geo.tile_words, (uint64_t)geo.grid));
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
@@ -752,13 +753,10 @@ int tsxc_route_overflowed(tsxc_table* t, int* overflowed) {
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
     CU(cudaStreamSynchronize(t->stream));
-    unsigned long long flags = 0;
-    CU(cudaMemcpy(&flags, t->d_ctr + CTR_ERRORS, sizeof flags, cudaMemcpyDeviceToHost));
-    *overflowed = (flags & ERR_SEND_OVERFLOW) ? 1 : 0;
-    if (*overflowed) {
-        flags &= ~(unsigned long long)ERR_SEND_OVERFLOW;
-        CU(cudaMemcpy(t->d_ctr + CTR_ERRORS, &flags, sizeof flags, cudaMemcpyHostToDevice));
-    }
+    unsigned long long flag = 0;
+    CU(cudaMemcpy(&flag, t->d_cursor + kMaxParts + 3, sizeof flag, cudaMemcpyDeviceToHost));
+    *overflowed = flag ? 1 : 0;
+    if (flag) CU(cudaMemset(t->d_cursor + kMaxParts + 3, 0, sizeof flag));
     return TSXC_OK;
 }
 

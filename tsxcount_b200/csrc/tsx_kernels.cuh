@@ -332,12 +332,12 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
 
     // k-mers that do not go through a bin (groups the extractor already aggregated, k-mers whose bin is full, a
     // hash equal to the hole marker) become (hash, count) records of the owner's spill list.  The kernel never
-    // touches the table: if a spill list runs out of room it raises pv.overflow (and ERR_SEND_OVERFLOW) and the
+    // touches the table: if a spill list runs out of room it raises pv.overflow and the
     // chunk is redone — by the fused kernel on a single GPU, in smaller pieces by the multi-GPU host loop.
     auto cold = [&](const Key<KW>& H, uint64_t cnt) {
         const uint32_t owner = (uint32_t)(((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask) >> pv.bins_per_shard_log2;
         const unsigned long long at = atomicAdd(pv.spill_n + owner, 1ULL);
-        if (at >= pv.spill_cap) { st.errors |= ERR_SEND_OVERFLOW; *pv.overflow = 1u; return; }
+        if (at >= pv.spill_cap) { *pv.overflow = 1u; return; }
         uint64_t* dst = pv.spill + ((uint64_t)owner * pv.spill_cap + at) * (KW + 1);
 #pragma unroll
         for (int j = 0; j < KW; ++j) dst[j] = H.w[j];
@@ -439,7 +439,6 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
         fill_holes(p, run_base[p].x, f < R ? f : R);
         fill_holes(p, run_base[p].y, f < R ? 0u : (f < 2 * R ? f - R : R));
     }
-    if (st.errors) atomicOr(tv.ctr + CTR_ERRORS, (unsigned long long)st.errors);
 }
 
 // phase B: work item = (bin, slice of kSliceEntries entries); items are numbered bin-major and handed out
