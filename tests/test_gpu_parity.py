@@ -443,3 +443,38 @@ def test_two_phase_spill_overflow_falls_back_to_the_fused_kernel(tsx, small_regi
         check_against_oracle(tsx, hm, oc)
         hm.addSequences(seqs[:50])                         # and the table stays usable afterwards
         assert hm.getKmerCount() == 24
+
+
+# ---- the default two-phase configuration at a size the oracle cannot count: size-independent properties ----
+def test_large_default_path_properties(tsx):
+    """2.4e8 uniform 31-mers into a 4 GiB table (16 regions of 256 MiB, the default geometry, several chunks of
+    host batches).  Properties: every k-mer is added exactly once (sum of counts), all are distinct (a duplicate
+    has probability ~1e-2 at this size), sampled k-mers regenerated by the oracle are present with count 1 and
+    absent ones with 0; a second pass doubles every sampled count and leaves the distinct count unchanged."""
+    lib = tsx._lib.load()
+    n_reads, read_len, k = 2_000_000, 150, 31
+    n_bases = n_reads * read_len
+    n_words = (n_bases + 31) // 32
+    n_kmers = n_reads * (read_len - k + 1)
+    d_packed, d_off = C.c_void_p(), C.c_void_p()
+    tsx._lib.check(lib.tsxc_device_alloc(0, (n_words + 8) * 8, C.byref(d_packed)))
+    tsx._lib.check(lib.tsxc_device_alloc(0, (n_reads + 1) * 8, C.byref(d_off)))
+    try:
+        gp = tsx.TsxcGenParams(0xBEEF, n_reads, read_len, 0, 0, 0, 0)
+        tsx._lib.check(lib.tsxc_gen_reads_device(C.byref(gp), 0, n_reads, 0, None, d_packed, d_off))
+        sample = orc.gen_reads(seed=0xBEEF, n_reads=n_reads, read_len=read_len, mode=0, first=777_000, count=300)
+        oc = orc.count_seqs(sample, k)
+        other = orc.count_seqs(orc.gen_reads(seed=0xBEEF + 1, n_reads=10, read_len=read_len, mode=0), k)
+        with tsx.TSXHashMapCUDA(29, 0, k) as hm:
+            for rep in (1, 2):
+                hm.addReadsDevice(d_packed, d_off, n_reads, n_bases)
+                hm.sync()
+                st = hm.stats()
+                assert st["error_flags"] == 0 and st["kmers_added"] == rep * n_kmers
+                assert st["distinct"] == n_kmers
+                assert st["main_kernel_launches"] >= 4 * rep          # the two-phase path ran
+                assert np.array_equal(hm.getKmerCounts(oc.keys_kw(1)), rep * oc.counts)
+                assert hm.getKmerCounts(other.keys_kw(1)).sum() == 0
+    finally:
+        lib.tsxc_device_free(0, d_packed)
+        lib.tsxc_device_free(0, d_off)
