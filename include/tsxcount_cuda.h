@@ -191,6 +191,23 @@ int tsxc_add_hash_counts_device(tsxc_table* t, const uint64_t* d_records, uint64
 /* Insert n already-hashed k-mers (KW words each) owned by this shard. */
 int tsxc_add_hashes_device(tsxc_table* t, const uint64_t* d_hashes, uint64_t n);
 
+/* ---- peer-memory plumbing for the multi-GPU exchange (one process per GPU) ------------------------ */
+/* Bin blocks travel to their owner with copy-engine peer copies over NVLink instead of a staged NCCL all-to-all:
+ * the owner exports its receive buffer (CUDA IPC), senders open it and cudaMemcpyAsync straight into it; two
+ * inter-process events per buffer set order "copies landed" -> insert and "buffer drained" -> next copies.
+ * All handles are 64 opaque bytes (cudaIpcMemHandle_t / cudaIpcEventHandle_t). */
+#define TSXC_IPC_HANDLE_BYTES 64
+int tsxc_ipc_export_mem(int device, void* dptr, unsigned char* handle_out);
+int tsxc_ipc_open_mem(int device, const unsigned char* handle, void** dptr_out);
+int tsxc_ipc_close_mem(int device, void* dptr);
+int tsxc_ipc_event_create(int device, void** event_out, unsigned char* handle_out);
+int tsxc_ipc_event_open(int device, const unsigned char* handle, void** event_out);
+int tsxc_event_destroy(int device, void* event);
+int tsxc_event_record(int device, void* event, void* stream);
+int tsxc_stream_wait_event(int device, void* stream, void* event);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): dst may be a peer pointer from tsxc_ipc_open_mem. */
+int tsxc_copy_async(int device, void* dst, const void* src, uint64_t bytes, void* stream);
+
 /* ---- host-side packing (replaces TSXSeqUtils::fromSequence on the feeder side) ----------- */
 /* 2-bit packs ASCII reads.  Non-ACGT bytes cannot be packed: each maximal ACGT run becomes its own
  * segment, which is exactly "skip every k-mer that spans a non-ACGT base" (the reference substitutes

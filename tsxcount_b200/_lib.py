@@ -103,6 +103,15 @@ PROTOTYPES = {
     "tsxc_device_alloc": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(_vp)]),
     "tsxc_device_free": (C.c_int, [C.c_int, _vp]),
     "tsxc_memcpy": (C.c_int, [C.c_int, _vp, _vp, C.c_uint64, C.c_int]),
+    "tsxc_ipc_export_mem": (C.c_int, [C.c_int, _vp, _vp]),
+    "tsxc_ipc_open_mem": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "tsxc_ipc_close_mem": (C.c_int, [C.c_int, _vp]),
+    "tsxc_ipc_event_create": (C.c_int, [C.c_int, C.POINTER(_vp), _vp]),
+    "tsxc_ipc_event_open": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "tsxc_event_destroy": (C.c_int, [C.c_int, _vp]),
+    "tsxc_event_record": (C.c_int, [C.c_int, _vp, _vp]),
+    "tsxc_stream_wait_event": (C.c_int, [C.c_int, _vp, _vp]),
+    "tsxc_copy_async": (C.c_int, [C.c_int, _vp, _vp, C.c_uint64, _vp]),
     "tsxc_debug_hash": (C.c_int, [C.c_uint32, _vp, _vp]),
     "tsxc_debug_unhash": (C.c_int, [C.c_uint32, _vp, _vp]),
     "tsxc_debug_layout": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(TsxcStats)]),

@@ -858,6 +858,83 @@ int tsxc_memcpy(int device, void* dst, const void* src, uint64_t bytes, int kind
     return TSXC_OK;
 }
 
+int tsxc_ipc_export_mem(int device, void* dptr, unsigned char* handle_out) {
+    tsxc_table* t = nullptr;
+    if (!dptr || !handle_out) return TSXC_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == TSXC_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, dptr));
+    std::memcpy(handle_out, &h, sizeof h);
+    return TSXC_OK;
+}
+int tsxc_ipc_open_mem(int device, const unsigned char* handle, void** dptr_out) {
+    tsxc_table* t = nullptr;
+    if (!handle || !dptr_out) return TSXC_E_INVALID;
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    CU(cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return TSXC_OK;
+}
+int tsxc_ipc_close_mem(int device, void* dptr) {
+    tsxc_table* t = nullptr;
+    CU(cudaSetDevice(device));
+    if (dptr) CU(cudaIpcCloseMemHandle(dptr));
+    return TSXC_OK;
+}
+int tsxc_ipc_event_create(int device, void** event_out, unsigned char* handle_out) {
+    tsxc_table* t = nullptr;
+    if (!event_out || !handle_out) return TSXC_E_INVALID;
+    static_assert(sizeof(cudaIpcEventHandle_t) == TSXC_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(device));
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventInterprocess));
+    cudaIpcEventHandle_t h;
+    CU(cudaIpcGetEventHandle(&h, ev));
+    std::memcpy(handle_out, &h, sizeof h);
+    *event_out = (void*)ev;
+    return TSXC_OK;
+}
+int tsxc_ipc_event_open(int device, const unsigned char* handle, void** event_out) {
+    tsxc_table* t = nullptr;
+    if (!handle || !event_out) return TSXC_E_INVALID;
+    CU(cudaSetDevice(device));
+    cudaIpcEventHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    cudaEvent_t ev;
+    CU(cudaIpcOpenEventHandle(&ev, h));
+    *event_out = (void*)ev;
+    return TSXC_OK;
+}
+int tsxc_event_destroy(int device, void* event) {
+    tsxc_table* t = nullptr;
+    CU(cudaSetDevice(device));
+    if (event) CU(cudaEventDestroy((cudaEvent_t)event));
+    return TSXC_OK;
+}
+int tsxc_event_record(int device, void* event, void* stream) {
+    tsxc_table* t = nullptr;
+    if (!event) return TSXC_E_INVALID;
+    CU(cudaSetDevice(device));
+    CU(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return TSXC_OK;
+}
+int tsxc_stream_wait_event(int device, void* stream, void* event) {
+    tsxc_table* t = nullptr;
+    if (!event) return TSXC_E_INVALID;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+    return TSXC_OK;
+}
+int tsxc_copy_async(int device, void* dst, const void* src, uint64_t bytes, void* stream) {
+    tsxc_table* t = nullptr;
+    if ((!dst || !src) && bytes) return TSXC_E_INVALID;
+    CU(cudaSetDevice(device));
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return TSXC_OK;
+}
+
 int tsxc_k0_random_rmw(tsxc_table* t, uint64_t table_bytes, uint64_t n_ops, int mode, float* ms_out) {
     if (!t || !ms_out) return fail(t, TSXC_E_INVALID, "null argument");
     std::lock_guard<std::mutex> g(t->mu);

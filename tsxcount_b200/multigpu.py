@@ -36,6 +36,7 @@ class CudaBackend:
         self.kw = self.lay.key_words
         self.stream = torch.cuda.ExternalStream(self.hm._lib.tsxc_stream(self.hm.handle), device=self.device)
         self.comm_stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)   # peer copies (copy engines)
 
     # buffers -----------------------------------------------------------------------------------------
     def alloc_u64(self, n):
@@ -68,6 +69,107 @@ class CudaBackend:
         return self.hm.getKmerCount()
 
 
+class RawBuf:
+    """A cudaMalloc'ed buffer (exportable through CUDA IPC) with the one tensor method the counter needs."""
+
+    def __init__(self, lib, device, nbytes):
+        self.lib, self.device, self.nbytes = lib, device, int(nbytes)
+        self.ptr = C.c_void_p()
+        _lib.check(lib.tsxc_device_alloc(device, max(self.nbytes, 8), C.byref(self.ptr)))
+
+    def data_ptr(self):
+        return self.ptr.value
+
+    def free(self):
+        if self.ptr.value:
+            self.lib.tsxc_device_free(self.device, self.ptr)
+            self.ptr = C.c_void_p()
+
+
+class PeerExchange:
+    """Optional exchange (TSXC_EXCHANGE=peer; the default is NCCL): bin blocks go to their owner with copy-engine
+    peer copies over NVLink (no SMs, no staging).  Measured on 8 B200s it is SLOWER than the NCCL all-to-all
+    (762 vs 730 ms per step): the copies run at full link speed and take HBM bandwidth from the routing kernel
+    (332 vs 294 ms), which is what the exchange overlaps with.  Kept because it is the building block for the
+    next step (routing kernel storing straight into peer memory).  Mechanics:
+    the owner's receive buffers are CUDA-IPC mapped into every sender; per buffer set two inter-process events
+    order `copies landed -> insert` and `buffer drained -> next copies`.  The ordering of the event calls across
+    processes comes from the small host-synchronised collectives every chunk performs anyway (see
+    ShardedCounter.add_reads_device).  Raises at construction if IPC is unavailable; the caller then falls back to
+    NCCL (collectively)."""
+
+    H = 64
+
+    def __init__(self, be, rank, world, group, lay):
+        self.be, self.rank, self.world = be, rank, world
+        lib, dev = be.hm._lib, be.device.index
+        self.lib, self.dev = lib, dev
+        self.block_bytes = lay.block_words * 8
+        self.cur_bytes = lay.bins_per_shard * 8
+        self.recv_bins = [RawBuf(lib, dev, world * self.block_bytes) for _ in range(2)]
+        self.recv_cur = [RawBuf(lib, dev, world * self.cur_bytes) for _ in range(2)]
+        mine = torch.zeros(8, self.H, dtype=torch.uint8)
+        self.ev_sent, self.ev_drained = [], []
+        for b in range(2):
+            for j, buf in ((0, self.recv_bins[b]), (1, self.recv_cur[b])):
+                h = (C.c_ubyte * self.H)()
+                _lib.check(lib.tsxc_ipc_export_mem(dev, buf.ptr, h))
+                mine[2 * b + j] = torch.tensor(list(h), dtype=torch.uint8)
+            for j, store in ((0, self.ev_sent), (1, self.ev_drained)):
+                ev, h = C.c_void_p(), (C.c_ubyte * self.H)()
+                _lib.check(lib.tsxc_ipc_event_create(dev, C.byref(ev), h))
+                store.append(ev)
+                mine[4 + 2 * b + j] = torch.tensor(list(h), dtype=torch.uint8)
+        allh = torch.empty(world, 8, self.H, dtype=torch.uint8, device=be.device)
+        dist.all_gather_into_tensor(allh, mine.to(be.device), group=group)
+        allh = allh.cpu()
+        self.peer_bins = [[None, None] for _ in range(world)]
+        self.peer_cur = [[None, None] for _ in range(world)]
+        self.peer_sent = [[None, None] for _ in range(world)]
+        self.peer_drained = [[None, None] for _ in range(world)]
+        for o in range(world):
+            for b in range(2):
+                if o == rank:
+                    self.peer_bins[o][b], self.peer_cur[o][b] = self.recv_bins[b].ptr, self.recv_cur[b].ptr
+                    self.peer_sent[o][b], self.peer_drained[o][b] = self.ev_sent[b], self.ev_drained[b]
+                    continue
+                for j, store in ((0, self.peer_bins), (1, self.peer_cur)):
+                    h = (C.c_ubyte * self.H)(*allh[o, 2 * b + j].tolist())
+                    p = C.c_void_p()
+                    _lib.check(lib.tsxc_ipc_open_mem(dev, h, C.byref(p)))
+                    store[o][b] = p
+                for j, store in ((0, self.peer_sent), (1, self.peer_drained)):
+                    h = (C.c_ubyte * self.H)(*allh[o, 4 + 2 * b + j].tolist())
+                    ev = C.c_void_p()
+                    _lib.check(lib.tsxc_ipc_event_open(dev, h, C.byref(ev)))
+                    store[o][b] = ev
+        self.used = [0, 0]
+
+    def send(self, b, send_bins, send_cursors, comm_stream_ptr):
+        """Queue the copies of buffer set b on the comm stream and record `sent`."""
+        lib, dev, G = self.lib, self.dev, self.world
+        if self.used[b]:
+            for o in range(G):   # the owner must have drained what we sent two chunks ago
+                _lib.check(lib.tsxc_stream_wait_event(dev, comm_stream_ptr, self.peer_drained[o][b]))
+        for i in range(G):
+            o = (self.rank + i) % G   # stagger the destinations
+            _lib.check(lib.tsxc_copy_async(dev, C.c_void_p(self.peer_bins[o][b].value + self.rank * self.block_bytes),
+                                           C.c_void_p(send_bins.data_ptr() + o * self.block_bytes), self.block_bytes,
+                                           comm_stream_ptr))
+            _lib.check(lib.tsxc_copy_async(dev, C.c_void_p(self.peer_cur[o][b].value + self.rank * self.cur_bytes),
+                                           C.c_void_p(send_cursors.data_ptr() + o * self.cur_bytes), self.cur_bytes,
+                                           comm_stream_ptr))
+        _lib.check(lib.tsxc_event_record(dev, self.ev_sent[b], comm_stream_ptr))
+        self.used[b] += 1
+
+    def wait_all_sent(self, b, stream_ptr):
+        for o in range(self.world):
+            _lib.check(self.lib.tsxc_stream_wait_event(self.dev, stream_ptr, self.peer_sent[o][b]))
+
+    def mark_drained(self, b, stream_ptr):
+        _lib.check(self.lib.tsxc_event_record(self.dev, self.ev_drained[b], stream_ptr))
+
+
 class ShardedCounter:
     """Counts the k-mers of this rank's reads into the table sharded over all ranks of `group`."""
 
@@ -82,11 +184,28 @@ class ShardedCounter:
         self.send = [dict(bins=backend.alloc_u64(G * lay.block_words), cursors=backend.alloc_u64(G * lay.bins_per_shard),
                           spill=backend.alloc_u64(G * lay.spill_cap * (kw + 1)), spill_n=backend.alloc_u64(G))
                      for _ in range(2)]
-        self.recv = [dict(bins=backend.alloc_u64(G * lay.block_words), cursors=backend.alloc_u64(G * lay.bins_per_shard),
-                          spill_n=backend.alloc_u64(G)) for _ in range(2)]
+        self.recv = [dict(spill_n=backend.alloc_u64(G)) for _ in range(2)]
         self.a2a_bytes = 0
         self.chunks = 0
         self.retries = 0
+        self.peer = None
+        import os
+        if world > 1 and isinstance(backend, CudaBackend) and os.environ.get("TSXC_EXCHANGE", "nccl") == "peer":
+            ok = 1
+            try:
+                peer = PeerExchange(backend, rank, world, group, lay)
+            except Exception as e:  # IPC not available on this host
+                ok, peer = 0, None
+                self.peer_error = str(e)
+            if self._agree(ok, dist.ReduceOp.MIN):
+                self.peer = peer
+                for b in range(2):   # the receive side lives in the IPC-exported buffers
+                    self.recv[b]["bins"], self.recv[b]["cursors"] = peer.recv_bins[b], peer.recv_cur[b]
+        if self.peer is None:
+            for b in range(2):
+                self.recv[b]["bins"] = backend.alloc_u64(G * lay.block_words)
+                self.recv[b]["cursors"] = backend.alloc_u64(G * lay.bins_per_shard)
+        self.exchange = "peer copies (CUDA IPC, copy engines)" if self.peer else ("nccl all_to_all" if world > 1 else "local")
 
     # -- exchange -----------------------------------------------------------------------------------------
     def _a2a(self, out, inp):
@@ -155,7 +274,11 @@ class ShardedCounter:
                 pb, ev, spill_rec, spill_total = pending
                 if use_cuda:
                     be.stream.wait_event(ev)
+                    if self.peer:
+                        self.peer.wait_all_sent(pb, be.stream.cuda_stream)
                 be.insert(self.recv[pb]["bins"], self.recv[pb]["cursors"], self.world)
+                if self.peer:
+                    self.peer.mark_drained(pb, be.stream.cuda_stream)
                 if spill_total:
                     be.insert_spill(spill_rec, spill_total)
                 pending = None
@@ -170,12 +293,19 @@ class ShardedCounter:
         s, r = self.send[b], self.recv[b]
 
         def body():
+            if self.peer:
+                # copies + `sent` record first, on their own stream: the collectives below (on the comm stream, so
+                # that their host synchronisation does not wait for the copies) are the host-level barrier that
+                # orders this record before every receiver's wait and every `drained` record before the next send
+                self.peer.send(b, s["bins"], s["cursors"], be.copy_stream.cuda_stream)
+                self.a2a_bytes += (self.world - 1) * (self.peer.block_bytes + self.peer.cur_bytes)
             self._a2a(r["spill_n"], s["spill_n"])
             send_n = be.to_host(s["spill_n"]).tolist()
             recv_n = be.to_host(r["spill_n"]).tolist()
             any_spill = self._agree(1 if (sum(send_n) or sum(recv_n)) else 0, dist.ReduceOp.MAX)
-            self._a2a(r["bins"], s["bins"])
-            self._a2a(r["cursors"], s["cursors"])
+            if not self.peer:
+                self._a2a(r["bins"], s["bins"])
+                self._a2a(r["cursors"], s["cursors"])
             rec = self._exchange_spill(b, send_n, recv_n) if any_spill else None
             return rec, (int(sum(recv_n)) if any_spill else 0)
 
@@ -226,6 +356,7 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None):
     be = CudaBackend(k, l_global, 0, rank, world, local_rank,
                      kmers_per_position=min(1.0, 1.02 * max(0, read_len - k + 1) / read_len))
     sc = ShardedCounter(be, rank, world)
+    log(f"rank {rank}: exchange = {sc.exchange} {getattr(sc, 'peer_error', '')}")
     layout = be.hm.stats()
 
     def fence():
@@ -308,7 +439,7 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None):
                                                 "bin by owner -> NCCL all-to-all over NVLink -> insert)",
                        "k": k, "l_global": l_global, "reads_per_gpu": n_reads, "kmers_per_step": n_kmers * world,
                        "distinct": total_distinct, "entry_bytes": E, "table_bytes_per_gpu": layout["table_bytes"],
-                       "chunks_per_step": sc.chunks // max(1, args.warmup + args.steps + (0 if args.no_e2e else 1 + args.steps)),
+                       "exchange": sc.exchange, "chunks_per_step": sc.chunks // max(1, args.warmup + args.steps + (0 if args.no_e2e else 1 + args.steps)),
                        "a2a_bytes_per_gpu_per_step": sc.a2a_bytes // max(1, args.warmup + args.steps + (0 if args.no_e2e else 1 + args.steps)),
                        "l2": "inputs and table shards far exceed the 126 MB L2; shards re-zeroed between steps",
                        "timing": "wall clock per step between barrier+synchronize fences, max over ranks; zeroing untimed"},
