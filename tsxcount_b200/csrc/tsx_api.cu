@@ -150,15 +150,19 @@ int status_from_flags(tsxc_table* t, uint64_t flags) {
 //            balances better: 183-186 ms vs 196 ms at 4 and 217 ms at 3 per SM on config 2; every extra block
 //            costs 1.5 runs of holes per bin)
 //   cap    : bin capacity = mean + 12.5 % + the hole tails of every block (1.5 runs each) + slack
-struct PartGeom { uint32_t tile_words, run; int grid; uint64_t cap; };
+struct PartGeom { uint32_t tile_words, run; int grid, threads; uint64_t cap; };
 
 PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, int blocks_per_sm, double kmers_per_position = 1.0) {
     PartGeom g{};
-    uint32_t iters = P >= 4096 ? 4 : 2;
+    // many bins: one fat block per SM keeps the write frontier (one partially filled sector per resident
+    // (block, bin)) inside L2; few bins: small blocks, finer grid-stride
+    g.threads = P > 1024 ? 1024 : kBlockThreads;
+    if (const char* e = std::getenv("TSXC_PART_THREADS")) { const int v = std::atoi(e); if (v == 256 || v == 512 || v == 1024) g.threads = v; }
+    uint32_t iters = (P >= 4096 && g.threads == kBlockThreads) ? 4 : 2;
     if (const char* e = std::getenv("TSXC_PART_ITERS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) iters = (uint32_t)v; }
-    blocks_per_sm = P <= 1024 ? 8 : 4;
+    blocks_per_sm = g.threads == 1024 ? 2 : (P <= 1024 ? 8 : 4);
     if (const char* e = std::getenv("TSXC_PART_GRID")) { const int v = std::atoi(e); if (v >= 1 && v <= 16) blocks_per_sm = v; }
-    g.tile_words = (kBlockThreads / 32) * 32 * iters;
+    g.tile_words = (g.threads / 32) * 32 * iters;
     const double m = 32.0 * g.tile_words / P;
     g.run = (uint32_t)std::ceil((m + 6.0 * std::sqrt(m)) / 2.0);
     g.run = (g.run + 3) & ~3u;           // whole 32-byte sectors
@@ -170,6 +174,18 @@ PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, in
     g.cap = mean + mean / 8 + 2ULL * (uint64_t)g.grid * g.run + 2048;
     g.cap = (g.cap + 7) & ~7ULL;
     return g;
+}
+
+void launch_partition(uint32_t KW, int threads, int grid, cudaStream_t s, const TableView& tv, const PartView& pv,
+                      const uint64_t* d_packed, const uint32_t* d_ends, uint64_t w0, uint64_t w1, uint64_t n_words,
+                      uint64_t n_bases) {
+    // KW = 4 needs > 64 registers per thread: 1024-thread blocks are not launchable for it
+    if (KW == 4 && threads > 512) threads = 512;
+#define L_(KW_, T_) k_partition_reads<KW_, T_><<<grid, T_, 0, s>>>(tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases)
+    if (KW == 1) { if (threads == 1024) L_(1, 1024); else if (threads == 512) L_(1, 512); else L_(1, 256); }
+    else if (KW == 2) { if (threads == 1024) L_(2, 1024); else if (threads == 512) L_(2, 512); else L_(2, 256); }
+    else { if (threads == 512) L_(4, 512); else L_(4, 256); }
+#undef L_
 }
 
 // Two-phase path for tables much larger than the per-SM translation reach (see tsx_kernels.cuh).
@@ -207,11 +223,7 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
         std::pair<cudaEvent_t, cudaEvent_t> eva, evb;
         // phase A: bins + spill records, nothing inserted
         const bool ta = main_begin(t, s, &eva);
-        switch (L.KW) {
-            case 1: k_partition_reads<1><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases); break;
-            case 2: k_partition_reads<2><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases); break;
-            default: k_partition_reads<4><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases); break;
-        }
+        launch_partition(L.KW, geo.threads, grid_a, s, t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases);
         if (ta) { cudaEventRecord(eva.second, s); t->ev_part.push_back(eva); }
         // phase B: bins, then the spill records; both skip when the chunk overflowed its spill list ...
         const bool tb = main_begin(t, s, &evb);
@@ -737,11 +749,7 @@ int tsxc_route_chunk(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64
     const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w_end - w_begin + geo.tile_words - 1) / geo.tile_words, (uint64_t)geo.grid));
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
-    switch (L.KW) {
-        case 1: k_partition_reads<1><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases); break;
-        case 2: k_partition_reads<2><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases); break;
-        default: k_partition_reads<4><<<grid_a, kBlockThreads, 0, s>>>(t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases); break;
-    }
+    launch_partition(L.KW, geo.threads, grid_a, s, t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases);
     t->n_launches++;
     if (timed) { cudaEventRecord(ev.second, s); t->ev_part.push_back(ev); t->n_main_launches++; }
     CU(cudaGetLastError());

@@ -311,8 +311,8 @@ constexpr uint64_t kHole = ~0ULL;                  // word 0 of an unused run en
 // thread reads after its atomicAdd are always the ones its index refers to.  A tile brings ~run/4 k-mers per
 // bin, so both runs running out inside one tile is a tail event; those k-mers take single entries straight
 // from the global cursor.  Unused tails of the runs a block still owns at the end are filled with holes.
-template <int KW>
-__global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_constant__ TableView tv,
+template <int KW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_partition_reads(const __grid_constant__ TableView tv,
                                                                    const __grid_constant__ PartView pv,
                                                                    const uint64_t* __restrict__ packed,
                                                                    const uint32_t* __restrict__ ends, uint64_t w_begin,
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
 
     for (uint64_t tile = w_begin + (uint64_t)blockIdx.x * kTileWords; tile < w_end; tile += (uint64_t)gridDim.x * kTileWords) {
         const uint64_t tile_end = tile + kTileWords < w_end ? tile + kTileWords : w_end;
-        for (uint64_t base = tile + wib * 32; base < tile_end; base += (kBlockThreads / 32) * 32) {
+        for (uint64_t base = tile + wib * 32; base < tile_end; base += (THREADS / 32) * 32) {
             uint64_t win[KW + 1];
             uint32_t ewin[NE + 1];
             load_window<KW, uint64_t>(packed, base, n_words, lane, win);
@@ -411,19 +411,19 @@ __global__ void __launch_bounds__(kBlockThreads) k_partition_reads(const __grid_
         // rotate the runs whose current one was used up during this tile; a thread issues its reservations four
         // at a time (independent global atomics), then consumes them
         constexpr int kBatch = 4;
-        for (uint32_t p0 = threadIdx.x; p0 < pv.P; p0 += kBatch * kBlockThreads) {
+        for (uint32_t p0 = threadIdx.x; p0 < pv.P; p0 += kBatch * THREADS) {
             unsigned long long nb[kBatch];
             bool rot[kBatch];
 #pragma unroll
             for (int i = 0; i < kBatch; ++i) {
-                const uint32_t p = p0 + i * kBlockThreads;
+                const uint32_t p = p0 + i * THREADS;
                 rot[i] = p < pv.P && run_fill[p] >= R;
                 nb[i] = rot[i] ? atomicAdd(pv.cursor + p, (unsigned long long)R) : 0ULL;
             }
 #pragma unroll
             for (int i = 0; i < kBatch; ++i) {
                 if (!rot[i]) continue;
-                const uint32_t p = p0 + i * kBlockThreads;
+                const uint32_t p = p0 + i * THREADS;
                 const unsigned int f = run_fill[p];
                 run_fill[p] = (f < 2 * R ? f : 2 * R) - R;
                 unsigned int fresh = kNoRun;
