@@ -203,7 +203,8 @@ def main():
                     help="reads per step of the CPU reference sample (60 000 x 150 bp = 7.2e6 31-mers, ~10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-batch-reads", type=int, default=4_000_000)
+    ap.add_argument("--e2e-batch-reads", type=int, default=14_000_000,
+                    help="reads per tsxc_add_reads call of the e2e leg (14e6 x 150 bp = one 2^26-word chunk)")
     ap.add_argument("--force-sharded", action="store_true", help="run the routed multi-GPU data path even with one rank")
     args = ap.parse_args()
 

@@ -254,6 +254,10 @@ int tsxc_k0_random_rmw(tsxc_table* t, uint64_t table_bytes, uint64_t n_ops, int 
 int tsxc_k0_windowed(tsxc_table* t, uint64_t footprint_bytes, uint64_t window_bytes, uint64_t n_ops, int mode,
                      int blocks, int threads, float* ms_out);
 
+/* K0r: all blocks sweep the footprint region by region, ops_per_region random RMWs each (L2-blocked variant). */
+int tsxc_k0_region_sweep(tsxc_table* t, uint64_t footprint_bytes, uint64_t region_bytes, uint64_t ops_per_region,
+                         uint32_t ops_per_item, int mode, float* ms_out);
+
 /* ---- debugging / tests ------------------------------------------------------------------- */
 /* The bijective hash and its inverse on the host (round-trip property of TSXHashMap::testHashFunction,
  * TSXHashMap.h:724-735).  key/out are KW words. */

@@ -98,6 +98,7 @@ PROTOTYPES = {
     "tsxc_k0_random_rmw": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
     "tsxc_k0_windowed": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_float)]),
+    "tsxc_k0_region_sweep": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_float)]),
     "tsxc_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_vp)]),
     "tsxc_host_free": (C.c_int, [_vp]),
     "tsxc_device_alloc": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(_vp)]),

@@ -54,7 +54,7 @@ struct tsxc_table {
     uint64_t* d_spill = nullptr; size_t cap_spill = 0;        // words: (hash, count) records of the single-GPU two-phase path
     unsigned long long* d_cursor = nullptr;                   // kMaxParts + 1 (last = ticket)
     uint32_t pbits = 0;                                        // log2(#regions); 0 = direct path only
-    uint32_t region_log2 = 28;
+    uint32_t region_log2 = 27;
     int part_blocks_per_sm = 3, route_blocks_per_sm = 3;   // resident blocks of k_partition_reads (occupancy query)
     // launch accounting (bench.py's gpu_launches / roofline come from here)
     uint64_t n_launches = 0, n_main_launches = 0;
@@ -176,6 +176,15 @@ PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, in
     return g;
 }
 
+uint32_t slice_entries_cfg() {
+    static const uint32_t v = [] {
+        const char* e = std::getenv("TSXC_SLICE");
+        const int x = e ? std::atoi(e) : 0;
+        return (x >= 256 && x <= (1 << 20)) ? (uint32_t)x : kSliceEntriesDefault;
+    }();
+    return v;
+}
+
 void launch_partition(uint32_t KW, int threads, int grid, cudaStream_t s, const TableView& tv, const PartView& pv,
                       const uint64_t* d_packed, const uint32_t* d_ends, uint64_t w0, uint64_t w1, uint64_t n_words,
                       uint64_t n_bases) {
@@ -193,12 +202,28 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
                                    uint64_t n_bases, cudaStream_t s) {
     const Layout& L = t->L;
     const uint32_t P = 1u << t->pbits;
-    const uint64_t chunk_words = std::min<uint64_t>(n_words, (1ULL << 25) / L.KW);
-    const PartGeom geo = part_geometry(t, P, chunk_words, t->part_blocks_per_sm);
-    const uint64_t cap = geo.cap;
-    // spill list: one record per 8 positions is far more than homopolymer runs and bin tails ever need; inputs
-    // that exceed it (a handful of k-mers making up most of a chunk) are redone by the fused kernel below
-    const uint64_t spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 8);
+    // Chunk = the reads binned before one insert pass.  Larger chunks touch every table region more densely per
+    // pass, which phase B turns into DRAM row locality and L2 hits (insert 334 / 290 / 261 ms on config 2 for
+    // chunks of 2^24 / 2^25 / 2^26 words), so take the largest chunk whose bins + spill list fit in free HBM.
+    static const int chunk_log2_env = [] { const char* e = std::getenv("TSXC_CHUNK_LOG2"); const int v = e ? std::atoi(e) : 0; return (v >= 16 && v <= 30) ? v : 0; }();
+    int chunk_log2 = chunk_log2_env ? chunk_log2_env : 26;
+    uint64_t chunk_words = 0, cap = 0, spill_cap = 0;
+    PartGeom geo{};
+    for (;; --chunk_log2) {
+        chunk_words = std::min<uint64_t>(n_words, (1ULL << chunk_log2) / L.KW);
+        geo = part_geometry(t, P, chunk_words, t->part_blocks_per_sm);
+        cap = geo.cap;
+        // spill list: one record per 8 positions is far more than homopolymer runs and bin tails ever need;
+        // inputs that exceed it (a handful of k-mers making up most of a chunk) are redone by the fused kernel
+        spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 8);
+        const size_t need_part = (size_t)P * cap * L.KW, need_spill = (size_t)spill_cap * (L.KW + 1);
+        if (chunk_log2_env || chunk_log2 <= 20) break;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); break; }
+        const size_t extra = (need_part > t->cap_part ? (need_part - t->cap_part) * 8 : 0) +
+                             (need_spill > t->cap_spill ? (need_spill - t->cap_spill) * 8 : 0);
+        if (extra + (3ULL << 30) <= free_b) break;   // keep 3 GiB free for staging buffers and the caller
+    }
     int rc = ensure(t, &t->d_part, &t->cap_part, (size_t)P * cap * L.KW);
     if (rc) return rc;
     if ((rc = ensure(t, &t->d_spill, &t->cap_spill, (size_t)spill_cap * (L.KW + 1)))) return rc;
@@ -210,7 +235,8 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     pv.pshift = L.LBl - t->pbits; pv.pmask = P - 1; pv.P = P; pv.run = geo.run; pv.tile_words = geo.tile_words;
     pv.spill = t->d_spill; pv.spill_n = spill_n; pv.spill_cap = spill_cap; pv.bins_per_shard_log2 = t->pbits;
     pv.overflow = overflow;
-    const uint32_t slices = (uint32_t)((cap + kSliceEntries - 1) / kSliceEntries);
+    const uint32_t slice_entries = slice_entries_cfg();
+    const uint32_t slices = (uint32_t)((cap + slice_entries - 1) / slice_entries);
     const bool agg = !(L.flags & TSXC_FLAG_NO_WARP_AGG);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
@@ -228,8 +254,8 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
         // phase B: bins, then the spill records; both skip when the chunk overflowed its spill list ...
         const bool tb = main_begin(t, s, &evb);
 #define M(KW_, W_)                                                                                                         \
-        if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket, overflow);  \
-        else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket, overflow);    \
+        if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, ticket, overflow);  \
+        else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, ticket, overflow);    \
         k_add_hash_counts<KW_, W_><<<t->sms * 2, kBlockThreads, 0, s>>>(t->tv, t->d_spill, spill_cap, spill_n, overflow);  \
         /* ... in which case the fused kernel redoes the whole chunk (it exits at once otherwise) */                       \
         if (agg) k_count_reads<KW_, W_, true><<<t->sms * 8, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, w0, w1, n_words, n_bases, overflow); \
@@ -328,7 +354,7 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
         const int v = std::atoi(env);
         if (v >= 16 && v <= 40) h->region_log2 = (uint32_t)v;
     }
-    {   // regions of 2^region_log2 bytes (default 256 MiB); a bucket is 32 bytes
+    {   // regions of 2^region_log2 bytes (default 128 MiB); a bucket is 32 bytes
         const uint32_t table_log2 = L.LBl + 5;
         h->pbits = table_log2 > h->region_log2 ? table_log2 - h->region_log2 : 0;
         if (h->pbits > 12) h->pbits = 12;   // kMaxParts bins
@@ -778,7 +804,8 @@ int tsxc_insert_routed(tsxc_table* t, const tsxc_route_layout_t* lay, const uint
     PartView pv{};
     pv.buf = const_cast<uint64_t*>(d_bins); pv.cursor = const_cast<unsigned long long*>(d_cursors);
     pv.cap = lay->bin_cap; pv.P = n_sources * lay->bins_per_shard;
-    const uint32_t slices = (uint32_t)((lay->bin_cap + kSliceEntries - 1) / kSliceEntries);
+    const uint32_t slice_entries = slice_entries_cfg();
+    const uint32_t slices = (uint32_t)((lay->bin_cap + slice_entries - 1) / slice_entries);
     unsigned long long* ticket = t->d_cursor + kMaxParts;
     CU(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s));
     const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
@@ -786,8 +813,8 @@ int tsxc_insert_routed(tsxc_table* t, const tsxc_route_layout_t* lay, const uint
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
 #define M(KW_, W_)                                                                                        \
-    if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket, nullptr); \
-    else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, ticket, nullptr)
+    if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, ticket, nullptr); \
+    else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, ticket, nullptr)
     TSX_DISPATCH(t->L, M);
 #undef M
     t->n_launches++;
@@ -974,6 +1001,28 @@ int tsxc_k0_windowed(tsxc_table* t, uint64_t footprint_bytes, uint64_t window_by
     CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
     CU(cudaEventRecord(a, t->stream));
     k_k0_windowed<<<blocks, threads, 0, t->stream>>>(t->d_words, fw, ww, n_ops / blocks, mode);
+    CU(cudaEventRecord(b, t->stream));
+    CU(cudaEventSynchronize(b));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(ms_out, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return TSXC_OK;
+}
+
+int tsxc_k0_region_sweep(tsxc_table* t, uint64_t footprint_bytes, uint64_t region_bytes, uint64_t ops_per_region,
+                         uint32_t ops_per_item, int mode, float* ms_out) {
+    if (!t || !ms_out || !ops_per_item) return fail(t, TSXC_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    uint64_t fw = 32, rw = 32;
+    while (fw * 2 * 8 <= std::min<uint64_t>(footprint_bytes, t->L.table_bytes)) fw *= 2;
+    while (rw * 2 * 8 <= region_bytes && rw * 2 <= fw) rw *= 2;
+    unsigned long long* ticket = t->d_cursor + kMaxParts;
+    CU(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), t->stream));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, t->stream));
+    k_k0_region_sweep<<<t->sms * 8, kBlockThreads, 0, t->stream>>>(t->d_words, rw, fw / rw, ops_per_region, ops_per_item, mode, ticket);
     CU(cudaEventRecord(b, t->stream));
     CU(cudaEventSynchronize(b));
     CU(cudaGetLastError());

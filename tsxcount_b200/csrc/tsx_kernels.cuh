@@ -441,14 +441,18 @@ __global__ void __launch_bounds__(THREADS) k_partition_reads(const __grid_consta
     }
 }
 
-// phase B: work item = (bin, slice of kSliceEntries entries); items are numbered bin-major and handed out
-// in order through `ticket`, so the blocks resident at any moment drain neighbouring slices.
-constexpr uint32_t kSliceEntries = 16384;
+// phase B: work item = (bin, slice of slice_entries entries); items are numbered bin-major and handed out in
+// order through `ticket`.  Slices are SMALL (1 K entries) on purpose: the ~1200 resident blocks then work on
+// one or two table regions at a time, and the K0r microbenchmark (tools/k0region.py) shows that concentrating
+// all SMs on a 16-64 MiB region lifts the dependent load+atomic rate from 21 G/s (8 K-entry items, ~18 regions
+// in flight) to 33 G/s at 0.25 touches per sector and to 56-65 G/s at 0.65: neighbouring sectors are requested
+// close together in time (DRAM row locality) and sectors touched twice are still in L2.
+constexpr uint32_t kSliceEntriesDefault = 1024;
 
 template <int KW, int W, bool WARP_AGG>
 __global__ void __launch_bounds__(kBlockThreads) k_insert_partitions(const __grid_constant__ TableView tv,
                                                                      const __grid_constant__ PartView pv,
-                                                                     uint32_t slices_per_bin,
+                                                                     uint32_t slices_per_bin, uint32_t slice_entries,
                                                                      unsigned long long* __restrict__ ticket,
                                                                      const unsigned int* __restrict__ skip_if) {
     const unsigned full = 0xffffffffu;
@@ -463,11 +467,11 @@ __global__ void __launch_bounds__(kBlockThreads) k_insert_partitions(const __gri
         __syncthreads();
         if (item >= n_items) break;
         const uint32_t p = (uint32_t)(item / slices_per_bin);
-        const uint64_t lo = (uint64_t)(item % slices_per_bin) * kSliceEntries;
+        const uint64_t lo = (uint64_t)(item % slices_per_bin) * slice_entries;
         unsigned long long n = __ldcg(pv.cursor + p);
         if (n > pv.cap) n = pv.cap;
         if (lo >= n) continue;
-        const uint64_t hi = lo + kSliceEntries < n ? lo + kSliceEntries : n;
+        const uint64_t hi = lo + slice_entries < n ? lo + slice_entries : n;
         const uint64_t* src = pv.buf + (uint64_t)p * pv.cap * KW;
         for (uint64_t i0 = lo; i0 < hi; i0 += blockDim.x) {
             const uint64_t i = i0 + threadIdx.x;
@@ -565,6 +569,38 @@ __global__ void k_k0_windowed(uint64_t* __restrict__ words, uint64_t footprint_w
         }
     }
     if (sink == 0x123456789ULL) words[0] = sink;
+}
+
+// K0r: all blocks sweep the footprint region by region (work items handed out in order through a ticket), each
+// region receiving ops_per_region random RMWs: the L2-blocked variant of the insert (is a second touch of a
+// sector cheaper while its region is resident?).
+__global__ void __launch_bounds__(kBlockThreads) k_k0_region_sweep(uint64_t* __restrict__ words, uint64_t region_words,
+                                                                   uint64_t n_regions, uint64_t ops_per_region,
+                                                                   uint32_t ops_per_item, int mode,
+                                                                   unsigned long long* __restrict__ ticket) {
+    __shared__ unsigned long long item_s;
+    const uint64_t items_per_region = (ops_per_region + ops_per_item - 1) / ops_per_item;
+    const unsigned long long n_items = n_regions * items_per_region;
+    const uint64_t wmask = region_words - 1;
+    while (true) {
+        if (threadIdx.x == 0) item_s = atomicAdd(ticket, 1ULL);
+        __syncthreads();
+        const unsigned long long item = item_s;
+        __syncthreads();
+        if (item >= n_items) break;
+        const uint64_t base = (item / items_per_region) * region_words;
+        for (uint32_t i = threadIdx.x; i < ops_per_item; i += blockDim.x) {
+            const uint64_t a = base + (fmix64((item * ops_per_item + i) * kC1 + 0x1234567ULL) & wmask);
+            if (mode == 0) {
+                atomicAdd((unsigned long long*)(words + a), 1ULL);
+            } else {
+                uint64_t w[4];
+                load_bucket(words + (a & ~3ULL), w);
+                const uint64_t pick = (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x5a5a5a5a5a5a5a5aULL ? 1 : 0;
+                atomicAdd((unsigned long long*)(words + ((a & ~3ULL) | ((a + pick) & 3ULL))), 1ULL << 40);
+            }
+        }
+    }
 }
 
 }  // namespace tsx
