@@ -149,18 +149,18 @@ int status_from_flags(tsxc_table* t, uint64_t flags) {
 //   grid   : 8 blocks per SM for few bins, 4 for many (measured: 3 are resident, a finer grid-stride still
 //            balances better: 183-186 ms vs 196 ms at 4 and 217 ms at 3 per SM on config 2; every extra block
 //            costs 1.5 runs of holes per bin)
-//   cap    : bin capacity = mean + 12.5 % + the hole tails of every block (1.5 runs each) + slack
+//   cap    : bin capacity = mean + 1 % + 8 sigma + the hole tails of every block (2 runs each) + slack
 struct PartGeom { uint32_t tile_words, run; int grid, threads; uint64_t cap; };
 
 PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, int blocks_per_sm, double kmers_per_position = 1.0) {
     PartGeom g{};
     // many bins: one fat block per SM keeps the write frontier (one partially filled sector per resident
     // (block, bin)) inside L2; few bins: small blocks, finer grid-stride
-    g.threads = P > 1024 ? 1024 : kBlockThreads;
+    g.threads = P > 1024 ? 1024 : (P > 512 ? 512 : kBlockThreads);
     if (const char* e = std::getenv("TSXC_PART_THREADS")) { const int v = std::atoi(e); if (v == 256 || v == 512 || v == 1024) g.threads = v; }
     uint32_t iters = (P >= 4096 && g.threads == kBlockThreads) ? 4 : 2;
     if (const char* e = std::getenv("TSXC_PART_ITERS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) iters = (uint32_t)v; }
-    blocks_per_sm = g.threads == 1024 ? 2 : (P <= 1024 ? 8 : 4);
+    blocks_per_sm = g.threads == 1024 ? 2 : (g.threads == 512 ? 4 : 8);
     if (const char* e = std::getenv("TSXC_PART_GRID")) { const int v = std::atoi(e); if (v >= 1 && v <= 16) blocks_per_sm = v; }
     g.tile_words = (g.threads / 32) * 32 * iters;
     const double m = 32.0 * g.tile_words / P;
@@ -171,7 +171,8 @@ PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, in
     const uint64_t tiles = (chunk_words + g.tile_words - 1) / g.tile_words;
     g.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)t->sms * blocks_per_sm));
     const uint64_t mean = (uint64_t)(32.0 * chunk_words * kmers_per_position / P) + 1;
-    g.cap = mean + mean / 8 + 2ULL * (uint64_t)g.grid * g.run + 2048;
+    // hash-uniform bins: sigma = sqrt(mean), so 1 % + 8 sigma on top of the mean is ample
+    g.cap = mean + mean / 100 + 8 * (uint64_t)std::sqrt((double)mean) + 2ULL * (uint64_t)g.grid * g.run + 2048;
     g.cap = (g.cap + 7) & ~7ULL;
     return g;
 }
@@ -204,18 +205,22 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     const uint32_t P = 1u << t->pbits;
     // Chunk = the reads binned before one insert pass.  Larger chunks touch every table region more densely per
     // pass, which phase B turns into DRAM row locality and L2 hits (insert 334 / 290 / 261 ms on config 2 for
-    // chunks of 2^24 / 2^25 / 2^26 words), so take the largest chunk whose bins + spill list fit in free HBM.
+    // chunks of 2^24 / 2^25 / 2^26 words), so take the largest chunk (up to 2^27 words) whose bins + spill list fit in free HBM.
     static const int chunk_log2_env = [] { const char* e = std::getenv("TSXC_CHUNK_LOG2"); const int v = e ? std::atoi(e) : 0; return (v >= 16 && v <= 30) ? v : 0; }();
-    int chunk_log2 = chunk_log2_env ? chunk_log2_env : 26;
+    int chunk_log2 = chunk_log2_env ? chunk_log2_env : 27;
     uint64_t chunk_words = 0, cap = 0, spill_cap = 0;
     PartGeom geo{};
     for (;; --chunk_log2) {
-        chunk_words = std::min<uint64_t>(n_words, (1ULL << chunk_log2) / L.KW);
+        {   // equal chunks no larger than 2^chunk_log2 / KW words
+            const uint64_t max_words = (1ULL << chunk_log2) / L.KW;
+            const uint64_t n_chunks = (n_words + max_words - 1) / max_words;
+            chunk_words = ((n_words + n_chunks - 1) / n_chunks + 31) & ~31ULL;
+        }
         geo = part_geometry(t, P, chunk_words, t->part_blocks_per_sm);
         cap = geo.cap;
-        // spill list: one record per 8 positions is far more than homopolymer runs and bin tails ever need;
+        // spill list: one record per 16 positions is far more than homopolymer runs and bin tails ever need;
         // inputs that exceed it (a handful of k-mers making up most of a chunk) are redone by the fused kernel
-        spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 8);
+        spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 16);
         const size_t need_part = (size_t)P * cap * L.KW, need_spill = (size_t)spill_cap * (L.KW + 1);
         if (chunk_log2_env || chunk_log2 <= 20) break;
         size_t free_b = 0, total_b = 0;
