@@ -259,8 +259,8 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
         // phase B: bins, then the spill records; both skip when the chunk overflowed its spill list ...
         const bool tb = main_begin(t, s, &evb);
 #define M(KW_, W_)                                                                                                         \
-        if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, ticket, overflow);  \
-        else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, ticket, overflow);    \
+        if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, 1u, ticket, overflow);  \
+        else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, 1u, ticket, overflow);    \
         k_add_hash_counts<KW_, W_><<<t->sms * 2, kBlockThreads, 0, s>>>(t->tv, t->d_spill, spill_cap, spill_n, overflow);  \
         /* ... in which case the fused kernel redoes the whole chunk (it exits at once otherwise) */                       \
         if (agg) k_count_reads<KW_, W_, true><<<t->sms * 8, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, w0, w1, n_words, n_bases, overflow); \
@@ -732,7 +732,7 @@ int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, uint32_t kmers_pe
     std::memset(out, 0, sizeof *out);
     out->n_shards = n_shards; out->bins_per_shard = 1u << pb; out->key_words = L.KW; out->spill_record_words = L.KW + 1;
     out->chunk_words = chunk_words; out->bin_cap = cap; out->block_words = ((uint64_t)1 << pb) * cap * L.KW;
-    out->spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 16 / n_shards * 2);
+    out->spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 32 / n_shards * 2);   // per destination: twice its share of one record per 32 positions
     return TSXC_OK;
 }
 
@@ -818,8 +818,8 @@ int tsxc_insert_routed(tsxc_table* t, const tsxc_route_layout_t* lay, const uint
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
 #define M(KW_, W_)                                                                                        \
-    if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, ticket, nullptr); \
-    else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, ticket, nullptr)
+    if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, n_sources, ticket, nullptr); \
+    else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, n_sources, ticket, nullptr)
     TSX_DISPATCH(t->L, M);
 #undef M
     t->n_launches++;

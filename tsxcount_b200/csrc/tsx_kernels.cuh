@@ -453,6 +453,7 @@ template <int KW, int W, bool WARP_AGG>
 __global__ void __launch_bounds__(kBlockThreads) k_insert_partitions(const __grid_constant__ TableView tv,
                                                                      const __grid_constant__ PartView pv,
                                                                      uint32_t slices_per_bin, uint32_t slice_entries,
+                                                                     uint32_t n_sources,
                                                                      unsigned long long* __restrict__ ticket,
                                                                      const unsigned int* __restrict__ skip_if) {
     const unsigned full = 0xffffffffu;
@@ -466,7 +467,13 @@ __global__ void __launch_bounds__(kBlockThreads) k_insert_partitions(const __gri
         const unsigned long long item = item_s;
         __syncthreads();
         if (item >= n_items) break;
-        const uint32_t p = (uint32_t)(item / slices_per_bin);
+        // bins are stored source-major (bin = source * regions + region) but drained REGION-major: all sources'
+        // bins of one table region are handled back to back, so a region is visited once per chunk
+        const uint32_t regions = pv.P / n_sources;
+        const unsigned long long per_region = (unsigned long long)n_sources * slices_per_bin;
+        const uint32_t region = (uint32_t)(item / per_region);
+        const uint32_t source = (uint32_t)((item % per_region) / slices_per_bin);
+        const uint32_t p = source * regions + region;
         const uint64_t lo = (uint64_t)(item % slices_per_bin) * slice_entries;
         unsigned long long n = __ldcg(pv.cursor + p);
         if (n > pv.cap) n = pv.cap;

@@ -32,6 +32,8 @@ class CudaBackend:
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         self.hm = TSXHashMapCUDA(l_global, s, k, device=device, flags=flags, shard_rank=rank, n_shards=world)
+        self.kmers_per_position = kmers_per_position
+        self.fixed_chunk = max_chunk_words
         self.lay = self.hm.routeLayout(max_chunk_words, kmers_per_position)
         self.kw = self.lay.key_words
         self.stream = torch.cuda.ExternalStream(self.hm._lib.tsxc_stream(self.hm.handle), device=self.device)
@@ -39,6 +41,24 @@ class CudaBackend:
         self.copy_stream = torch.cuda.Stream(device=self.device)   # peer copies (copy engines)
 
     # buffers -----------------------------------------------------------------------------------------
+    def buffer_bytes(self, lay):
+        """Two send sets + two receive sets of bins, cursors and spill lists for this layout."""
+        G = lay.n_shards
+        one = G * lay.block_words * 8 + G * lay.bins_per_shard * 8
+        return 4 * one + 2 * G * lay.spill_cap * (lay.key_words + 1) * 8
+
+    def candidate_layouts(self):
+        """Largest chunk first: the insert pass of a chunk touches every table region once, so bigger chunks mean
+        denser, more local passes; the limit is free HBM next to the shard."""
+        if self.fixed_chunk:
+            return [self.lay]
+        kw = self.lay.key_words
+        return [self.hm.routeLayout(w // kw, self.kmers_per_position) for w in (1 << 25, 3 << 23, 1 << 24, 1 << 23, 1 << 22)]
+
+    def fits(self, lay, reserve=3 << 30):
+        free, _ = torch.cuda.mem_get_info(self.device)
+        return self.buffer_bytes(lay) + reserve <= free
+
     def alloc_u64(self, n):
         return torch.empty(max(int(n), 1), dtype=torch.int64, device=self.device)
 
@@ -176,6 +196,14 @@ class ShardedCounter:
     def __init__(self, backend, rank, world, group=None, min_split_words=1024):
         self.be, self.rank, self.world, self.group = backend, rank, world, group
         self.min_split_words = min_split_words
+        if hasattr(backend, "candidate_layouts"):
+            # every rank must use the same geometry: take the largest chunk that fits on ALL ranks
+            cands = backend.candidate_layouts()
+            mine = next((i for i, c in enumerate(cands) if backend.fits(c)), len(cands) - 1)
+            t = torch.tensor([mine], dtype=torch.int64, device=backend.device)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            backend.lay = cands[int(t.item())]
         lay = backend.lay
         assert lay.n_shards == world
         self.lay = lay
