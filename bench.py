@@ -35,10 +35,12 @@ WORKLOADS = {
     # name: (k, per-GPU log2 slots, gen mode, per-GPU reads, read_len, genome_len, sub_q16, seed, description)
     "c2": dict(k=31, l=34, mode=0, reads=66_666_667, read_len=150, genome=0, sub=0, seed=0xC2,
                desc="config 2: synthetic uniform 150bp reads, 10 Gbases, k=31, 2^34 slots (128 GiB)"),
-    "c2-fakeseq": dict(k=31, l=34, mode=1, reads=66_666_667, read_len=150, genome=0, sub=0, seed=0xC2,
-                       desc="config 2 (generateFakeSequences.py style: random body + poly-A tail), 10 Gbases, k=31"),
-    "c3": dict(k=63, l=33, mode=2, reads=66_666_667, read_len=150, genome=1 << 24, sub=655, seed=0xC3,
-               desc="config 3: log-uniform (Zipf-like) dictionary of 2^24 150-mers, 1% substitutions, k=63"),
+    "c2-fakeseq": dict(k=31, l=34, mode=1, reads=66_666_667, read_len=150, genome=0, sub=0, seed=0xC2, flags=8,
+                       desc="config 2 (generateFakeSequences.py style: random body + poly-A tail), 10 Gbases, k=31 "
+                            "(table created with TSXC_FLAG_SKEWED)"),
+    "c3": dict(k=63, l=33, mode=2, reads=66_666_667, read_len=150, genome=1 << 24, sub=655, seed=0xC3, flags=8,
+               desc="config 3: log-uniform (Zipf-like) dictionary of 2^24 150-mers, 1% substitutions, k=63 "
+                    "(table created with TSXC_FLAG_SKEWED)"),
     "c4": dict(k=127, l=32, mode=0, reads=66_666_667, read_len=150, genome=0, sub=0, seed=0xC4,
                desc="config 4: synthetic uniform 150bp reads, 10 Gbases, k=127, 2^32 slots x 32 B (128 GiB)"),
     "c5": dict(k=31, l=34, mode=3, reads=83_333_333, read_len=150, genome=3_100_000_000, sub=328, seed=0xC5,
@@ -251,7 +253,7 @@ def main():
     d_packed, d_off = dalloc((n_words + 8) * 8), dalloc((n_reads + 1) * 8)
     gp = tsx.TsxcGenParams(wl["seed"], n_reads, read_len, wl["mode"], wl["genome"], wl["sub"], 0)
     tsx._lib.check(lib.tsxc_gen_reads_device(C.byref(gp), 0, n_reads, dev, None, d_packed, d_off))
-    hm = tsx.TSXHashMapCUDA(l, 0, k, device=dev)
+    hm = tsx.TSXHashMapCUDA(l, 0, k, device=dev, flags=wl.get("flags", 0))
     hm.sync()
     layout = hm.stats()
 

@@ -60,6 +60,12 @@ enum {
 /* Always use the single fused extract+insert kernel, never the two-phase region-partitioned path that
  * large tables take by default (DESIGN.md "TLB-aware insert") — for A/B measurements. */
 #define TSXC_FLAG_DIRECT 4u
+/* Hint: a few k-mers make up a large share of the input (Zipf-like reads, amplicons).  Phase B of the two-phase
+ * path then drains the bins in slices 16x as long, which spreads the resident thread blocks over many table
+ * regions instead of concentrating them on one: with dominant k-mers the concentration turns into contention on
+ * their table entries (config 3: insert 541 ms with short slices, 212 ms with long ones; the opposite holds for
+ * uniform k-mers, config 2: 249 ms vs 391 ms).  Counts are identical either way. */
+#define TSXC_FLAG_SKEWED 8u
 
 typedef struct tsxc_table tsxc_table; /* opaque */
 

@@ -404,6 +404,12 @@ def test_partitioned_path_ragged_reads_and_repeats(tsx, small_regions):
         assert np.array_equal(hm.getKmerCounts(oc.keys_kw(1)), 2 * oc.counts)
 
 
+def test_skewed_flag_same_counts(tsx, small_regions):
+    seqs = orc.gen_reads(seed=0xC3, n_reads=4000, read_len=150, mode=2, genome_len=1 << 8, sub_rate_q16=655)
+    st, oc = run_case(tsx, seqs, 63, 19, 0, flags=tsx.TSXC_FLAG_SKEWED)
+    assert st["main_kernel_launches"] >= 4
+
+
 def test_direct_flag_forces_single_kernel(tsx, small_regions):
     seqs = orc.gen_reads(seed=3, n_reads=2000, read_len=150, mode=0)
     st, oc = run_case(tsx, seqs, 31, 20, 0, flags=4)

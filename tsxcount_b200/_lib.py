@@ -23,6 +23,7 @@ TSXC_FLAG_NONE = 0
 TSXC_FLAG_EXACT_S = 1
 TSXC_FLAG_NO_WARP_AGG = 2
 TSXC_FLAG_DIRECT = 4
+TSXC_FLAG_SKEWED = 8
 
 
 class TsxcStats(C.Structure):

@@ -177,13 +177,14 @@ PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, in
     return g;
 }
 
-uint32_t slice_entries_cfg() {
+uint32_t slice_entries_cfg(uint32_t flags) {
     static const uint32_t v = [] {
         const char* e = std::getenv("TSXC_SLICE");
         const int x = e ? std::atoi(e) : 0;
-        return (x >= 256 && x <= (1 << 20)) ? (uint32_t)x : kSliceEntriesDefault;
+        return (x >= 256 && x <= (1 << 20)) ? (uint32_t)x : 0u;
     }();
-    return v;
+    if (v) return v;
+    return (flags & TSXC_FLAG_SKEWED) ? 16 * kSliceEntriesDefault : kSliceEntriesDefault;
 }
 
 void launch_partition(uint32_t KW, int threads, int grid, cudaStream_t s, const TableView& tv, const PartView& pv,
@@ -240,7 +241,7 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     pv.pshift = L.LBl - t->pbits; pv.pmask = P - 1; pv.P = P; pv.run = geo.run; pv.tile_words = geo.tile_words;
     pv.spill = t->d_spill; pv.spill_n = spill_n; pv.spill_cap = spill_cap; pv.bins_per_shard_log2 = t->pbits;
     pv.overflow = overflow;
-    const uint32_t slice_entries = slice_entries_cfg();
+    const uint32_t slice_entries = slice_entries_cfg(t->L.flags);
     const uint32_t slices = (uint32_t)((cap + slice_entries - 1) / slice_entries);
     const bool agg = !(L.flags & TSXC_FLAG_NO_WARP_AGG);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -809,7 +810,7 @@ int tsxc_insert_routed(tsxc_table* t, const tsxc_route_layout_t* lay, const uint
     PartView pv{};
     pv.buf = const_cast<uint64_t*>(d_bins); pv.cursor = const_cast<unsigned long long*>(d_cursors);
     pv.cap = lay->bin_cap; pv.P = n_sources * lay->bins_per_shard;
-    const uint32_t slice_entries = slice_entries_cfg();
+    const uint32_t slice_entries = slice_entries_cfg(t->L.flags);
     const uint32_t slices = (uint32_t)((lay->bin_cap + slice_entries - 1) / slice_entries);
     unsigned long long* ticket = t->d_cursor + kMaxParts;
     CU(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s));
