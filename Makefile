@@ -11,6 +11,7 @@ LIBDIR   := tsxcount_b200/lib
 BINDIR   := tsxcount_b200/bin
 LIB      := $(LIBDIR)/libtsxcuda.so
 CLI      := $(BINDIR)/tsxcount
+INGEST   := $(BINDIR)/ingest_check
 
 .PHONY: all lib cli oracle clean
 all: lib cli oracle
@@ -21,11 +22,15 @@ $(LIB): $(CSRC)/tsx_api.cu $(CSRC)/tsx_host_pack.cpp $(wildcard $(CSRC)/*.cuh) i
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/tsx_api.cu $(CSRC)/tsx_host_pack.cpp
 
-cli: $(CLI)
+cli: $(CLI) $(INGEST)
+
+$(INGEST): $(HOST)/tools/ingest_check.cpp $(HOST)/FastxReader.h include/tsxcount_cuda.h $(LIB)
+	@mkdir -p $(BINDIR)
+	$(HOSTCXX) -O2 -std=c++17 -Wall -Iinclude -I$(HOST) -o $@ $(HOST)/tools/ingest_check.cpp -L$(LIBDIR) -ltsxcuda -lz -Wl,-rpath,'$$ORIGIN/../lib'
 
 $(CLI): $(wildcard $(HOST)/*.cpp) $(wildcard $(HOST)/*.h) include/tsxcount_cuda.h $(LIB)
 	@mkdir -p $(BINDIR)
-	$(HOSTCXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(wildcard $(HOST)/*.cpp) -L$(LIBDIR) -ltsxcuda -lz -Wl,-rpath,'$$ORIGIN/../lib'
+	$(HOSTCXX) -O2 -std=c++17 -Wall -pthread -Iinclude -o $@ $(wildcard $(HOST)/*.cpp) -L$(LIBDIR) -ltsxcuda -lz -Wl,-rpath,'$$ORIGIN/../lib'
 
 oracle:
 	$(MAKE) -C oracle all

@@ -8,6 +8,10 @@
 // N policy: the reference writes two rand()%2 bits for any byte outside upper-case ACGT (:126-137) —
 // unseeded and called from OpenMP tasks, hence not reproducible.  Here such a byte ends the current
 // segment: each maximal ACGT run is emitted as its own segment, so no k-mer spans it.
+//
+// Fast path: 8 bases at a time.  For the four valid letters ((c >> 1) ^ (c >> 2)) & 3 is exactly the code
+// (A 0x41 -> 0, C 0x43 -> 1, G 0x47 -> 2, T 0x54 -> 3); a SWAR test proves that all 8 bytes are valid letters,
+// anything else drops to the byte-wise path.
 #include <cstdint>
 #include <cstring>
 
@@ -22,6 +26,23 @@ struct Lut {
     }
 };
 const Lut kLut;
+
+constexpr uint64_t kLo7 = 0x7f7f7f7f7f7f7f7fULL, kHi = 0x8080808080808080ULL;
+// 0x80 in every byte of x that is zero
+inline uint64_t zero_bytes(uint64_t x) { return ~(((x & kLo7) + kLo7) | x) & kHi; }
+inline uint64_t rep(uint8_t b) { return 0x0101010101010101ULL * b; }
+
+// 16 bits = the 2-bit codes of 8 valid letters (byte i -> bits [2i, 2i+1])
+inline uint64_t codes8(uint64_t x) {
+    uint64_t y = ((x >> 1) ^ (x >> 2)) & 0x0303030303030303ULL;   // one code per byte
+    y = (y | (y >> 6)) & 0x000f000f000f000fULL;                   // two codes per 16 bits
+    y = (y | (y >> 12)) & 0x000000ff000000ffULL;                  // four codes per 32 bits
+    return (y | (y >> 24)) & 0xffffULL;                           // eight codes
+}
+inline bool all_acgt(uint64_t x) {
+    const uint64_t ok = zero_bytes(x ^ rep('A')) | zero_bytes(x ^ rep('C')) | zero_bytes(x ^ rep('G')) | zero_bytes(x ^ rep('T'));
+    return ok == kHi;
+}
 }  // namespace
 
 extern "C" int tsxc_pack_reads(const char* ascii, const uint64_t* offsets, uint64_t n_reads, uint64_t* packed_out,
@@ -30,13 +51,30 @@ extern "C" int tsxc_pack_reads(const char* ascii, const uint64_t* offsets, uint6
     if (!offsets || !packed_out || !seg_offsets_out || !n_segments_out || seg_capacity < 1) return TSXC_E_INVALID;
     if (n_reads && !ascii) return TSXC_E_INVALID;
     uint64_t nseg = 0, g = 0, bad = 0;  // g = bases written so far
-    uint64_t acc = 0;                   // word under construction
+    uint64_t acc = 0;                   // word under construction (bases g - g%32 .. g-1)
     seg_offsets_out[0] = 0;
+    auto put_codes = [&](uint64_t codes, unsigned n) {   // append n <= 8 bases (2n bits)
+        const unsigned pos = (unsigned)(g & 31);
+        acc |= codes << (2 * pos);
+        if (pos + n >= 32) {
+            packed_out[g >> 5] = acc;
+            const unsigned used = 32 - pos;               // bases that went into the finished word
+            acc = used < n ? codes >> (2 * used) : 0;
+        }
+        g += n;
+    };
     for (uint64_t r = 0; r < n_reads; ++r) {
         const uint64_t b = offsets[r], e = offsets[r + 1];
         uint64_t seg_start = g;
-        for (uint64_t i = b; i < e; ++i) {
+        uint64_t i = b;
+        while (i < e) {
+            if (i + 8 <= e) {
+                uint64_t x;
+                std::memcpy(&x, ascii + i, 8);
+                if (all_acgt(x)) { put_codes(codes8(x), 8); i += 8; continue; }
+            }
             const int c = kLut.v[(unsigned char)ascii[i]];
+            ++i;
             if (c < 0) {
                 ++bad;
                 if (g > seg_start) {
@@ -46,8 +84,7 @@ extern "C" int tsxc_pack_reads(const char* ascii, const uint64_t* offsets, uint6
                 seg_start = g;
                 continue;
             }
-            acc |= (uint64_t)c << (2 * (g & 31));
-            if ((++g & 31) == 0) { packed_out[(g >> 5) - 1] = acc; acc = 0; }
+            put_codes((uint64_t)c, 1);
         }
         // a read always closes a segment, even an empty one (read count == segment count on clean input;
         // empty segments contribute no k-mers)

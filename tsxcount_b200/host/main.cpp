@@ -11,16 +11,21 @@
 // New: --mode=CUDA (the only mode this binary implements — the CPU modes are the reference's own),
 //      --dump=FILE (KMER<TAB>COUNT, format of count_kmers.py:32-34), --device=N, --widevalue (use every
 //      spare bit of the entry for the value field instead of exactly s bits).
-// The count phase streams FASTQ through FastxReader -> tsxc_pack_reads -> pinned buffers -> tsxc_add_reads
-// (double-buffered: parsing/packing of batch b+1 overlaps the GPU work on batch b).
+// The count phase streams FASTQ through a reader thread (FastxReader), packer threads (tsxc_pack_reads into
+// pinned buffers) and tsxc_add_reads; see countKMers.
 #include <argp.h>
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <exception>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "FastxReader.h"
@@ -36,7 +41,7 @@ static struct argp_option options[] = {
     {"input", 'i', "INPUT_FASTA", 0, "input string"},
     {"check", 'c', 0, OPTION_ARG_OPTIONAL, "check counts"},
     {"checkabort", 'a', 0, OPTION_ARG_OPTIONAL, "abort if check count raises error"},
-    {"threads", 't', "THREADS", OPTION_ARG_OPTIONAL, "Number of host threads (accepted for compatibility)."},
+    {"threads", 't', "THREADS", OPTION_ARG_OPTIONAL, "Number of host threads (1 reader + THREADS-1 packers)."},
     {"mode", 'm', "MODE", OPTION_ARG_OPTIONAL, "counting mode (CUDA)"},
     {"dump", 'd', "FILE", 0, "write KMER<TAB>COUNT lines"},
     {"device", 'g', "N", 0, "CUDA device index"},
@@ -45,7 +50,7 @@ static struct argp_option options[] = {
 
 struct arguments {
     uint16_t k = 14, l = 26, storagebits = 4;   // main.cpp:409-413
-    int threads = 1;
+    int threads = 3;   // 1 reader + 2 packers: the reader (~0.9 Gbases/s) is the limit; measured 0.6 Gbases/s end to end
     std::string input_path, dump_path, mode = "CUDA";
     bool check = false, checkabort = false, wide = false;
     int device = 0;
@@ -95,30 +100,129 @@ bool encode_kmer(const std::string& s, uint32_t kw, uint64_t* out) {
     return true;
 }
 
+// Count phase.  The reference has one OpenMP producer that reads 40 records at a time and one task per batch that
+// packs and inserts k-mer by k-mer (main.cpp:132-206).  Here: one reader thread (FastxReader, ~0.9 Gbases/s),
+// `threads` packer threads (tsxc_pack_reads into pinned buffers, ~0.9 Gbases/s each) and the GPU behind
+// tsxc_add_reads, connected by two bounded queues.  Batches may be submitted in any order (counting commutes).
+// A pinned buffer is reused only after a tsxc_sync() that started after its submission returned.
 void countKMers(TSXHashMapCUDA& map, const arguments& args) {
-    FastxReader reader(args.input_path);
+    struct Raw { std::string bases; std::vector<uint64_t> offsets; size_t n = 0; };
+    enum class St { Free, Filling, Submitted };
+    struct Slot { PinnedBatch pin; St st = St::Free; uint64_t epoch = 0; };
+
     const size_t kBatchReads = 1 << 18;
-    PinnedBatch pin[2];
-    std::string bases;
-    std::vector<uint64_t> offsets;
-    uint64_t n_reads_total = 0, n_bad_total = 0;
-    int cur = 0;
-    size_t n;
-    while ((n = reader.nextBatch(kBatchReads, bases, offsets)) > 0) {
-        PinnedBatch& pb = pin[cur];
-        // the previous use of this pinned pair (two batches ago) must have been consumed
-        if (n_reads_total >= 2 * kBatchReads) map.sync();
-        size_t bad_upper = 0;
-        for (char c : bases) bad_upper += !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
-        pb.ensure(bases.size() / 32 + 2, n + bad_upper + 2);
-        uint64_t nseg = 0, nbad = 0;
-        if (tsxc_pack_reads(bases.data(), offsets.data(), n, pb.packed, pb.offsets, pb.off_cap, &nseg, &nbad) != TSXC_OK)
-            throw TSXException("tsxc_pack_reads failed");
-        map.addReads(pb.packed, pb.offsets, nseg);
-        n_reads_total += n;
-        n_bad_total += nbad;
-        cur ^= 1;
-    }
+    const int n_packers = std::max(1, std::min(args.threads > 1 ? args.threads - 1 : 1, 16));
+    const int n_slots = 2 * n_packers + 2;
+    std::vector<Slot> slots(n_slots);
+    std::mutex mu;
+    std::condition_variable cv_raw_free, cv_raw_ready, cv_slot;
+    std::deque<Raw*> raw_free, raw_ready;
+    std::vector<Raw> raws(n_packers + 2);
+    for (auto& r : raws) raw_free.push_back(&r);
+    bool reader_done = false;
+    std::exception_ptr failure;
+    uint64_t epoch = 0, n_reads_total = 0, n_bad_total = 0;
+    bool syncing = false;
+
+    std::thread reader([&] {
+        try {
+            FastxReader rd(args.input_path);
+            for (;;) {
+                Raw* r;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_raw_free.wait(lk, [&] { return !raw_free.empty() || failure; });
+                    if (failure) break;
+                    r = raw_free.front(); raw_free.pop_front();
+                }
+                r->n = rd.nextBatch(kBatchReads, r->bases, r->offsets);
+                std::lock_guard<std::mutex> lk(mu);
+                if (r->n == 0) { raw_free.push_back(r); break; }
+                raw_ready.push_back(r);
+                cv_raw_ready.notify_one();
+            }
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!failure) failure = std::current_exception();
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        reader_done = true;
+        cv_raw_ready.notify_all();
+    });
+
+    auto acquire_slot = [&]() -> Slot* {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            if (failure) throw TSXException("aborted: another pipeline thread failed");
+            for (auto& sl : slots) if (sl.st == St::Free) { sl.st = St::Filling; return &sl; }
+            bool any_submitted = false;
+            for (auto& sl : slots) any_submitted |= (sl.st == St::Submitted);
+            if (any_submitted && !syncing) {
+                // everything submitted before this point is finished once the sync returns
+                syncing = true;
+                const uint64_t e = epoch++;
+                lk.unlock();
+                try {
+                    map.sync();
+                } catch (...) {
+                    lk.lock();
+                    syncing = false;
+                    cv_slot.notify_all();
+                    throw;
+                }
+                lk.lock();
+                for (auto& sl : slots) if (sl.st == St::Submitted && sl.epoch <= e) sl.st = St::Free;
+                syncing = false;
+                cv_slot.notify_all();
+                continue;
+            }
+            cv_slot.wait(lk);
+        }
+    };
+
+    auto packer = [&] {
+        try {
+            for (;;) {
+                Raw* r;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_raw_ready.wait(lk, [&] { return !raw_ready.empty() || reader_done || failure; });
+                    if (failure) return;
+                    if (raw_ready.empty()) return;   // reader finished and nothing left
+                    r = raw_ready.front(); raw_ready.pop_front();
+                }
+                Slot* sl = acquire_slot();
+                PinnedBatch& pb = sl->pin;
+                const size_t n = r->n;
+                pb.ensure(r->bases.size() / 32 + 2, n + 2);
+                uint64_t nseg = 0, nbad = 0;
+                int prc = tsxc_pack_reads(r->bases.data(), r->offsets.data(), n, pb.packed, pb.offsets, pb.off_cap, &nseg, &nbad);
+                if (prc == TSXC_E_INVALID) {   // non-ACGT bytes split reads into more segments than reads
+                    size_t bad_upper = 0;
+                    for (char c : r->bases) bad_upper += !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+                    pb.ensure(r->bases.size() / 32 + 2, n + bad_upper + 2);
+                    prc = tsxc_pack_reads(r->bases.data(), r->offsets.data(), n, pb.packed, pb.offsets, pb.off_cap, &nseg, &nbad);
+                }
+                if (prc != TSXC_OK) throw TSXException("tsxc_pack_reads failed");
+                map.addReads(pb.packed, pb.offsets, nseg);
+                std::lock_guard<std::mutex> lk(mu);
+                sl->st = St::Submitted; sl->epoch = epoch;
+                n_reads_total += n; n_bad_total += nbad;
+                raw_free.push_back(r);
+                cv_raw_free.notify_one();
+                cv_slot.notify_all();
+            }
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!failure) failure = std::current_exception();
+            cv_raw_free.notify_all(); cv_raw_ready.notify_all(); cv_slot.notify_all();
+        }
+    };
+    std::vector<std::thread> packers;
+    for (int i = 0; i < n_packers; ++i) packers.emplace_back(packer);
+    reader.join();
+    for (auto& th : packers) th.join();
+    if (failure) std::rethrow_exception(failure);
     map.sync();
     std::cerr << "Reads: " << n_reads_total << std::endl;
     if (n_bad_total)

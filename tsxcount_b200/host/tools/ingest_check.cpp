@@ -1,0 +1,60 @@
+// ingest_check — host-only exerciser of the feeder (FastxReader + tsxc_pack_reads): prints the number of
+// reads, bases, non-ACGT bases, an FNV-1a hash of the concatenated sequences and of the packed stream, and the
+// throughput.  Used by tests/test_cli.py (no GPU needed) and for ingest measurements.
+//   ingest_check <file> [batch_reads] [block_bytes]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "FastxReader.h"
+#include "tsxcount_cuda.h"
+
+static uint64_t fnv(uint64_t h, const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ULL; }
+    return h;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) { std::fprintf(stderr, "usage: ingest_check <file> [batch_reads] [block_bytes]\n"); return 2; }
+    const size_t batch = argc > 2 ? std::strtoull(argv[2], nullptr, 0) : (1u << 18);
+    const size_t block = argc > 3 ? std::strtoull(argv[3], nullptr, 0) : (8u << 20);
+    FastxReader reader(argv[1], 4, block);
+    std::string bases;
+    std::vector<uint64_t> offsets, packed, seg;
+    uint64_t reads = 0, total = 0, bad_total = 0, segs = 0, h_bases = 0xcbf29ce484222325ULL, h_lens = h_bases, h_packed = h_bases;
+    double t_read = 0, t_pack = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const auto a = std::chrono::steady_clock::now();
+        const size_t n = reader.nextBatch(batch, bases, offsets);
+        const auto b = std::chrono::steady_clock::now();
+        if (!n) break;
+        packed.resize(bases.size() / 32 + 2);
+        seg.resize(n + 2);
+        uint64_t nseg = 0, nbad = 0;
+        int rc = tsxc_pack_reads(bases.data(), offsets.data(), n, packed.data(), seg.data(), seg.size(), &nseg, &nbad);
+        if (rc == TSXC_E_INVALID) {   // non-ACGT bytes split reads into more segments than reads: size for the worst case
+            size_t bad_upper = 0;
+            for (char c : bases) bad_upper += !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+            seg.resize(n + bad_upper + 2);
+            rc = tsxc_pack_reads(bases.data(), offsets.data(), n, packed.data(), seg.data(), seg.size(), &nseg, &nbad);
+        }
+        if (rc != TSXC_OK) return 1;
+        const auto c = std::chrono::steady_clock::now();
+        t_read += std::chrono::duration<double>(b - a).count();
+        t_pack += std::chrono::duration<double>(c - b).count();
+        h_bases = fnv(h_bases, bases.data(), bases.size());
+        for (size_t i = 0; i < n; ++i) { const uint64_t len = offsets[i + 1] - offsets[i]; h_lens = fnv(h_lens, &len, 8); }
+        h_packed = fnv(h_packed, packed.data(), ((seg[nseg] + 31) / 32) * 8);
+        reads += n; total += bases.size(); bad_total += nbad; segs += nseg;
+    }
+    const double t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("reads=%llu bases=%llu bad=%llu segments=%llu hash_bases=%016llx hash_lens=%016llx hash_packed=%016llx\n",
+                (unsigned long long)reads, (unsigned long long)total, (unsigned long long)bad_total, (unsigned long long)segs,
+                (unsigned long long)h_bases, (unsigned long long)h_lens, (unsigned long long)h_packed);
+    std::fprintf(stderr, "%.2f s (read %.2f s, pack %.2f s): %.1f Mbases/s\n", t, t_read, t_pack, total / (t > 0 ? t : 1) / 1e6);
+    return 0;
+}
