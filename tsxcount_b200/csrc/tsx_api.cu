@@ -55,7 +55,6 @@ struct tsxc_table {
     unsigned long long* d_cursor = nullptr;                   // kMaxParts + 1 (last = ticket)
     uint32_t pbits = 0;                                        // log2(#regions); 0 = direct path only
     uint32_t region_log2 = 27;
-    int part_blocks_per_sm = 3, route_blocks_per_sm = 3;   // resident blocks of k_partition_reads (occupancy query)
     // launch accounting (bench.py's gpu_launches / roofline come from here)
     uint64_t n_launches = 0, n_main_launches = 0;
     double main_ms = 0.0;
@@ -152,7 +151,7 @@ int status_from_flags(tsxc_table* t, uint64_t flags) {
 //   cap    : bin capacity = mean + 1 % + 8 sigma + the hole tails of every block (2 runs each) + slack
 struct PartGeom { uint32_t tile_words, run; int grid, threads; uint64_t cap; };
 
-PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, int blocks_per_sm, double kmers_per_position = 1.0) {
+PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, double kmers_per_position = 1.0) {
     PartGeom g{};
     // many bins: one fat block per SM keeps the write frontier (one partially filled sector per resident
     // (block, bin)) inside L2; few bins: small blocks, finer grid-stride
@@ -160,7 +159,7 @@ PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, in
     if (const char* e = std::getenv("TSXC_PART_THREADS")) { const int v = std::atoi(e); if (v == 256 || v == 512 || v == 1024) g.threads = v; }
     uint32_t iters = (P >= 4096 && g.threads == kBlockThreads) ? 4 : 2;
     if (const char* e = std::getenv("TSXC_PART_ITERS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) iters = (uint32_t)v; }
-    blocks_per_sm = g.threads == 1024 ? 2 : (g.threads == 512 ? 4 : 8);
+    int blocks_per_sm = g.threads == 1024 ? 2 : (g.threads == 512 ? 4 : 8);
     if (const char* e = std::getenv("TSXC_PART_GRID")) { const int v = std::atoi(e); if (v >= 1 && v <= 16) blocks_per_sm = v; }
     g.tile_words = (g.threads / 32) * 32 * iters;
     const double m = 32.0 * g.tile_words / P;
@@ -217,7 +216,7 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
             const uint64_t n_chunks = (n_words + max_words - 1) / max_words;
             chunk_words = ((n_words + n_chunks - 1) / n_chunks + 31) & ~31ULL;
         }
-        geo = part_geometry(t, P, chunk_words, t->part_blocks_per_sm);
+        geo = part_geometry(t, P, chunk_words);
         cap = geo.cap;
         // spill list: one record per 16 positions is far more than homopolymer runs and bin tails ever need;
         // inputs that exceed it (a handful of k-mers making up most of a chunk) are redone by the fused kernel
@@ -729,7 +728,7 @@ int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, uint32_t kmers_pe
     const uint64_t chunk_words = max_chunk_words ? max_chunk_words : (1ULL << 24) / L.KW;
     const uint32_t P = n_shards << pb;
     const double frac = kmers_per_position_q16 ? std::min(1.0, kmers_per_position_q16 / 65536.0) : 1.0;
-    const uint64_t cap = part_geometry(t, P, chunk_words, t->route_blocks_per_sm, frac).cap;
+    const uint64_t cap = part_geometry(t, P, chunk_words, frac).cap;
     std::memset(out, 0, sizeof *out);
     out->n_shards = n_shards; out->bins_per_shard = 1u << pb; out->key_words = L.KW; out->spill_record_words = L.KW + 1;
     out->chunk_words = chunk_words; out->bin_cap = cap; out->block_words = ((uint64_t)1 << pb) * cap * L.KW;
@@ -770,7 +769,7 @@ int tsxc_route_chunk(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64
     CU(cudaMemsetAsync(d_cursors, 0, (size_t)P * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(d_spill_n, 0, (size_t)lay->n_shards * sizeof(unsigned long long), s));
     if (w_end == w_begin) return TSXC_OK;
-    const PartGeom geo = part_geometry(t, P, lay->chunk_words, t->route_blocks_per_sm);
+    const PartGeom geo = part_geometry(t, P, lay->chunk_words);
     PartView pv{};
     pv.buf = d_bins; pv.cursor = d_cursors; pv.cap = lay->bin_cap;
     pv.pshift = L.LBl - pb; pv.pmask = P - 1; pv.P = P;

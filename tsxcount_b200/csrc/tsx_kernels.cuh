@@ -1,12 +1,17 @@
 // tsx_kernels.cuh — the sm_100a kernels of the counting path.
 //
-//   K1+K2  k_count_reads    packed reads -> forward k-mers -> hash -> insert (fused; no k-mer array in HBM)
-//   K2     k_add_kmers      batched addKmer on explicit k-mers / on pre-hashed k-mers
-//   K4     k_lookup         batched getKmerCount(kmer)
-//   K5     k_dump           table scan -> (k-mer, count) via the inverse hash
-//   K6     k_partition_reads<ROUTE>  extraction + hash + binning by owning shard and table region (multi-GPU
-//                              send side); k_insert_partitions / k_add_hash_counts on the receiving shard
-//          k_mark_ends      read offsets -> "last base of a read" bitmap
+//   K1+K2  k_count_reads        packed reads -> forward k-mers -> hash -> insert, fused (small tables, and the
+//                               device-side fallback of a two-phase chunk)
+//   K1     k_partition_reads    phase A of the two-phase path: extract + hash, bin every k-mer by (owning shard,)
+//                               table region; never touches the table
+//   K2     k_insert_partitions  phase B: drain the bins region by region, insert
+//          k_add_hash_counts    (hash, count) spill records
+//          k_add_kmers          batched addKmer on explicit k-mers / on pre-hashed k-mers
+//   K4     k_lookup             batched getKmerCount(kmer)
+//   K5     k_dump               table scan -> (k-mer, count) via the inverse hash
+//   K6     = K1 with bins keyed by (owner, region) on the sender + K2 on the receiver; the exchange is the host's
+//          k_mark_ends          read offsets -> "last base of a read" bitmap
+//   K0     k_k0_random_rmw / k_k0_windowed / k_k0_region_sweep   random-access roofline microbenchmarks
 //
 // Reference semantics (paths relative to mjoppich/tsxCount):
 //   extraction  src/mains/testExecution.h:15-36   every forward substring seq[i:i+k]; none if len < k

@@ -472,7 +472,7 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None):
                        "l2": "inputs and table shards far exceed the 126 MB L2; shards re-zeroed between steps",
                        "timing": "wall clock per step between barrier+synchronize fences, max over ranks; zeroing untimed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_partition_reads<ROUTE> + k_insert_partitions (per GPU)",
+                         "traffic": None, "peak_source": peak_src, "kernel": "k_partition_reads (bins by owner and region) + k_insert_partitions (per GPU)",
                          "algorithmic_bytes_per_kmer": 2 * E + in_b,
                          "phase_ms_rank0_total": {"route": st["partition_ms"], "insert": st["insert_ms"]}},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
