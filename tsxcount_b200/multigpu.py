@@ -381,7 +381,7 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None):
     _lib.check(lib.tsxc_gen_reads_device(C.byref(gp), rank * n_reads, n_reads, local_rank, None, d_packed.data_ptr(), d_off.data_ptr()))
     torch.cuda.synchronize()
     # bins are sized for the k-mers a read of this length yields (+2 %); anything beyond goes through the spill path
-    be = CudaBackend(k, l_global, 0, rank, world, local_rank,
+    be = CudaBackend(k, l_global, 0, rank, world, local_rank, flags=wl.get("flags", 0),
                      kmers_per_position=min(1.0, 1.02 * max(0, read_len - k + 1) / read_len))
     sc = ShardedCounter(be, rank, world)
     log(f"rank {rank}: exchange = {sc.exchange} {getattr(sc, 'peer_error', '')}")
