@@ -362,6 +362,9 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None):
     import statistics
     import time
 
+    # stdout carries exactly one JSON line (rank 0): NCCL's version / debug lines go to stderr
+    import os
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if not dist.is_initialized():
