@@ -69,22 +69,19 @@ def main():
                           "partition_ms": round(st["partition_ms"], 2), "insert_ms": round(st["insert_ms"], 2),
                           "launches": st["kernel_launches"]}))
     if args.query:
-        # K4: batched getKmerCount on device-resident k-mers (here: the table's own dump = all present); K5: dump scan
-        import numpy as np
+        # K4: batched getKmerCount on device-resident k-mers (random keys: almost all absent, one probe each)
         n_q = min(1 << 27, st["distinct"])
-        d_keys = torch.empty(n_q * hm.kw, dtype=torch.int64, device="cuda")
         d_cnt = torch.empty(n_q, dtype=torch.int64, device="cuda")
-        # keys = hashes of consecutive integers are not k-mers of the table; use absent keys (random) and present keys
         rnd = torch.randint(0, 2**62, (n_q * hm.kw,), dtype=torch.int64, device="cuda")
-        if args.k < 32:
-            rnd &= (1 << (2 * args.k)) - 1 if hm.kw == 1 else -1
+        if hm.kw == 1 and args.k < 32:
+            rnd &= (1 << (2 * args.k)) - 1
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         tsx._lib.check(lib.tsxc_lookup_device(hm.handle, rnd.data_ptr(), n_q, d_cnt.data_ptr()), hm.handle)
         e1.record(stream)
         hm.sync()
-        print(json.dumps({"k4_lookup_absent_keys": n_q, "ms": round(e0.elapsed_time(e1), 2),
+        print(json.dumps({"k4_lookup_random_keys": n_q, "ms": round(e0.elapsed_time(e1), 2),
                           "g_lookups_per_s": round(n_q / e0.elapsed_time(e1) / 1e6, 2)}))
     if args.k0:
         for mode, name in ((0, "red_add"), (1, "cas"), (2, "sector_load+atomic")):
