@@ -446,8 +446,8 @@ __global__ void __launch_bounds__(THREADS) k_partition_reads(const __grid_consta
     }
 }
 
-// phase B: work item = (bin, slice of slice_entries entries); items are numbered bin-major and handed out in
-// order through `ticket`.  Slices are SMALL (1 K entries) on purpose: the ~1200 resident blocks then work on
+// phase B: work item = (region, source, slice of slice_entries entries); items are numbered region-major and
+// handed out in order through `ticket`.  Slices are SMALL (1 K entries) on purpose: the ~1200 resident blocks then work on
 // one or two table regions at a time, and the K0r microbenchmark (tools/k0region.py) shows that concentrating
 // all SMs on a 16-64 MiB region lifts the dependent load+atomic rate from 21 G/s (8 K-entry items, ~18 regions
 // in flight) to 33 G/s at 0.25 touches per sector and to 56-65 G/s at 0.65: neighbouring sectors are requested
