@@ -89,6 +89,17 @@ def test_cli_gz_input_and_n_bases(tmp_path):
     assert "Non-ACGT bases: 1" in p.stderr
 
 
+@pytest.mark.gpu
+def test_cli_parallel_readers_give_the_same_counts(tmp_path):
+    fastq = orc.golden_path("c1_bundled_k14.fastq", tmp_path)
+    orc.golden_path("c1_bundled_k14.fastq.14.count", tmp_path)
+    assert os.path.getsize(fastq) > 4 << 16
+    p = subprocess.run([CLI, f"--input={fastq}", "--mode=CUDA", "--check", "--readers=4", "--threads=4"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "Readers=4" in p.stderr
+    assert "Added a total of 194697 different kmers" in p.stdout and "total errors0" in p.stdout
+
+
 # ---- host feeder (FastxReader + tsxc_pack_reads) without a GPU -------------------------------------------
 INGEST = os.path.join(ROOT, "tsxcount_b200", "bin", "ingest_check")
 
@@ -149,3 +160,40 @@ def test_feeder_edge_cases(tmp_path):
     misnamed = tmp_path / "gz_without_suffix.fastq"               # the gzip magic decides, not the name
     misnamed.write_bytes(gz.read_bytes())
     assert _run_ingest(misnamed) == _expected_ingest(seqs)
+
+
+@pytest.mark.parametrize("ranges", [2, 3, 7, 64])
+def test_feeder_byte_ranges_deliver_every_record_exactly_once(tmp_path, ranges):
+    """--readers: N readers on disjoint byte ranges must reproduce the sequential stream, also when quality lines
+    begin with '@' or '+', with empty lines between records and with range borders in every kind of line."""
+    import random
+    from tsxcount_b200 import sequtils
+    rnd = random.Random(ranges)
+    p = tmp_path / "r.fastq"
+    with open(p, "w") as f:
+        for i in range(3000):
+            n = rnd.randint(1, 90)
+            seq = "".join(rnd.choice("ACGT") for _ in range(n))
+            qual = "".join(rnd.choice("@+I#>") for _ in range(n))
+            f.write(f"@r{i} extra\n{seq}\n+\n{qual}\n")
+            if rnd.random() < 0.05:
+                f.write("\n")
+    seqs = sequtils.read_fastq(p)
+    assert len(seqs) == 3000
+    want = _expected_ingest(seqs)
+    for batch, block in ((1 << 18, 8 << 20), (5, 64)):
+        got = _run_ingest(p, batch, block, ranges)
+        assert got[:5] == want[:5]
+    # threads, one per range: totals only
+    out = subprocess.run([INGEST, str(p), "100", "4096", str(ranges), "parallel"], capture_output=True, text=True, check=True).stdout
+    kv = dict(item.split("=") for item in out.split())
+    assert (int(kv["reads"]), int(kv["bases"])) == want[:2]
+
+
+def test_feeder_byte_ranges_more_ranges_than_records(tmp_path):
+    from tsxcount_b200 import sequtils
+    p = tmp_path / "tiny.fastq"
+    p.write_bytes(b"@a\nACGT\n+\n@@@@\n@b\nGG\n+\n@+\n")
+    seqs = sequtils.read_fastq(p)
+    for ranges in (2, 5, 13, 26):
+        assert _run_ingest(p, 10, 16, ranges)[:5] == _expected_ingest(seqs)[:5]

@@ -25,17 +25,42 @@
 
 class FastxReader {
 public:
-    explicit FastxReader(const std::string& path, int lines_per_record = 4, size_t block_bytes = 8u << 20)
-        : m_lines(lines_per_record), m_buf(block_bytes) {
+    // Whole file, or (plain files only) the records that START in the byte range [range_begin, range_end):
+    // several readers on disjoint ranges of one file deliver every record exactly once.  A reader that does not
+    // start at byte 0 has to find a record boundary by itself: for FASTQ the first line that begins with '@'
+    // and whose second next non-empty line begins with '+' (a quality line may begin with '@', but then the
+    // line two further down is a sequence); for FASTA the first line beginning with '>'.  This is exact for
+    // well-formed files only, so ranges are opt-in (the CLI's --readers); the default reads sequentially with
+    // the reference's tolerant semantics.
+    explicit FastxReader(const std::string& path, int lines_per_record = 4, size_t block_bytes = 8u << 20,
+                         uint64_t range_begin = 0, uint64_t range_end = ~0ULL)
+        : m_lines(lines_per_record), m_buf(block_bytes), m_range_end(range_end) {
         m_fd = ::open(path.c_str(), O_RDONLY);
         if (m_fd < 0) throw std::runtime_error("FastxReader: cannot open " + path);
         unsigned char magic[2] = {0, 0};
         const ssize_t got = ::pread(m_fd, magic, 2, 0);
         if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+            if (range_begin != 0 || range_end != ~0ULL) { ::close(m_fd); throw std::runtime_error("FastxReader: byte ranges need a plain file"); }
             m_gz = gzdopen(m_fd, "rb");
             if (!m_gz) { ::close(m_fd); throw std::runtime_error("FastxReader: gzdopen failed for " + path); }
             gzbuffer(m_gz, 1 << 20);
+        } else if (range_begin > 0) {
+            // start one byte early: if that byte is '\n', range_begin is the start of a line
+            if (::lseek(m_fd, (off_t)(range_begin - 1), SEEK_SET) < 0) throw std::runtime_error("FastxReader: seek failed");
+            m_file_off = range_begin - 1;
+            const char* l; size_t n; uint64_t off;
+            nextLine(l, n, off);                       // the (rest of the) line we landed in belongs to the previous range
+            syncToRecord();
         }
+    }
+
+    static bool isGzip(const std::string& path) {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        unsigned char magic[2] = {0, 0};
+        const ssize_t got = ::pread(fd, magic, 2, 0);
+        ::close(fd);
+        return got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
     }
     ~FastxReader() {
         if (m_gz) gzclose(m_gz);        // closes the descriptor too
@@ -49,11 +74,13 @@ public:
     size_t nextBatch(size_t max_reads, std::string& bases, std::vector<uint64_t>& offsets) {
         bases.clear();
         offsets.assign(1, 0);
-        while (offsets.size() - 1 < max_reads) {
+        while (offsets.size() - 1 < max_reads && !m_range_done) {
             const char* line;
             size_t len;
-            if (!nextLine(line, len)) break;
+            uint64_t off;
+            if (!nextLine(line, len, off)) break;
             if (len == 0) continue;
+            if (m_in_record == 0 && off >= m_range_end) { m_range_done = true; break; }   // starts in the next range
             if (m_in_record == 1) bases.append(line, len);   // the record may still turn out incomplete at EOF
             if (++m_in_record == m_lines) {
                 offsets.push_back(bases.size());
@@ -70,26 +97,52 @@ private:
         const ssize_t r = ::read(m_fd, dst, n);
         return r > 0 ? (size_t)r : 0;
     }
+    // Positions the reader on the first record boundary at or after the current line (see the constructor).
+    void syncToRecord() {
+        struct L { uint64_t off; char first; };
+        std::vector<L> win;                            // non-empty lines seen so far, with their file offsets
+        const char first_char = m_lines == 4 ? '@' : '>';
+        for (;;) {
+            const char* l; size_t n; uint64_t off;
+            if (!nextLine(l, n, off)) { m_range_done = true; return; }
+            if (n == 0) continue;
+            win.push_back({off, l[0]});
+            const size_t need = m_lines == 4 ? 3 : 1;  // FASTQ: header, sequence, '+'
+            while (win.size() >= need) {
+                const bool ok = win[0].first == first_char && (m_lines != 4 || win[2].first == '+');
+                if (ok) { rewindTo(win[0].off); return; }
+                win.erase(win.begin());
+            }
+        }
+    }
+    // Re-reads from an absolute file offset (used once, after syncToRecord looked ahead).
+    void rewindTo(uint64_t off) {
+        if (::lseek(m_fd, (off_t)off, SEEK_SET) < 0) throw std::runtime_error("FastxReader: seek failed");
+        m_file_off = off; m_pos = m_end = 0; m_eof = false;
+    }
+
     // Next line as a view into the block buffer (valid until the next call); std::getline semantics: the
-    // terminating '\n' is stripped, nothing else; a last line without '\n' is delivered.
-    bool nextLine(const char*& line, size_t& len) {
+    // terminating '\n' is stripped, nothing else; a last line without '\n' is delivered.  off = file offset of
+    // the line's first byte (plain files).
+    bool nextLine(const char*& line, size_t& len, uint64_t& off) {
         for (;;) {
             const char* b = m_buf.data() + m_pos;
             const char* nl = m_end > m_pos ? (const char*)std::memchr(b, '\n', m_end - m_pos) : nullptr;
             if (nl) {
-                line = b; len = (size_t)(nl - b);
+                line = b; len = (size_t)(nl - b); off = m_file_off + m_pos;
                 m_pos += len + 1;
                 return true;
             }
             if (m_eof) {
                 if (m_end == m_pos) return false;
-                line = b; len = m_end - m_pos;
+                line = b; len = m_end - m_pos; off = m_file_off + m_pos;
                 m_pos = m_end;
                 return true;
             }
             // no complete line left: move the tail to the front and refill
             const size_t tail = m_end - m_pos;
             if (tail && m_pos) std::memmove(m_buf.data(), b, tail);
+            m_file_off += m_pos;
             m_pos = 0; m_end = tail;
             if (m_end == m_buf.size()) m_buf.resize(m_buf.size() * 2);   // a line longer than the block
             const size_t got = readSome(m_buf.data() + m_end, m_buf.size() - m_end);
@@ -105,4 +158,7 @@ private:
     std::vector<char> m_buf;
     size_t m_pos = 0, m_end = 0;
     bool m_eof = false;
+    uint64_t m_file_off = 0;       // file offset of m_buf[0]
+    uint64_t m_range_end = ~0ULL;
+    bool m_range_done = false;
 };

@@ -28,6 +28,8 @@
 #include <thread>
 #include <vector>
 
+#include <sys/stat.h>
+
 #include "FastxReader.h"
 #include "TSXHashMapCUDA.h"
 
@@ -46,6 +48,7 @@ static struct argp_option options[] = {
     {"dump", 'd', "FILE", 0, "write KMER<TAB>COUNT lines"},
     {"device", 'g', "N", 0, "CUDA device index"},
     {"widevalue", 'w', 0, 0, "widen the value field to every spare entry bit (default: exactly s bits)"},
+    {"readers", 'r', "N", 0, "reader threads on disjoint byte ranges of a plain (not gzip) well-formed input (default 1)"},
     {0}};
 
 struct arguments {
@@ -54,6 +57,7 @@ struct arguments {
     std::string input_path, dump_path, mode = "CUDA";
     bool check = false, checkabort = false, wide = false;
     int device = 0;
+    int readers = 1;
 };
 
 static error_t parse_opt(int key, char* arg, struct argp_state* state) {
@@ -70,6 +74,7 @@ static error_t parse_opt(int key, char* arg, struct argp_state* state) {
         case 'd': a->dump_path = arg ? arg : ""; break;
         case 'g': a->device = atoi(arg); break;
         case 'w': a->wide = true; break;
+        case 'r': a->readers = atoi(arg); break;
         case ARGP_KEY_ARG: return 0;
         default: return ARGP_ERR_UNKNOWN;
     }
@@ -101,9 +106,10 @@ bool encode_kmer(const std::string& s, uint32_t kw, uint64_t* out) {
 }
 
 // Count phase.  The reference has one OpenMP producer that reads 40 records at a time and one task per batch that
-// packs and inserts k-mer by k-mer (main.cpp:132-206).  Here: one reader thread (FastxReader, ~0.9 Gbases/s),
-// `threads` packer threads (tsxc_pack_reads into pinned buffers, ~0.9 Gbases/s each) and the GPU behind
-// tsxc_add_reads, connected by two bounded queues.  Batches may be submitted in any order (counting commutes).
+// packs and inserts k-mer by k-mer (main.cpp:132-206).  Here: reader threads (FastxReader, ~0.9 Gbases/s each; one
+// by default, --readers=N splits a plain file into N byte ranges), `threads`-1 packer threads (tsxc_pack_reads into
+// pinned buffers, ~0.9 Gbases/s each) and the GPU behind tsxc_add_reads, connected by two bounded queues.  Batches
+// may be submitted in any order (counting commutes).
 // A pinned buffer is reused only after a tsxc_sync() that started after its submission returned.
 void countKMers(TSXHashMapCUDA& map, const arguments& args) {
     struct Raw { std::string bases; std::vector<uint64_t> offsets; size_t n = 0; };
@@ -117,16 +123,29 @@ void countKMers(TSXHashMapCUDA& map, const arguments& args) {
     std::mutex mu;
     std::condition_variable cv_raw_free, cv_raw_ready, cv_slot;
     std::deque<Raw*> raw_free, raw_ready;
-    std::vector<Raw> raws(n_packers + 2);
+    int n_readers = std::max(1, std::min(args.readers, 64));
+    uint64_t file_bytes = 0;
+    if (n_readers > 1) {
+        struct stat sb;
+        if (FastxReader::isGzip(args.input_path) || ::stat(args.input_path.c_str(), &sb) != 0 || sb.st_size < (off_t)(n_readers << 16)) {
+            n_readers = 1;   // gzip streams cannot be split; tiny files are not worth it
+        } else {
+            file_bytes = (uint64_t)sb.st_size;
+        }
+    }
+    std::vector<Raw> raws(n_packers + 2 * n_readers);
     for (auto& r : raws) raw_free.push_back(&r);
+    int readers_left = n_readers;
     bool reader_done = false;
     std::exception_ptr failure;
     uint64_t epoch = 0, n_reads_total = 0, n_bad_total = 0;
     bool syncing = false;
 
-    std::thread reader([&] {
+    auto reader = [&](int idx) {
         try {
-            FastxReader rd(args.input_path);
+            const uint64_t lo = n_readers > 1 ? file_bytes / n_readers * idx : 0;
+            const uint64_t hi = n_readers > 1 && idx + 1 < n_readers ? file_bytes / n_readers * (idx + 1) : ~0ULL;
+            FastxReader rd(args.input_path, 4, 8u << 20, lo, hi);
             for (;;) {
                 Raw* r;
                 {
@@ -137,7 +156,7 @@ void countKMers(TSXHashMapCUDA& map, const arguments& args) {
                 }
                 r->n = rd.nextBatch(kBatchReads, r->bases, r->offsets);
                 std::lock_guard<std::mutex> lk(mu);
-                if (r->n == 0) { raw_free.push_back(r); break; }
+                if (r->n == 0) { raw_free.push_back(r); cv_raw_free.notify_one(); break; }
                 raw_ready.push_back(r);
                 cv_raw_ready.notify_one();
             }
@@ -146,9 +165,11 @@ void countKMers(TSXHashMapCUDA& map, const arguments& args) {
             if (!failure) failure = std::current_exception();
         }
         std::lock_guard<std::mutex> lk(mu);
-        reader_done = true;
+        if (--readers_left == 0) reader_done = true;
         cv_raw_ready.notify_all();
-    });
+    };
+    std::vector<std::thread> readers;
+    for (int i = 0; i < n_readers; ++i) readers.emplace_back(reader, i);
 
     auto acquire_slot = [&]() -> Slot* {
         std::unique_lock<std::mutex> lk(mu);
@@ -220,7 +241,7 @@ void countKMers(TSXHashMapCUDA& map, const arguments& args) {
     };
     std::vector<std::thread> packers;
     for (int i = 0; i < n_packers; ++i) packers.emplace_back(packer);
-    reader.join();
+    for (auto& th : readers) th.join();
     for (auto& th : packers) th.join();
     if (failure) std::rethrow_exception(failure);
     map.sync();
@@ -302,6 +323,7 @@ int main(int argc, char* argv[]) {
     std::cerr << "Check=" << (args.check ? "Yes" : "No") << std::endl;
     std::cerr << "Input=" << args.input_path << std::endl;
     std::cerr << "Threads=" << args.threads << std::endl;
+    if (args.readers > 1) std::cerr << "Readers=" << args.readers << std::endl;
     std::cerr << "Mode=" << args.mode << std::endl;
 
     if (args.mode != "CUDA") {
