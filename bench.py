@@ -314,6 +314,16 @@ def main():
                 else "k_partition_reads + k_insert_partitions (two-phase insert, one pair per chunk of reads)",
                 "algorithmic_bytes_per_kmer": 2 * E + in_bytes_per_kmer,
                 "phase_ms": {"partition": st["partition_ms"], "insert": st["insert_ms"]}}
+    # per-kernel view of the two-phase path: bytes each phase has to move per k-mer by design (phase A reads the
+    # packed input and writes one hashed entry to a bin; phase B reads it back and does one RMW of a table entry)
+    per_kernel = []
+    for name, ms, bpk in (("k_partition_reads", st["partition_ms"], in_bytes_per_kmer + E),
+                          ("k_insert_partitions", st["insert_ms"], 3 * E)):
+        if ms and ms > 0:
+            gbs = n_kmers * bpk / (ms * 1e-3) / 1e9
+            per_kernel.append({"kernel": name, "ms_per_step": ms, "share_of_step": ms / st["step_ms"],
+                               "bytes_per_kmer": bpk, "achieved": gbs, "frac": gbs / peak})
+    roofline["kernels"] = per_kernel
     # K0: the random 8-byte RMW rate on a table of the same size, measured live
     k0 = {}
     for mode, name in ((0, "atomic_add"), (2, "sector_load_plus_atomic")):
