@@ -460,7 +460,8 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None):
         in_b = 0.25 * read_len / max(1, read_len - k + 1)
         import bench as _bench
         peak, peak_src = _bench.read_peaks()
-        main_ms = (st["partition_ms"] + st["insert_ms"])
+        n_calls = max(1, args.warmup + args.steps + (0 if args.no_e2e else 1 + args.steps))
+        a2a_step = sc.a2a_bytes // n_calls                               # bytes this rank sent to peers per step
         achieved = n_kmers * (2 * E + in_b) / (T / args.steps) / 1e9   # per GPU: this rank's k-mers over the step time
         line = {
             "metric": "k-mers counted/sec", "value": value, "unit": "Gk-mer/s", "n_gpus": world, "steps": args.steps,
@@ -470,14 +471,17 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None):
                                                 "bin by owner -> NCCL all-to-all over NVLink -> insert)",
                        "k": k, "l_global": l_global, "reads_per_gpu": n_reads, "kmers_per_step": n_kmers * world,
                        "distinct": total_distinct, "entry_bytes": E, "table_bytes_per_gpu": layout["table_bytes"],
-                       "exchange": sc.exchange, "chunks_per_step": sc.chunks // max(1, args.warmup + args.steps + (0 if args.no_e2e else 1 + args.steps)),
-                       "a2a_bytes_per_gpu_per_step": sc.a2a_bytes // max(1, args.warmup + args.steps + (0 if args.no_e2e else 1 + args.steps)),
+                       "exchange": sc.exchange, "chunks_per_step": sc.chunks // n_calls,
+                       "a2a_bytes_per_gpu_per_step": a2a_step,
                        "l2": "inputs and table shards far exceed the 126 MB L2; shards re-zeroed between steps",
                        "timing": "wall clock per step between barrier+synchronize fences, max over ranks; zeroing untimed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "k_partition_reads (bins by owner and region) + k_insert_partitions (per GPU)",
                          "algorithmic_bytes_per_kmer": 2 * E + in_b,
                          "phase_ms_rank0_total": {"route": st["partition_ms"], "insert": st["insert_ms"]}},
+            "nvlink": {"sent_bytes_per_gpu_per_step": a2a_step, "avg_GB_s_per_gpu_per_direction": a2a_step / (T / args.steps) / 1e9,
+                       "note": "payload of the all-to-all averaged over the whole step; the exchange of chunk c runs on a side "
+                               "stream while chunk c+1 is routed and chunk c-1 inserted"},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
