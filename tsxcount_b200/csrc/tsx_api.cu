@@ -53,8 +53,10 @@ struct tsxc_table {
     uint64_t* d_part = nullptr; size_t cap_part = 0;          // words
     uint64_t* d_spill = nullptr; size_t cap_spill = 0;        // words: (hash, count) records of the single-GPU two-phase path
     unsigned long long* d_cursor = nullptr;                   // kMaxParts + 1 (last = ticket)
+    unsigned long long* d_subfill = nullptr; size_t cap_subfill = 0;   // static phase A: fill per (block, bin)
     uint32_t pbits = 0;                                        // log2(#regions); 0 = direct path only
     uint32_t region_log2 = 27;
+    bool part_static = false;                                  // EXPERIMENTAL phase A variant (TSXC_PART_STATIC=1 at creation)
     // launch accounting (bench.py's gpu_launches / roofline come from here)
     uint64_t n_launches = 0, n_main_launches = 0;
     double main_ms = 0.0;
@@ -198,6 +200,27 @@ void launch_partition(uint32_t KW, int threads, int grid, cudaStream_t s, const 
 #undef L_
 }
 
+void launch_partition_static(uint32_t KW, int threads, int grid, cudaStream_t s, const TableView& tv, const PartView& pv,
+                             const uint64_t* d_packed, const uint32_t* d_ends, uint64_t w0, uint64_t w1, uint64_t n_words,
+                             uint64_t n_bases) {
+    if (KW == 4 && threads > 512) threads = 512;
+#define L_(KW_, T_) k_partition_reads_static<KW_, T_><<<grid, T_, 0, s>>>(tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases)
+    if (KW == 1) { if (threads == 1024) L_(1, 1024); else if (threads == 512) L_(1, 512); else L_(1, 256); }
+    else if (KW == 2) { if (threads == 1024) L_(2, 1024); else if (threads == 512) L_(2, 512); else L_(2, 256); }
+    else { if (threads == 512) L_(4, 512); else L_(4, 256); }
+#undef L_
+}
+
+// EXPERIMENTAL (TSXC_PART_STATIC=1): slab capacity of the static phase A for a chunk of chunk_words words: the
+// positions of the block with the most tiles, spread over P bins, + 6 sigma.
+uint64_t static_sub_cap(const PartGeom& g, uint32_t P, uint64_t chunk_words) {
+    const uint64_t tiles = (chunk_words + g.tile_words - 1) / g.tile_words;
+    const uint64_t tiles_per_block = (tiles + g.grid - 1) / g.grid;
+    const double mean = 32.0 * (double)tiles_per_block * g.tile_words / P;
+    const uint64_t cap = (uint64_t)(mean + 6.0 * std::sqrt(mean)) + 16;
+    return (cap + 3) & ~3ULL;
+}
+
 // Two-phase path for tables much larger than the per-SM translation reach (see tsx_kernels.cuh).
 int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words,
                                    uint64_t n_bases, cudaStream_t s) {
@@ -207,8 +230,9 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     // pass, which phase B turns into DRAM row locality and L2 hits (insert 334 / 290 / 261 ms on config 2 for
     // chunks of 2^24 / 2^25 / 2^26 words), so take the largest chunk (up to 2^27 words) whose bins + spill list fit in free HBM.
     static const int chunk_log2_env = [] { const char* e = std::getenv("TSXC_CHUNK_LOG2"); const int v = e ? std::atoi(e) : 0; return (v >= 16 && v <= 30) ? v : 0; }();
+    const bool part_static = t->part_static;
     int chunk_log2 = chunk_log2_env ? chunk_log2_env : 27;
-    uint64_t chunk_words = 0, cap = 0, spill_cap = 0;
+    uint64_t chunk_words = 0, cap = 0, spill_cap = 0, sub_cap = 0;
     PartGeom geo{};
     for (;; --chunk_log2) {
         {   // equal chunks no larger than 2^chunk_log2 / KW words
@@ -218,6 +242,10 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
         }
         geo = part_geometry(t, P, chunk_words);
         cap = geo.cap;
+        if (part_static) {   // bins = grid slabs of sub_cap entries each
+            sub_cap = static_sub_cap(geo, P, chunk_words);
+            cap = (uint64_t)geo.grid * sub_cap;
+        }
         // spill list: one record per 16 positions is far more than homopolymer runs and bin tails ever need;
         // inputs that exceed it (a handful of k-mers making up most of a chunk) are redone by the fused kernel
         spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 16);
@@ -232,6 +260,7 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     int rc = ensure(t, &t->d_part, &t->cap_part, (size_t)P * cap * L.KW);
     if (rc) return rc;
     if ((rc = ensure(t, &t->d_spill, &t->cap_spill, (size_t)spill_cap * (L.KW + 1)))) return rc;
+    if (part_static && (rc = ensure(t, &t->d_subfill, &t->cap_subfill, (size_t)geo.grid * P))) return rc;
     unsigned long long* ticket = t->d_cursor + kMaxParts;
     unsigned long long* spill_n = t->d_cursor + kMaxParts + 1;
     unsigned int* overflow = reinterpret_cast<unsigned int*>(t->d_cursor + kMaxParts + 2);
@@ -241,11 +270,13 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
     pv.spill = t->d_spill; pv.spill_n = spill_n; pv.spill_cap = spill_cap; pv.bins_per_shard_log2 = t->pbits;
     pv.overflow = overflow;
     const uint32_t slice_entries = slice_entries_cfg(t->L.flags);
-    const uint32_t slices = (uint32_t)((cap + slice_entries - 1) / slice_entries);
+    uint32_t slices = (uint32_t)((cap + slice_entries - 1) / slice_entries);
+    uint32_t n_sources = 1;
     const bool agg = !(L.flags & TSXC_FLAG_NO_WARP_AGG);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, s, &ev);
     int main_launches = 0;
+    const PartView pv_bins = pv;   // phase A view; phase B's differs in the static variant
     for (uint64_t w0 = 0; w0 < n_words; w0 += chunk_words) {
         const uint64_t w1 = std::min(n_words, w0 + chunk_words);
         CU(cudaMemsetAsync(t->d_cursor, 0, (kMaxParts + 8) * sizeof(unsigned long long), s));
@@ -254,13 +285,23 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
         std::pair<cudaEvent_t, cudaEvent_t> eva, evb;
         // phase A: bins + spill records, nothing inserted
         const bool ta = main_begin(t, s, &eva);
-        launch_partition(L.KW, geo.threads, grid_a, s, t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases);
+        if (part_static) {
+            PartView pa = pv_bins;                       // [block][bin][sub_cap] slabs, fills at d_subfill[block * P + bin]
+            pa.cap = sub_cap; pa.cursor = t->d_subfill;
+            launch_partition_static(L.KW, geo.threads, grid_a, s, t->tv, pa, d_packed, d_ends, w0, w1, n_words, n_bases);
+            pv = pa;                                     // phase B: every block of phase A is a source
+            pv.P = (uint32_t)grid_a * P;
+            n_sources = (uint32_t)grid_a;
+            slices = (uint32_t)((sub_cap + slice_entries - 1) / slice_entries);
+        } else {
+            launch_partition(L.KW, geo.threads, grid_a, s, t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases);
+        }
         if (ta) { cudaEventRecord(eva.second, s); t->ev_part.push_back(eva); }
         // phase B: bins, then the spill records; both skip when the chunk overflowed its spill list ...
         const bool tb = main_begin(t, s, &evb);
 #define M(KW_, W_)                                                                                                         \
-        if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, 1u, ticket, overflow);  \
-        else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, 1u, ticket, overflow);    \
+        if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, n_sources, ticket, overflow);  \
+        else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, n_sources, ticket, overflow);    \
         k_add_hash_counts<KW_, W_><<<t->sms * 2, kBlockThreads, 0, s>>>(t->tv, t->d_spill, spill_cap, spill_n, overflow);  \
         /* ... in which case the fused kernel redoes the whole chunk (it exits at once otherwise) */                       \
         if (agg) k_count_reads<KW_, W_, true><<<t->sms * 8, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, w0, w1, n_words, n_bases, overflow); \
@@ -355,6 +396,7 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
         const int v = std::atoi(env);
         if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
     }
+    if (const char* env = std::getenv("TSXC_PART_STATIC")) h->part_static = std::atoi(env) == 1;
     if (const char* env = std::getenv("TSXC_REGION_LOG2")) {
         const int v = std::atoi(env);
         if (v >= 16 && v <= 40) h->region_log2 = (uint32_t)v;
@@ -484,7 +526,7 @@ int tsxc_destroy(tsxc_table* t) {
         for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& ev : t->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& m : t->marks) if (m) cudaEventDestroy(m);
-    cudaFree(t->d_part); cudaFree(t->d_spill); cudaFree(t->d_cursor);
+    cudaFree(t->d_part); cudaFree(t->d_spill); cudaFree(t->d_cursor); cudaFree(t->d_subfill);
     cudaFree(t->d_ends); cudaFree(t->d_keys); cudaFree(t->d_counts); cudaFree(t->d_nout);
     cudaFree(t->d_ctr); cudaFree(t->d_words);
     if (t->stream) cudaStreamDestroy(t->stream);

@@ -333,7 +333,6 @@ __global__ void __launch_bounds__(THREADS) k_partition_reads(const __grid_consta
     const unsigned wib = threadIdx.x >> 5;
     const uint32_t R = pv.run;
     const bool hole_possible = KW > 1 || tv.hp.nbits == 64;   // for 2k < 64 no hash has all 64 bits set
-    LocalStats st;
 
     // k-mers that do not go through a bin (groups the extractor already aggregated, k-mers whose bin is full, a
     // hash equal to the hole marker) become (hash, count) records of the owner's spill list.  The kernel never
@@ -443,6 +442,85 @@ __global__ void __launch_bounds__(THREADS) k_partition_reads(const __grid_consta
         const unsigned int f = run_fill[p];
         fill_holes(p, run_base[p].x, f < R ? f : R);
         fill_holes(p, run_base[p].y, f < R ? 0u : (f < 2 * R ? f - R : R));
+    }
+}
+
+// Phase A, static variant (EXPERIMENTAL, selected with TSXC_PART_STATIC=1; not validated on hardware yet — see
+// DESIGN.md §9 item 2a).  Every block owns ONE slab of pv.cap entries per bin for the whole chunk, laid out
+// [block][bin][pv.cap], so a k-mer costs one shared-memory atomicAdd and one store: no run bases to load, no run
+// rotation, no barrier between tiles, no holes, and a block's stores stay inside its own P * cap * 8 * KW byte
+// window.  The fill counts go to pv.cursor[block * P + bin]; phase B drains the slabs as n_sources = gridDim.x
+// sources.  A slab that runs full sends its k-mers to the spill list like a full bin does.
+template <int KW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_partition_reads_static(const __grid_constant__ TableView tv,
+                                                                          const __grid_constant__ PartView pv,
+                                                                          const uint64_t* __restrict__ packed,
+                                                                          const uint32_t* __restrict__ ends, uint64_t w_begin,
+                                                                          uint64_t w_end, uint64_t n_words, uint64_t n_bases) {
+    constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
+    const uint64_t kTileWords = pv.tile_words;
+    __shared__ unsigned int fill[kMaxParts];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned wib = threadIdx.x >> 5;
+    const bool hole_possible = KW > 1 || tv.hp.nbits == 64;   // phase B skips entries whose word 0 is the hole marker
+    uint64_t* const slab = pv.buf + (uint64_t)blockIdx.x * pv.P * pv.cap * KW;
+
+    auto cold = [&](const Key<KW>& H, uint64_t cnt) {
+        const uint32_t owner = (uint32_t)(((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask) >> pv.bins_per_shard_log2;
+        const unsigned long long at = atomicAdd(pv.spill_n + owner, 1ULL);
+        if (at >= pv.spill_cap) { *pv.overflow = 1u; return; }
+        uint64_t* dst = pv.spill + ((uint64_t)owner * pv.spill_cap + at) * (KW + 1);
+#pragma unroll
+        for (int j = 0; j < KW; ++j) dst[j] = H.w[j];
+        dst[KW] = cnt;
+    };
+
+    for (uint32_t p = threadIdx.x; p < pv.P; p += blockDim.x) fill[p] = 0;
+    __syncthreads();
+
+    // one k-mer per lane in flight, as in k_partition_reads: the ATOMS round trip overlaps the next extraction
+    Key<KW> pend_h;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) pend_h.w[j] = 0;
+    uint32_t pend_p = 0;
+    unsigned int pend_idx = 0;
+    bool pend = false;
+    auto complete = [&]() {
+        if (!pend) return;
+        pend = false;
+        if ((uint64_t)pend_idx < pv.cap) {
+            uint64_t* dst = slab + ((uint64_t)pend_p * pv.cap + pend_idx) * KW;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) __stcg(dst + j, pend_h.w[j]);
+        } else {
+            cold(pend_h, 1);
+        }
+    };
+
+    for (uint64_t tile = w_begin + (uint64_t)blockIdx.x * kTileWords; tile < w_end; tile += (uint64_t)gridDim.x * kTileWords) {
+        const uint64_t tile_end = tile + kTileWords < w_end ? tile + kTileWords : w_end;
+        for (uint64_t base = tile + wib * 32; base < tile_end; base += (THREADS / 32) * 32) {
+            uint64_t win[KW + 1];
+            uint32_t ewin[NE + 1];
+            load_window<KW, uint64_t>(packed, base, n_words, lane, win);
+            load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
+            const uint64_t limit = (base + lane < tile_end) ? n_bases : 0;
+            for_each_kmer_group<KW, false>(win, ewin[0], first_end_after<NE>(ewin), base + lane, limit, tv.L.k, tv.hp,
+                                           [&](const Key<KW>& key, uint64_t cnt) {
+                                               const Key<KW> H = hash_key<KW>(key, tv.hp);
+                                               if (cnt >= 2 || (hole_possible && H.w[0] == kHole)) { cold(H, cnt); return; }
+                                               const uint32_t p = (uint32_t)((H.w[0] & tv.lbg_mask) >> pv.pshift) & pv.pmask;
+                                               const unsigned int idx = atomicAdd(&fill[p], 1u);
+                                               complete();                 // the previous k-mer of this lane
+                                               pend_h = H; pend_p = p; pend_idx = idx; pend = true;
+                                           });
+        }
+    }
+    complete();
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < pv.P; p += blockDim.x) {
+        const unsigned int f = fill[p];
+        pv.cursor[(uint64_t)blockIdx.x * pv.P + p] = (uint64_t)f < pv.cap ? f : pv.cap;
     }
 }
 
