@@ -197,3 +197,36 @@ def test_feeder_byte_ranges_more_ranges_than_records(tmp_path):
     seqs = sequtils.read_fastq(p)
     for ranges in (2, 5, 13, 26):
         assert _run_ingest(p, 10, 16, ranges)[:5] == _expected_ingest(seqs)[:5]
+
+
+def test_feeder_multiline_fasta_split_keeps_the_kmer_multiset(tmp_path):
+    """Extension over the reference: multi-line FASTA, soft-masked bases, long sequences cut into pieces that
+    overlap by k-1 bases.  The pieces must match the Python mirror and carry exactly the k-mers of the records."""
+    import random
+    from tsxcount_b200 import sequtils
+    rnd = random.Random(11)
+    k = 21
+    recs = [rnd.randint(1, 7000) for _ in range(12)] + [k - 1, k, 1000, 2000, 1000 + (1000 - (k - 1)), 0]
+    whole = []
+    p = tmp_path / "g.fa"
+    with open(p, "w") as f:
+        for i, n in enumerate(recs):
+            seq = "".join(rnd.choice("ACGTacgtN" if rnd.random() < 0.02 else "ACGTacgt") for _ in range(n))
+            whole.append(seq.upper().encode())
+            f.write(f">chr{i} some description\n")
+            for j in range(0, n, 60):
+                f.write(seq[j:j + 60] + "\n")
+            if rnd.random() < 0.3:
+                f.write("\n")
+    env = dict(os.environ, INGEST_PIECE="1000", INGEST_OVERLAP=str(k - 1))
+    want_pieces = sequtils.read_fasta(p, piece_len=1000, overlap=k - 1)
+    want = _expected_ingest(want_pieces)
+    for batch, block in ((1 << 18, 8 << 20), (3, 64), (1, 100)):
+        out = subprocess.run([INGEST, str(p), str(batch), str(block)], capture_output=True, text=True, check=True, env=env).stdout
+        kv = dict(item.split("=") for item in out.split())
+        got = (int(kv["reads"]), int(kv["bases"]), int(kv["bad"]), int(kv["hash_bases"], 16), int(kv["hash_lens"], 16))
+        assert got == want[:5], (batch, block)
+    a, b = orc.count_seqs([w for w in whole if w], k), orc.count_seqs(want_pieces, k)
+    assert a.n_total == b.n_total and a.n_distinct == b.n_distinct
+    assert (a.keys == b.keys).all() and (a.counts == b.counts).all()
+    assert max(len(x) for x in want_pieces) == 1000

@@ -7,6 +7,10 @@
 //     the sequence is the 2nd line (:70, :108); a trailing incomplete record is dropped (:242);
 //   - gzip input is inflated with zlib (:387-440; the reference sniffs the ".gz" suffix, :185-190 — here the
 //     gzip magic bytes decide, so a mis-named file still works).
+// Beyond the reference (opt-in, lines_per_record = 0 = auto-detect): a file whose first non-empty byte is '>' is read
+// as multi-line FASTA — a record is a '>' header plus all following lines up to the next header, lower-case
+// (soft-masked) bases are folded to upper case, and a sequence longer than piece_len bases is delivered as pieces
+// that overlap by `overlap` (= k-1) bases, which preserves the multiset of k-mers exactly.
 // Instead of a vector of entry objects with three std::string copies per record (:239-253) the reader scans
 // lines in place in a large block buffer (memchr) and appends only the sequence lines to one buffer plus an
 // offsets array — the layout tsxc_pack_reads takes.  ~0.8 GB/s of FASTQ text per thread.
@@ -39,19 +43,41 @@ public:
         if (m_fd < 0) throw std::runtime_error("FastxReader: cannot open " + path);
         unsigned char magic[2] = {0, 0};
         const ssize_t got = ::pread(m_fd, magic, 2, 0);
+        auto die = [&](const std::string& msg) {       // a throwing constructor runs no destructor
+            if (m_gz) gzclose(m_gz); else ::close(m_fd);
+            throw std::runtime_error("FastxReader: " + msg);
+        };
         if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-            if (range_begin != 0 || range_end != ~0ULL) { ::close(m_fd); throw std::runtime_error("FastxReader: byte ranges need a plain file"); }
+            if (range_begin != 0 || range_end != ~0ULL) die("byte ranges need a plain file");
             m_gz = gzdopen(m_fd, "rb");
-            if (!m_gz) { ::close(m_fd); throw std::runtime_error("FastxReader: gzdopen failed for " + path); }
+            if (!m_gz) die("gzdopen failed for " + path);
             gzbuffer(m_gz, 1 << 20);
-        } else if (range_begin > 0) {
+        }
+        if (m_lines == 0) {                            // auto: '>' -> multi-line FASTA, anything else -> FASTQ
+            m_multi_fasta = (range_begin == 0 ? firstByte() : sniff(path)) == '>';
+            m_lines = m_multi_fasta ? 2 : 4;
+            if (m_multi_fasta && (range_begin != 0 || range_end != ~0ULL)) die("byte ranges need FASTQ input");
+        }
+        if (!m_gz && range_begin > 0) {
             // start one byte early: if that byte is '\n', range_begin is the start of a line
-            if (::lseek(m_fd, (off_t)(range_begin - 1), SEEK_SET) < 0) throw std::runtime_error("FastxReader: seek failed");
+            if (::lseek(m_fd, (off_t)(range_begin - 1), SEEK_SET) < 0) die("seek failed");
+            m_pos = m_end = 0; m_eof = false;          // auto-detection may have buffered the start of the file
             m_file_off = range_begin - 1;
             const char* l; size_t n; uint64_t off;
             nextLine(l, n, off);                       // the (rest of the) line we landed in belongs to the previous range
             syncToRecord();
         }
+    }
+
+    // Multi-line FASTA only: sequences longer than piece_len are split into pieces overlapping by `overlap` bases.
+    void setFastaSplit(size_t piece_len, size_t overlap) {
+        if (piece_len <= overlap) throw std::runtime_error("FastxReader: piece length must exceed the overlap");
+        m_piece_len = piece_len; m_overlap = overlap;
+    }
+    bool isMultiFasta() const { return m_multi_fasta; }
+    // '@', '>' or 0 (empty / unreadable): first non-empty byte of the (possibly gzip) file
+    static char sniff(const std::string& path) {
+        try { FastxReader r(path, 4, 1u << 16); return r.firstByte(); } catch (...) { return 0; }
     }
 
     static bool isGzip(const std::string& path) {
@@ -72,6 +98,7 @@ public:
     // Appends up to max_reads sequences to `bases`; offsets gets n+1 entries (offsets[0] == 0).
     // Returns the number of reads delivered (0 at end of file).
     size_t nextBatch(size_t max_reads, std::string& bases, std::vector<uint64_t>& offsets) {
+        if (m_multi_fasta) return nextBatchFasta(max_reads, bases, offsets);
         bases.clear();
         offsets.assign(1, 0);
         while (offsets.size() - 1 < max_reads && !m_range_done) {
@@ -92,6 +119,51 @@ public:
     }
 
 private:
+    // Multi-line FASTA.  The piece under construction is the tail of `bases` after offsets.back(); when a batch
+    // ends with an open piece, the piece moves to m_carry and continues in the next batch.
+    size_t nextBatchFasta(size_t max_reads, std::string& bases, std::vector<uint64_t>& offsets) {
+        const size_t kMaxBatchBases = 64u << 20;
+        bases.assign(m_carry);
+        m_carry.clear();
+        offsets.assign(1, 0);
+        auto close_piece = [&] {                       // end of a record: deliver what is left if it has new bases
+            if (m_fresh) offsets.push_back(bases.size()); else bases.resize(offsets.back());
+            m_fresh = 0;
+        };
+        while (offsets.size() - 1 < max_reads && offsets.back() < kMaxBatchBases) {
+            const char* line;
+            size_t len;
+            uint64_t off;
+            if (!nextLine(line, len, off)) { close_piece(); return offsets.size() - 1; }
+            if (len == 0) continue;
+            if (line[0] == '>') { close_piece(); continue; }
+            const size_t at = bases.size();
+            bases.append(line, len);
+            for (size_t i = at; i < bases.size(); ++i) { const char c = bases[i]; if (c >= 'a' && c <= 'z') bases[i] = (char)(c - 32); }
+            m_fresh += len;
+            while (bases.size() - offsets.back() >= m_piece_len) {
+                const size_t end = offsets.back() + m_piece_len;       // the piece is bases[offsets.back(), end)
+                const std::string lap = bases.substr(end - m_overlap, m_overlap);
+                m_fresh = bases.size() - end;                           // bases of the record not delivered yet
+                bases.insert(end, lap);                                 // next piece = overlap + the rest
+                offsets.push_back(end);
+            }
+        }
+        // batch full: an open piece continues in the next batch
+        m_carry.assign(bases, offsets.back(), std::string::npos);
+        bases.resize(offsets.back());
+        return offsets.size() - 1;
+    }
+    char firstByte() {
+        for (;;) {
+            for (size_t i = m_pos; i < m_end; ++i) if (m_buf[i] != '\n') return m_buf[i];
+            if (m_eof) return 0;
+            m_file_off += m_end; m_pos = m_end = 0;    // only newlines so far: drop them
+            const size_t got = readSome(m_buf.data(), m_buf.size());
+            if (got == 0) m_eof = true;
+            m_end = got;
+        }
+    }
     size_t readSome(char* dst, size_t n) {
         if (m_gz) { const int r = gzread(m_gz, dst, (unsigned)n); return r > 0 ? (size_t)r : 0; }
         const ssize_t r = ::read(m_fd, dst, n);
@@ -161,4 +233,7 @@ private:
     uint64_t m_file_off = 0;       // file offset of m_buf[0]
     uint64_t m_range_end = ~0ULL;
     bool m_range_done = false;
+    bool m_multi_fasta = false;
+    size_t m_piece_len = 1u << 20, m_overlap = 0, m_fresh = 0;
+    std::string m_carry;
 };

@@ -125,6 +125,8 @@ void countKMers(TSXHashMapCUDA& map, const arguments& args) {
     std::deque<Raw*> raw_free, raw_ready;
     int n_readers = std::max(1, std::min(args.readers, 64));
     uint64_t file_bytes = 0;
+    const bool multi_fasta = FastxReader::sniff(args.input_path) == '>';   // extension: multi-line FASTA input
+    if (multi_fasta) n_readers = 1;                  // records are whole chromosomes: one sequential reader
     if (n_readers > 1) {
         struct stat sb;
         if (FastxReader::isGzip(args.input_path) || ::stat(args.input_path.c_str(), &sb) != 0 || sb.st_size < (off_t)(n_readers << 16)) {
@@ -145,7 +147,8 @@ void countKMers(TSXHashMapCUDA& map, const arguments& args) {
         try {
             const uint64_t lo = n_readers > 1 ? file_bytes / n_readers * idx : 0;
             const uint64_t hi = n_readers > 1 && idx + 1 < n_readers ? file_bytes / n_readers * (idx + 1) : ~0ULL;
-            FastxReader rd(args.input_path, 4, 8u << 20, lo, hi);
+            FastxReader rd(args.input_path, multi_fasta ? 0 : 4, 8u << 20, lo, hi);
+            if (multi_fasta) rd.setFastaSplit(1u << 20, args.k - 1);   // pieces overlap by k-1 bases: same k-mer multiset
             for (;;) {
                 Raw* r;
                 {

@@ -71,6 +71,40 @@ def read_fastq(path, lines_per_record=4):
     return seqs
 
 
+def read_fasta(path, piece_len=1 << 20, overlap=0):
+    """Multi-line FASTA (mirror of FastxReader's auto-detected FASTA mode, an extension over the reference): a
+    record is a '>' header plus all lines up to the next header; bases are upper-cased; a sequence longer than
+    piece_len is cut into pieces overlapping by `overlap` (= k-1) bases, which keeps the k-mer multiset."""
+    if piece_len <= overlap:
+        raise ValueError("piece length must exceed the overlap")
+    opener = gzip.open if str(path).endswith(".gz") else open
+    records, cur = [], None
+    with opener(path, "rb") as f:
+        for raw in f:
+            line = raw[:-1] if raw.endswith(b"\n") else raw
+            if len(line) == 0:
+                continue
+            if line[:1] == b">":
+                if cur:
+                    records.append(b"".join(cur))
+                cur = []
+            elif cur is not None:
+                cur.append(bytes(c - 32 if 97 <= c <= 122 else c for c in line))
+            else:                      # sequence lines before the first header still form a record
+                cur = [bytes(c - 32 if 97 <= c <= 122 else c for c in line)]
+    if cur:
+        records.append(b"".join(cur))
+    pieces = []
+    for s in records:
+        start = 0
+        while len(s) - start > piece_len:
+            pieces.append(s[start:start + piece_len])
+            start += piece_len - overlap
+        if len(s) - start > (overlap if start else 0):
+            pieces.append(s[start:])
+    return pieces
+
+
 def concat_reads(seqs):
     """list of bytes -> (ascii uint8 array, offsets uint64[n+1])"""
     lens = np.fromiter((len(s) for s in seqs), dtype=np.uint64, count=len(seqs))
