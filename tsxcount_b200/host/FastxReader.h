@@ -20,6 +20,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -137,16 +138,22 @@ private:
             if (!nextLine(line, len, off)) { close_piece(); return offsets.size() - 1; }
             if (len == 0) continue;
             if (line[0] == '>') { close_piece(); continue; }
-            const size_t at = bases.size();
-            bases.append(line, len);
-            for (size_t i = at; i < bases.size(); ++i) { const char c = bases[i]; if (c >= 'a' && c <= 'z') bases[i] = (char)(c - 32); }
-            m_fresh += len;
-            while (bases.size() - offsets.back() >= m_piece_len) {
-                const size_t end = offsets.back() + m_piece_len;       // the piece is bases[offsets.back(), end)
-                const std::string lap = bases.substr(end - m_overlap, m_overlap);
-                m_fresh = bases.size() - end;                           // bases of the record not delivered yet
-                bases.insert(end, lap);                                 // next piece = overlap + the rest
-                offsets.push_back(end);
+            for (size_t consumed = 0; consumed < len;) {
+                const size_t cur = bases.size() - offsets.back();
+                const size_t take = std::min(len - consumed, m_piece_len - cur);
+                const size_t at = bases.size();
+                bases.append(line + consumed, take);
+                char* dst = &bases[at];
+                for (size_t i = 0; i < take; ++i) { const char c = dst[i]; dst[i] = (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
+                consumed += take;
+                m_fresh += take;
+                if (bases.size() - offsets.back() == m_piece_len) {     // piece full: the next one starts with its last k-1 bases
+                    const size_t end = bases.size();
+                    offsets.push_back(end);
+                    const std::string lap = bases.substr(end - m_overlap, m_overlap);
+                    bases.append(lap);
+                    m_fresh = 0;
+                }
             }
         }
         // batch full: an open piece continues in the next batch
