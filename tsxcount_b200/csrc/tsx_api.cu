@@ -281,7 +281,8 @@ int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, cons
         const uint64_t w1 = std::min(n_words, w0 + chunk_words);
         CU(cudaMemsetAsync(t->d_cursor, 0, (kMaxParts + 8) * sizeof(unsigned long long), s));
         const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w1 - w0 + geo.tile_words - 1) / geo.tile_words, (uint64_t)geo.grid));
-        const int grid_b = t->sms * 8;
+        static const int insert_blocks_per_sm = [] { const char* e = std::getenv("TSXC_INSERT_GRID"); const int v = e ? std::atoi(e) : 0; return (v >= 1 && v <= 16) ? v : 8; }();
+        const int grid_b = t->sms * insert_blocks_per_sm;
         std::pair<cudaEvent_t, cudaEvent_t> eva, evb;
         // phase A: bins + spill records, nothing inserted
         const bool ta = main_begin(t, s, &eva);
