@@ -164,3 +164,49 @@ def test_read_fastq_reference_semantics(tmp_path):
     with gzip.open(gz, "wb") as f:
         f.write(b"@r1\nACGT\n+\n&&&&\n")
     assert sequtils.read_fastq(gz) == [b"ACGT"]
+
+
+def test_pack_reads_randomized_against_numpy_packer():
+    """Independent check of the SWAR / AVX2 packer: random read lengths (every alignment of the 8- and 32-base fast
+    paths), non-ACGT bytes at random places, against a straightforward numpy packer with the same N policy."""
+    rng = np.random.default_rng(77)
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for trial in range(30):
+        n = int(rng.integers(1, 60))
+        seqs = []
+        for _ in range(n):
+            s = alphabet[rng.integers(0, 4, size=int(rng.integers(0, 300)))].copy()
+            if len(s) and rng.random() < 0.4:
+                bad = rng.integers(0, len(s), size=int(rng.integers(1, 4)))
+                s[bad] = rng.choice(np.frombuffer(b"Nacgt@[`BDH", dtype=np.uint8), size=len(bad))
+            seqs.append(s.tobytes())
+        ascii_, off = sequtils.concat_reads(seqs)
+        packed, seg, nbad = sequtils.pack_reads(ascii_, off)
+        # reference packer: drop the bad bytes, remember where segments end
+        code = np.full(256, 255, dtype=np.uint8)
+        code[[65, 67, 71, 84]] = [0, 1, 2, 3]
+        c = code[ascii_]
+        good = c != 255
+        assert nbad == int((~good).sum())
+        codes = c[good].astype(np.uint64)
+        total = len(codes)
+        want = np.zeros(total // 32 + 2, dtype=np.uint64)
+        idx = np.arange(total)
+        np.bitwise_or.at(want, idx // 32, codes << (2 * (idx % 32)).astype(np.uint64))
+        assert int(seg[-1]) == total
+        assert np.array_equal(packed[: (total + 31) // 32], want[: (total + 31) // 32])
+        # segment boundaries: after every read end and at every bad byte, counted in kept bases; empty segments
+        # only come from reads (a bad byte never opens an empty segment)
+        kept_before = np.concatenate([[0], np.cumsum(good)])
+        bounds = [0]
+        for r in range(len(seqs)):
+            b, e = int(off[r]), int(off[r + 1])
+            start = int(kept_before[b])
+            for i in range(b, e):
+                if not good[i]:
+                    g = int(kept_before[i])
+                    if g > start:
+                        bounds.append(g)
+                    start = g
+            bounds.append(int(kept_before[e]))
+        assert seg.tolist() == bounds

@@ -11,9 +11,14 @@
 //
 // Fast path: 8 bases at a time.  For the four valid letters ((c >> 1) ^ (c >> 2)) & 3 is exactly the code
 // (A 0x41 -> 0, C 0x43 -> 1, G 0x47 -> 2, T 0x54 -> 3); a SWAR test proves that all 8 bytes are valid letters,
-// anything else drops to the byte-wise path.
+// anything else drops to the byte-wise path.  Where the CPU has AVX2 (checked at run time) 32 bases are packed per
+// step into one whole output word.
 #include <cstdint>
 #include <cstring>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define TSXC_HAVE_AVX2_PATH 1
+#endif
 
 #include "../../include/tsxcount_cuda.h"
 
@@ -43,6 +48,27 @@ inline bool all_acgt(uint64_t x) {
     const uint64_t ok = zero_bytes(x ^ rep('A')) | zero_bytes(x ^ rep('C')) | zero_bytes(x ^ rep('G')) | zero_bytes(x ^ rep('T'));
     return ok == kHi;
 }
+
+#ifdef TSXC_HAVE_AVX2_PATH
+// 32 ASCII bases -> 64 bits of codes (base i at bits [2i, 2i+1]); false if any byte is not one of ACGT
+__attribute__((target("avx2"))) inline bool codes32_avx2(const char* p, uint64_t* out) {
+    const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p));
+    const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('A')), _mm256_cmpeq_epi8(x, _mm256_set1_epi8('C'))),
+                                       _mm256_or_si256(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('G')), _mm256_cmpeq_epi8(x, _mm256_set1_epi8('T'))));
+    if ((unsigned)_mm256_movemask_epi8(ok) != 0xffffffffu) return false;
+    // per byte: ((c >> 1) ^ (c >> 2)) & 3; the 16-bit shifts only leak neighbour bits above bit 5
+    const __m256i c = _mm256_and_si256(_mm256_xor_si256(_mm256_srli_epi16(x, 1), _mm256_srli_epi16(x, 2)), _mm256_set1_epi8(3));
+    const __m256i n = _mm256_maddubs_epi16(c, _mm256_set1_epi16(0x0401));       // 16-bit lanes: c0 + 4*c1
+    const __m256i b = _mm256_madd_epi16(n, _mm256_set1_epi32(0x00100001));      // 32-bit lanes: n0 + 16*n1 (one byte)
+    // byte 0 of every dword -> the low 4 bytes of each 128-bit half
+    const __m256i sh = _mm256_shuffle_epi8(b, _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                                                0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1));
+    const uint64_t lo = (uint32_t)_mm256_extract_epi32(sh, 0), hi = (uint32_t)_mm256_extract_epi32(sh, 4);
+    *out = lo | (hi << 32);
+    return true;
+}
+const bool kHaveAvx2 = __builtin_cpu_supports("avx2");
+#endif
 }  // namespace
 
 extern "C" int tsxc_pack_reads(const char* ascii, const uint64_t* offsets, uint64_t n_reads, uint64_t* packed_out,
@@ -63,11 +89,27 @@ extern "C" int tsxc_pack_reads(const char* ascii, const uint64_t* offsets, uint6
         }
         g += n;
     };
+    auto put_word = [&](uint64_t codes) {                 // append 32 bases (64 bits)
+        const unsigned pos = (unsigned)(g & 31);
+        if (pos == 0) {
+            packed_out[g >> 5] = codes;
+        } else {
+            packed_out[g >> 5] = acc | (codes << (2 * pos));
+            acc = codes >> (64 - 2 * pos);
+        }
+        g += 32;
+    };
     for (uint64_t r = 0; r < n_reads; ++r) {
         const uint64_t b = offsets[r], e = offsets[r + 1];
         uint64_t seg_start = g;
         uint64_t i = b;
         while (i < e) {
+#ifdef TSXC_HAVE_AVX2_PATH
+            if (kHaveAvx2 && i + 32 <= e) {
+                uint64_t c64;
+                if (codes32_avx2(ascii + i, &c64)) { put_word(c64); i += 32; continue; }
+            }
+#endif
             if (i + 8 <= e) {
                 uint64_t x;
                 std::memcpy(&x, ascii + i, 8);
