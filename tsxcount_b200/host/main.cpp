@@ -53,7 +53,7 @@ static struct argp_option options[] = {
 
 struct arguments {
     uint16_t k = 14, l = 26, storagebits = 4;   // main.cpp:409-413
-    int threads = 3;   // 1 reader + 2 packers: the reader (~0.9 Gbases/s) is the limit; measured 0.6 Gbases/s end to end
+    int threads = 3;   // 1 reader + 2 packers: a reader (~1 Gbases/s) is slower than a packer (~2 with AVX2); more input bandwidth: --readers
     std::string input_path, dump_path, mode = "CUDA";
     bool check = false, checkabort = false, wide = false;
     int device = 0;
@@ -108,7 +108,7 @@ bool encode_kmer(const std::string& s, uint32_t kw, uint64_t* out) {
 // Count phase.  The reference has one OpenMP producer that reads 40 records at a time and one task per batch that
 // packs and inserts k-mer by k-mer (main.cpp:132-206).  Here: reader threads (FastxReader, ~0.9 Gbases/s each; one
 // by default, --readers=N splits a plain file into N byte ranges), `threads`-1 packer threads (tsxc_pack_reads into
-// pinned buffers, ~0.9 Gbases/s each) and the GPU behind tsxc_add_reads, connected by two bounded queues.  Batches
+// pinned buffers, ~2 Gbases/s each with AVX2) and the GPU behind tsxc_add_reads, connected by two bounded queues.  Batches
 // may be submitted in any order (counting commutes).
 // A pinned buffer is reused only after a tsxc_sync() that started after its submission returned.
 void countKMers(TSXHashMapCUDA& map, const arguments& args) {
