@@ -4,7 +4,8 @@
 NVCC     ?= /usr/local/cuda/bin/nvcc
 HOSTCXX  := $(shell [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo g++)
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas -ccbin $(HOSTCXX) -cudart static
+EXTRA_DEFS ?=
+NVFLAGS  := $(EXTRA_DEFS) $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas -ccbin $(HOSTCXX) -cudart static
 CSRC     := tsxcount_b200/csrc
 HOST     := tsxcount_b200/host
 LIBDIR   := tsxcount_b200/lib
@@ -38,3 +39,9 @@ oracle:
 clean:
 	rm -rf $(LIBDIR) $(BINDIR)
 	$(MAKE) -C oracle clean
+
+# A/B builds of the kernels for experiments (not shipped): make variant NAME=match EXTRA_DEFS=-DTSX_RANK_MATCH
+# -> tsxcount_b200/lib/libtsxcuda_$(NAME).so, picked up with TSXC_LIB=<path> (tsxcount_b200/_lib.py)
+variant:
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -o $(LIBDIR)/libtsxcuda_$(NAME).so $(CSRC)/tsx_api.cu $(CSRC)/tsx_host_pack.cpp

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TSXC_ABI_VERSION 1
+#define TSXC_ABI_VERSION 2
 #define TSXC_MAX_K 128
 
 /* ---- status codes ------------------------------------------------------------------------ */
@@ -57,15 +57,12 @@ enum {
 #define TSXC_FLAG_EXACT_S 1u
 /* Disable warp-level pre-aggregation (__match_any_sync) — for measurements only. */
 #define TSXC_FLAG_NO_WARP_AGG 2u
-/* Always use the single fused extract+insert kernel, never the two-phase region-partitioned path that
- * large tables take by default (DESIGN.md "TLB-aware insert") — for A/B measurements. */
+/* Always use the single fused extract+insert kernel, never the region-sorted pipeline that large tables take by
+ * default (DESIGN.md "Why a sort by table region") — for A/B measurements. */
 #define TSXC_FLAG_DIRECT 4u
-/* Hint: a few k-mers make up a large share of the input (Zipf-like reads, amplicons).  Phase B of the two-phase
- * path then drains the bins in slices 16x as long, which spreads the resident thread blocks over many table
- * regions instead of concentrating them on one: with dominant k-mers the concentration turns into contention on
- * their table entries (config 3: insert 541 ms with short slices, 212 ms with long ones; the opposite holds for
- * uniform k-mers, config 2: 249 ms vs 391 ms).  Counts are identical either way. */
-#define TSXC_FLAG_SKEWED 8u
+/* (Round 1 had TSXC_FLAG_SKEWED = 8, a caller hint for inputs dominated by a few k-mers.  The pipeline now sizes
+ * every bin from exact histograms and combines duplicates in shared memory before they reach the table, so there is
+ * nothing left to hint; the bit is ignored.) */
 
 typedef struct tsxc_table tsxc_table; /* opaque */
 
@@ -90,8 +87,14 @@ typedef struct tsxc_stats_t {
     uint64_t kernel_launches;     /* kernels of this library launched on the handle since create/clear */
     uint64_t main_kernel_launches;/* launches of the dominant (extract+insert / insert) kernels among them */
     double   main_kernel_ms;      /* their summed device time (CUDA events on the handle's stream) */
-    double   partition_ms;        /* of which: phase A (extract+hash+bin) of the two-phase path */
-    double   insert_ms;           /* of which: phase B (insert from bins) of the two-phase path */
+    double   partition_ms;        /* of which: histogram + both radix partition passes of the region-sorted pipeline */
+    double   insert_ms;           /* of which: phase B (insert in table-region order) */
+    double   hist_ms;             /* partition_ms split: S0 (extract+hash+digit-1 histogram, chunk planner) */
+    double   part1_ms;            /*                     S1 (extract+hash+tile sort by digit 1) */
+    double   part2_ms;            /*                     S2 (digit-2 histogram, scan, tile sort by digit 2) */
+    uint64_t chunk_cap_keys;      /* capacity of key buffer A: k-mers per insert pass (0 until the pipeline ran) */
+    uint64_t group_cap_keys;      /* capacity of key buffer B */
+    uint32_t radix_digit1_bits, radix_digit2_bits;
 } tsxc_stats_t;
 
 /* Words per k-mer for this k: 1 (k<=32), 2 (k<=64), 4 (k<=128); 0 if k is out of range. */
@@ -117,6 +120,9 @@ int tsxc_create_shard(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t f
 int tsxc_destroy(tsxc_table* t);
 /* Re-zero the table and its counters (no reference counterpart; used between benchmark passes). */
 int tsxc_clear(tsxc_table* t);
+/* Give back the key buffers of the insert pipeline (they take whatever HBM the table leaves free and are sized
+ * again by the next batch).  Waits for queued work.  No effect while the buffers are exported to peer ranks. */
+int tsxc_trim(tsxc_table* t);
 /* The CUDA stream (cudaStream_t) the handle queues work on, as an opaque pointer. */
 void* tsxc_stream(tsxc_table* t);
 
@@ -155,53 +161,47 @@ int tsxc_dump_file(tsxc_table* t, const char* path);
 int tsxc_stats(tsxc_table* t, tsxc_stats_t* out);
 
 /* ---- multi-GPU routing (hash-sharded table) ------------------------------- */
-/* Data path of one chunk of reads on a box of n_shards GPUs (one process per GPU, each holding one shard):
- *   sender    tsxc_route_chunk   extract + hash, bin every k-mer by (owning shard, table region of that shard)
- *   exchange  the caller moves block `o` of the bins / cursors / spill lists to shard o (all-to-all over NVLink;
- *             torch.distributed/NCCL in tsxcount_b200/multigpu.py, or peer copies)
- *   receiver  tsxc_insert_routed inserts the received bins region by region (the same phase B the single-GPU
- *             path uses), tsxc_add_hash_counts_device inserts the received spill records.
+/* One process per GPU, each holding one shard (tsxc_create_shard).  A batch of reads is counted in rounds; in every
+ * round each rank routes one chunk of its reads and inserts what it receives.  Per round, all on the handle's stream:
+ *   tsxc_route_hist    this rank's exact k-mer counts per routing bin (owner-major) -> caller's d_hist (bins x uint32)
+ *   [caller]           all-gather of d_hist over the ranks (NCCL) -> d_hist_all (n_shards x bins x uint32)
+ *   tsxc_route_send    every rank derives from d_hist_all where each of its bins starts in each owner's receive
+ *                      buffer; the routing kernel (extract + hash + tile sort) then stores its runs STRAIGHT INTO the
+ *                      owners' peer-mapped buffers over NVLink: compute and exchange are one kernel
+ *   [caller]           a barrier collective on the stream (all stores have landed)
+ *   tsxc_route_insert  sort the received k-mers by fine table region and insert them (same kernels as one GPU)
+ *   [the next round's all-gather doubles as "every receive buffer has been drained"]
+ * Sizes are exact, so nothing can overflow silently: if a round would exceed a receive buffer, every rank sees it in
+ * d_hist_all, all of them skip the round, and tsxc_sync reports TSXC_E_INVALID.
  * (No reference counterpart: the reference is one process on one shared table, src/mains/main.cpp:132-218.) */
-typedef struct tsxc_route_layout_t {
-    uint32_t n_shards;
-    uint32_t bins_per_shard;      /* table regions per shard */
-    uint32_t key_words;           /* KW: words per hash */
-    uint32_t spill_record_words;  /* KW + 1: hash + count */
-    uint64_t chunk_words;         /* packed stream words one tsxc_route_chunk call may cover */
-    uint64_t bin_cap;             /* entries per bin */
-    uint64_t block_words;         /* 64-bit words of the bins destined to ONE shard: bins_per_shard*bin_cap*KW */
-    uint64_t spill_cap;           /* records per destination spill list */
-} tsxc_route_layout_t;
-/* Buffer geometry for chunks of at most max_chunk_words packed words (0 = library default).
- * kmers_per_position_q16: expected k-mers per base position in 1/65536 units, e.g. (len-k+1)/len for reads of one
- * length (0 = 65536: every position starts a k-mer).  It only sizes the bins: an underestimate sends the excess
- * through the spill lists and, if those fill up, makes tsxc_route_overflowed report the chunk for splitting. */
-int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, uint32_t kmers_per_position_q16, tsxc_route_layout_t* out);
-/* Build the read-boundary bitmap of a read batch (kept inside the handle until the next prepare). */
-int tsxc_route_prepare(tsxc_table* t, const uint64_t* d_offsets, uint64_t n_reads, uint64_t n_bases);
-/* Route packed words [w_begin, w_end) of the prepared batch.  d_bins: n_shards*block_words words,
- * d_cursors: n_shards*bins_per_shard fill counters, d_spill: n_shards*spill_cap records,
- * d_spill_n: n_shards counters.  Cursors and spill counters are zeroed first.  Nothing is inserted. */
-int tsxc_route_chunk(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64_t* d_packed, uint64_t n_bases,
-                     uint64_t w_begin, uint64_t w_end, uint64_t* d_bins, unsigned long long* d_cursors,
-                     uint64_t* d_spill, unsigned long long* d_spill_n);
-/* Waits for the routing kernels; *overflowed = 1 if a spill list ran out of room (the flag is cleared):
- * the caller repeats the chunk in smaller pieces. */
-int tsxc_route_overflowed(tsxc_table* t, int* overflowed);
-/* Insert the bins received from n_sources senders: d_bins holds n_sources blocks of block_words words,
- * d_cursors n_sources*bins_per_shard fill counters (the sender's block for THIS shard). */
-int tsxc_insert_routed(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64_t* d_bins,
-                       const unsigned long long* d_cursors, uint32_t n_sources);
-/* Insert n (hash, count) records of KW+1 words (received spill lists). */
-int tsxc_add_hash_counts_device(tsxc_table* t, const uint64_t* d_records, uint64_t n);
+typedef struct tsxc_route_info_t {
+    uint32_t n_shards, shard_rank;
+    uint32_t bins;               /* routing bins = entries of d_hist (n_shards * bins_per_shard) */
+    uint32_t bins_per_shard;
+    uint32_t key_words;
+    uint32_t reserved;
+    uint64_t recv_cap_keys;      /* capacity of this rank's receive buffer in k-mers (0 before tsxc_route_recv_buffer) */
+} tsxc_route_info_t;
+int tsxc_route_info(tsxc_table* t, tsxc_route_info_t* out);
+/* Allocate this rank's receive buffer (cap_keys k-mers; 0 = what free HBM allows) and return its device pointer so
+ * that the caller can export it to the other ranks (tsxc_ipc_export_mem, or directly within one process). */
+int tsxc_route_recv_buffer(tsxc_table* t, uint64_t cap_keys, void** d_ptr_out, uint64_t* cap_keys_out);
+/* peer_buffers[o] = shard o's receive buffer as addressable from this device (peer_buffers[shard_rank] = own);
+ * recv_cap_keys = the smallest capacity among them (every rank must pass the same value). */
+int tsxc_route_set_peers(tsxc_table* t, void* const* peer_buffers, uint64_t recv_cap_keys);
+/* Start a batch: read-end bitmap, histogram, chunk plan.  *rounds_out = upper bound of the rounds this rank needs
+ * (the caller takes the maximum over the ranks; surplus rounds send nothing). */
+int tsxc_route_begin(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint64_t n_reads, uint64_t n_bases,
+                     uint32_t* rounds_out);
+int tsxc_route_hist(tsxc_table* t, uint32_t round, uint32_t* d_hist_out);
+int tsxc_route_send(tsxc_table* t, uint32_t round, const uint32_t* d_hist_all);
+int tsxc_route_insert(tsxc_table* t);
 /* Insert n already-hashed k-mers (KW words each) owned by this shard. */
 int tsxc_add_hashes_device(tsxc_table* t, const uint64_t* d_hashes, uint64_t n);
 
 /* ---- peer-memory plumbing for the multi-GPU exchange (one process per GPU) ------------------------ */
-/* Bin blocks travel to their owner with copy-engine peer copies over NVLink instead of a staged NCCL all-to-all:
- * the owner exports its receive buffer (CUDA IPC), senders open it and cudaMemcpyAsync straight into it; two
- * inter-process events per buffer set order "copies landed" -> insert and "buffer drained" -> next copies.
- * All handles are 64 opaque bytes (cudaIpcMemHandle_t / cudaIpcEventHandle_t). */
+/* The owner exports its receive buffer (CUDA IPC), the other ranks open it and pass the mapped pointers to
+ * tsxc_route_set_peers.  All handles are 64 opaque bytes (cudaIpcMemHandle_t / cudaIpcEventHandle_t). */
 #define TSXC_IPC_HANDLE_BYTES 64
 int tsxc_ipc_export_mem(int device, void* dptr, unsigned char* handle_out);
 int tsxc_ipc_open_mem(int device, const unsigned char* handle, void** dptr_out);

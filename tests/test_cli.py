@@ -230,3 +230,19 @@ def test_feeder_multiline_fasta_split_keeps_the_kmer_multiset(tmp_path):
     assert a.n_total == b.n_total and a.n_distinct == b.n_distinct
     assert (a.keys == b.keys).all() and (a.counts == b.counts).all()
     assert max(len(x) for x in want_pieces) == 1000
+
+
+def test_feeder_rejects_truncated_gzip(tmp_path):
+    """A damaged .gz must not look like a (shorter) input: the reader throws, the tool exits non-zero."""
+    import gzip
+    seqs = orc.gen_reads(seed=9, n_reads=4000, read_len=150, mode=0)
+    raw = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, s, b"&" * len(s)) for i, s in enumerate(seqs))
+    good = tmp_path / "ok.fastq.gz"
+    with gzip.open(good, "wb") as f:
+        f.write(raw)
+    assert _run_ingest(good)[:2] == (4000, 4000 * 150)
+    data = good.read_bytes()
+    bad = tmp_path / "cut.fastq.gz"
+    bad.write_bytes(data[: len(data) // 2])
+    p = subprocess.run([INGEST, str(bad)], capture_output=True, text=True)
+    assert p.returncode != 0

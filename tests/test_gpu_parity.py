@@ -258,124 +258,118 @@ def test_device_generator_matches_oracle(tsx, mode, genome, sub):
     assert np.array_equal(packed, want_packed[:n_words])
 
 
-# ---- hash-sharded table on one GPU (the multi-GPU data path without the exchange) -------------------
-@pytest.mark.parametrize("k,n_shards,mode", [(31, 2, 1), (31, 8, 0), (63, 4, 2), (127, 2, 1)])
-def test_sharded_route_and_insert(tsx, k, n_shards, mode, monkeypatch):
-    """All shards live on one GPU; block o of the sender's bins is handed to shard o directly."""
-    monkeypatch.setenv("TSXC_REGION_LOG2", "16")     # several table regions per shard even for small tables
+# ---- hash-sharded table on one GPU: the multi-GPU data path with every "rank" in this process ---------------
+def _route_all(tsx, shards, d_packed, d_off, n_reads, n_bases, recv_cap_keys=0):
+    """The round protocol of tsxcount_b200/multigpu.py with the collectives done by hand: all ranks own the same
+    reads here, so every rank sends every k-mer and each k-mer arrives len(shards) times."""
+    import torch
     lib = tsx._lib.load()
-    seqs = orc.gen_reads(seed=31, n_reads=3000, read_len=150, mode=mode, genome_len=1 << 8 if mode == 2 else 0)
+    G = len(shards)
+    bufs = [hm.routeRecvBuffer(recv_cap_keys) for hm in shards]
+    cap = min(c for _, c in bufs)
+    for hm in shards:
+        hm.routeSetPeers([p for p, _ in bufs], cap)       # same device: the "peer" pointers are plain pointers
+    bins = shards[0].routeInfo().bins
+    rounds = max(hm.routeBegin(d_packed, d_off, n_reads, n_bases) for hm in shards)
+    hist = torch.zeros(G * bins, dtype=torch.int32, device="cuda")
+    for r in range(rounds):
+        for i, hm in enumerate(shards):
+            hm.routeHist(r, hist.data_ptr() + 4 * i * bins)
+            hm.sync()
+        for hm in shards:
+            hm.routeSend(r, hist.data_ptr())
+        for hm in shards:
+            hm.sync()                                      # the barrier: every rank's stores have landed
+        for hm in shards:
+            hm.routeInsert()
+            hm.sync()
+    return rounds, cap
+
+
+@pytest.mark.parametrize("k,n_shards,mode,region", [(31, 2, 1, "12"), (31, 8, 0, "12"), (63, 4, 2, "14"), (127, 2, 1, "12"),
+                                                    (31, 4, 3, "30")])
+def test_sharded_route_and_insert(tsx, k, n_shards, mode, region, monkeypatch):
+    monkeypatch.setenv("TSXC_REGION_LOG2", region)    # "30": no fine regions at all, routing by owner only
+    monkeypatch.setenv("TSXC_SEG_LOG2", "9")          # many planner segments, several rounds
+    lib = tsx._lib.load()
+    seqs = orc.gen_reads(seed=31, n_reads=3000, read_len=150, mode=mode,
+                         genome_len=(1 << 8) if mode == 2 else (50_000 if mode == 3 else 0), sub_rate_q16=328 if mode == 3 else 0)
     oc = orc.count_seqs(seqs, k)
     ascii_, offsets = tsx.sequtils.concat_reads(seqs)
     packed, seg, _ = tsx.sequtils.pack_reads(ascii_, offsets)
     n_bases = int(seg[-1])
-    n_words = (n_bases + 31) // 32
     shards = [tsx.TSXHashMapCUDA(20, 4, k, shard_rank=r, n_shards=n_shards) for r in range(n_shards)]
     kw = shards[0].kw
-    lay = shards[0].routeLayout(1 << 12)             # small chunks: several route calls
-    assert lay.n_shards == n_shards and lay.bins_per_shard >= 2
-    bufs = {}
+    bufs = []
 
-    def dalloc(name, nbytes):
+    def dalloc(nbytes):
         p = C.c_void_p()
         tsx._lib.check(lib.tsxc_device_alloc(0, nbytes, C.byref(p)))
-        bufs[name] = p
+        bufs.append(p)
         return p
 
     try:
-        d_packed = dalloc("packed", packed.nbytes)
-        d_off = dalloc("off", seg.nbytes)
-        d_bins = dalloc("bins", n_shards * lay.block_words * 8)
-        d_cur = dalloc("cur", n_shards * lay.bins_per_shard * 8)
-        d_spill = dalloc("spill", n_shards * lay.spill_cap * (kw + 1) * 8)
-        d_spn = dalloc("spn", n_shards * 8)
+        d_packed, d_off = dalloc(packed.nbytes + 64), dalloc(seg.nbytes)
         tsx._lib.check(lib.tsxc_memcpy(0, d_packed, packed.ctypes.data, packed.nbytes, 1))
         tsx._lib.check(lib.tsxc_memcpy(0, d_off, seg.ctypes.data, seg.nbytes, 1))
-        sender = shards[0]
-        sender.routePrepare(d_off, len(seg) - 1, n_bases)
-        n_spilled = 0
-        for w0 in range(0, n_words, lay.chunk_words):
-            w1 = min(n_words, w0 + lay.chunk_words)
-            sender.routeChunk(lay, d_packed, n_bases, w0, w1, d_bins, d_cur, d_spill, d_spn)
-            assert not sender.routeOverflowed()
-            spn = np.zeros(n_shards, dtype=np.uint64)
-            tsx._lib.check(lib.tsxc_memcpy(0, spn.ctypes.data, d_spn, spn.nbytes, 2))
-            for r, hm in enumerate(shards):
-                hm.insertRouted(lay, C.c_void_p(d_bins.value + r * lay.block_words * 8),
-                                C.c_void_p(d_cur.value + r * lay.bins_per_shard * 8), 1)
-                hm.addHashCountsDevice(C.c_void_p(d_spill.value + r * lay.spill_cap * (kw + 1) * 8), int(spn[r]))
-                hm.sync()
-            n_spilled += int(spn.sum())
-        if mode == 1 and k <= 31:
-            assert n_spilled > 0                     # poly-A runs are pre-aggregated and travel as (hash, count)
+        # receive buffers far smaller than the batch: several rounds
+        rounds, cap = _route_all(tsx, shards, d_packed, d_off, len(seg) - 1, n_bases, recv_cap_keys=oc.n_total // 3)
+        assert rounds >= 2
         got = {}
         for hm in shards:
+            assert hm.stats()["error_flags"] == 0
             keys, counts = hm.getAllKmers()
             for key, c in zip(keys.tolist(), counts.tolist()):
                 assert tuple(key) not in got, "k-mer present in two shards"
                 got[tuple(key)] = int(c)
-        assert got == oc.as_dict(kw)
+        want = {key: n_shards * c for key, c in oc.as_dict(kw).items()}     # every "rank" sent the same reads
+        assert got == want
         assert sum(hm.getKmerCount() for hm in shards) == oc.n_distinct
-        assert sum(hm.stats()["kmers_added"] for hm in shards) == oc.n_total
+        assert sum(hm.stats()["kmers_added"] for hm in shards) == n_shards * oc.n_total
         # a shard answers 0 for k-mers it does not own; the per-shard answers sum to the oracle's
         total = sum(hm.getKmerCounts(oc.keys_kw(kw)) for hm in shards)
-        assert np.array_equal(total, oc.counts)
+        assert np.array_equal(total, n_shards * oc.counts)
     finally:
-        for p in bufs.values():
-            lib.tsxc_device_free(0, p)
         for hm in shards:
             hm.close()
+        for p in bufs:
+            lib.tsxc_device_free(0, p)
 
 
-def test_route_spill_overflow_is_reported_not_dropped(tsx):
-    """A chunk whose pre-aggregated groups exceed the spill list raises the flag; halving the chunk succeeds."""
+def test_route_receive_overflow_is_reported_not_dropped(tsx, monkeypatch):
+    """Every k-mer of every rank belongs to ONE owner (a single repeated read): a round brings that owner more than
+    its receive buffer holds.  All ranks see it in the gathered histograms, skip the round together, nothing is
+    inserted or written out of bounds, and the sticky status says so."""
+    monkeypatch.setenv("TSXC_SEG_LOG2", "9")
     lib = tsx._lib.load()
-    seqs = [b"A" * 40 + b"C" * 40 + b"G" * 40 + b"T" * 40] * 4000     # every word ends several homopolymer runs
-    oc = orc.count_seqs(seqs, 21)
+    seqs = [b"ACGTTGCAAGGCTTAACCGGATATCGCGATTA" * 4] * 3000
+    oc = orc.count_seqs(seqs, 63)
+    assert oc.n_distinct <= 32
     ascii_, offsets = tsx.sequtils.concat_reads(seqs)
     packed, seg, _ = tsx.sequtils.pack_reads(ascii_, offsets)
-    n_bases = int(seg[-1]); n_words = (n_bases + 31) // 32
-    with tsx.TSXHashMapCUDA(16, 4, 21, shard_rank=0, n_shards=1) as hm:
-        lay = hm.routeLayout(n_words + 32)
-        lay.spill_cap = 64                            # force the overflow
-        ptrs = []
-
-        def dalloc(nbytes):
-            p = C.c_void_p(); tsx._lib.check(lib.tsxc_device_alloc(0, nbytes, C.byref(p))); ptrs.append(p); return p
-        try:
-            d_packed, d_off = dalloc(packed.nbytes), dalloc(seg.nbytes)
-            d_bins, d_cur = dalloc(lay.block_words * 8), dalloc(lay.bins_per_shard * 8)
-            d_spill, d_spn = dalloc(lay.spill_cap * 2 * 8), dalloc(8)
-            tsx._lib.check(lib.tsxc_memcpy(0, d_packed, packed.ctypes.data, packed.nbytes, 1))
-            tsx._lib.check(lib.tsxc_memcpy(0, d_off, seg.ctypes.data, seg.nbytes, 1))
-            hm.routePrepare(d_off, len(seg) - 1, n_bases)
-            hm.routeChunk(lay, d_packed, n_bases, 0, n_words, d_bins, d_cur, d_spill, d_spn)
-            assert hm.routeOverflowed() and not hm.routeOverflowed()     # reported once, then cleared
-            assert hm.getKmerCount() == 0                                 # routing never inserts
-            todo = [(0, n_words)]
-            while todo:
-                w0, w1 = todo.pop()
-                hm.routeChunk(lay, d_packed, n_bases, w0, w1, d_bins, d_cur, d_spill, d_spn)
-                if hm.routeOverflowed():
-                    mid = (w0 + w1) // 2
-                    todo += [(w0, mid), (mid, w1)]
-                    continue
-                spn = np.zeros(1, dtype=np.uint64)
-                tsx._lib.check(lib.tsxc_memcpy(0, spn.ctypes.data, d_spn, 8, 2))
-                hm.insertRouted(lay, d_bins, d_cur, 1)
-                hm.addHashCountsDevice(d_spill, int(spn[0]))
-                hm.sync()
-            check_against_oracle(tsx, hm, oc)
-        finally:
-            for p in ptrs:
-                lib.tsxc_device_free(0, p)
+    shards = [tsx.TSXHashMapCUDA(16, 4, 63, shard_rank=r, n_shards=4) for r in range(4)]
+    d_packed, d_off = C.c_void_p(), C.c_void_p()
+    tsx._lib.check(lib.tsxc_device_alloc(0, packed.nbytes + 64, C.byref(d_packed)))
+    tsx._lib.check(lib.tsxc_device_alloc(0, seg.nbytes, C.byref(d_off)))
+    try:
+        tsx._lib.check(lib.tsxc_memcpy(0, d_packed, packed.ctypes.data, packed.nbytes, 1))
+        tsx._lib.check(lib.tsxc_memcpy(0, d_off, seg.ctypes.data, seg.nbytes, 1))
+        with pytest.raises(tsx.TsxcError) as e:
+            _route_all(tsx, shards, d_packed, d_off, len(seg) - 1, int(seg[-1]), recv_cap_keys=oc.n_total // 4)
+        assert e.value.status == tsx.TSXC_E_INVALID and "receive buffer" in str(e.value)
+    finally:
+        for hm in shards:
+            hm.close()
+        lib.tsxc_device_free(0, d_packed)
+        lib.tsxc_device_free(0, d_off)
 
 
-# ---- the region-partitioned (two-phase) insert path -----------------------------------------------------
-@pytest.fixture
-def small_regions(monkeypatch):
-    """Tables larger than one region take the two-phase path; shrink the region so small tables do too."""
-    monkeypatch.setenv("TSXC_REGION_LOG2", "16")
+# ---- the region-sorted insert pipeline (tsx_radix.cuh) on small tables ----------------------------------------
+@pytest.fixture(params=["12", "16"], ids=["two_digits", "one_digit"])
+def small_regions(monkeypatch, request):
+    """Tables of 512 MiB and more take the pipeline; shrink the fine regions so that small tables do too
+    (4 KiB regions: both radix digits; 64 KiB regions: digit 1 only)."""
+    monkeypatch.setenv("TSXC_REGION_LOG2", request.param)
 
 
 PART_CASES = [c for c in CASES if c[0] in (
@@ -384,36 +378,29 @@ PART_CASES = [c for c in CASES if c[0] in (
 
 
 @pytest.mark.parametrize("case", PART_CASES, ids=[c[0] for c in PART_CASES])
-def test_partitioned_path_parity(tsx, small_regions, case):
+def test_pipeline_parity(tsx, small_regions, case):
     name, gen, n_reads, read_len, k, l, s, flags = case
     seqs = orc.gen_reads(n_reads=n_reads, read_len=read_len, **gen)
     st, oc = run_case(tsx, seqs, k, l, s, flags)
-    assert st["main_kernel_launches"] >= 2, "expected the partition + insert kernels"
+    assert st["main_kernel_launches"] >= 4, "expected the pipeline (histogram, partition, insert)"
 
 
-# The static phase A variant (TSXC_PART_STATIC=1) is compiled in but was written after the
-# round's GPU budget was spent: its parity tests only run on request, so they cannot mask or break the gate.
-experimental = pytest.mark.skipif(os.environ.get("TSXC_TEST_EXPERIMENTAL") != "1",
-                                  reason="experimental phase A variant: set TSXC_TEST_EXPERIMENTAL=1 to run")
-
-
-@experimental
-@pytest.mark.parametrize("case", PART_CASES, ids=[c[0] for c in PART_CASES])
-def test_partitioned_path_static_variant_parity(tsx, small_regions, monkeypatch, case):
-    monkeypatch.setenv("TSXC_PART_STATIC", "1")
+@pytest.mark.parametrize("case", [PART_CASES[0], PART_CASES[4], PART_CASES[7]], ids=lambda c: c[0])
+def test_pipeline_many_chunks_and_groups(tsx, monkeypatch, case):
+    """Key buffers far smaller than the batch: the planner cuts it into several chunks (insert passes), every chunk
+    into several groups of buffer B; segments of one block round make chunk boundaries fall inside reads."""
+    monkeypatch.setenv("TSXC_REGION_LOG2", "12")
+    monkeypatch.setenv("TSXC_SEG_LOG2", "9")
+    monkeypatch.setenv("TSXC_CHUNK_KEYS", "70000")
+    monkeypatch.setenv("TSXC_GROUP_KEYS", "9000")
     name, gen, n_reads, read_len, k, l, s, flags = case
     seqs = orc.gen_reads(n_reads=n_reads, read_len=read_len, **gen)
     st, oc = run_case(tsx, seqs, k, l, s, flags)
-    assert st["main_kernel_launches"] >= 2
+    assert st["chunk_cap_keys"] == 70000 and st["group_cap_keys"] == 9000
+    assert st["main_kernel_launches"] >= 3 * (2 + 5 * 7)
 
 
-@experimental
-def test_partitioned_path_static_variant_ragged_reads_and_repeats(tsx, small_regions, monkeypatch):
-    monkeypatch.setenv("TSXC_PART_STATIC", "1")
-    test_partitioned_path_ragged_reads_and_repeats(tsx, None)
-
-
-def test_partitioned_path_ragged_reads_and_repeats(tsx, small_regions):
+def test_pipeline_ragged_reads_and_repeats(tsx, small_regions):
     rng = np.random.default_rng(5)
     seqs = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(n))) for n in rng.integers(1, 400, size=1500)]
     seqs += [b"A" * 3000, b"", b"ACGT" * 300]
@@ -421,15 +408,32 @@ def test_partitioned_path_ragged_reads_and_repeats(tsx, small_regions):
     with tsx.TSXHashMapCUDA(20, 4, 31, flags=tsx.TSXC_FLAG_EXACT_S) as hm:
         hm.addSequences(seqs)
         hm.addSequences(seqs)                        # second batch hits existing entries
-        assert hm.stats()["main_kernel_launches"] >= 4
+        assert hm.stats()["main_kernel_launches"] >= 8
         assert hm.getKmerCount() == oc.n_distinct
         assert np.array_equal(hm.getKmerCounts(oc.keys_kw(1)), 2 * oc.counts)
 
 
-def test_skewed_flag_same_counts(tsx, small_regions):
-    seqs = orc.gen_reads(seed=0xC3, n_reads=4000, read_len=150, mode=2, genome_len=1 << 8, sub_rate_q16=655)
-    st, oc = run_case(tsx, seqs, 63, 19, 0, flags=tsx.TSXC_FLAG_SKEWED)
+@pytest.mark.parametrize("k,l", [(31, 20), (63, 19), (127, 18)])
+def test_pipeline_heavy_hitters_need_no_hint(tsx, small_regions, k, l):
+    """Zipf-like dictionary reads: a few k-mers make up most of the input.  Bins are sized from exact histograms and
+    duplicates are combined in shared memory before they reach the table: no creation flag, same counts."""
+    seqs = orc.gen_reads(seed=0xC3, n_reads=4000, read_len=150, mode=2, genome_len=1 << 6, sub_rate_q16=655)
+    st, oc = run_case(tsx, seqs, k, l, 0)
     assert st["main_kernel_launches"] >= 4
+    assert oc.counts.max() > 100
+
+
+def test_pipeline_one_kmer_is_the_whole_input(tsx, small_regions):
+    """24 distinct 12-mers, 7.8e5 k-mers: every tile, every bin and every insert slice holds the same few keys."""
+    seqs = [(b"A" * 13 + b"C" * 13) * 200] * 150
+    oc = orc.count_seqs(seqs, 12)
+    assert oc.n_distinct == 24
+    with tsx.TSXHashMapCUDA(20, 4, 12, flags=tsx.TSXC_FLAG_EXACT_S) as hm:
+        hm.addSequences(seqs)
+        assert hm.stats()["main_kernel_launches"] >= 4
+        check_against_oracle(tsx, hm, oc)
+        hm.addSequences(seqs[:50])                         # and the table stays usable afterwards
+        assert hm.getKmerCount() == 24
 
 
 def test_direct_flag_forces_single_kernel(tsx, small_regions):
@@ -459,24 +463,9 @@ def test_reference_pinned_fixtures(tsx, tmp_path):
             assert got == want, name
 
 
-def test_two_phase_spill_overflow_falls_back_to_the_fused_kernel(tsx, small_regions):
-    """24 distinct 12-mers over 128 bins: every bin that receives a k-mer overflows, the spill list overflows too;
-    the chunk must then be redone by the fused kernel on the device - same counts, no error."""
-    seqs = [(b"A" * 13 + b"C" * 13) * 200] * 300
-    oc = orc.count_seqs(seqs, 12)
-    assert oc.n_distinct == 24
-    with tsx.TSXHashMapCUDA(20, 4, 12, flags=tsx.TSXC_FLAG_EXACT_S) as hm:
-        hm.addSequences(seqs)
-        assert hm.stats()["main_kernel_launches"] >= 4     # partition, insert, spill drain, fused fallback
-        check_against_oracle(tsx, hm, oc)
-        hm.addSequences(seqs[:50])                         # and the table stays usable afterwards
-        assert hm.getKmerCount() == 24
-
-
 # ---- the default two-phase configuration at a size the oracle cannot count: size-independent properties ----
 def test_large_default_path_properties(tsx):
-    """2.4e8 uniform 31-mers into a 4 GiB table (16 regions of 256 MiB, the default geometry, several chunks of
-    host batches).  Properties: every k-mer is added exactly once (sum of counts), all are distinct (a duplicate
+    """2.4e8 uniform 31-mers into a 4 GiB table (512 regions of 8 MiB: the default geometry).  Properties: every k-mer is added exactly once (sum of counts), all are distinct (a duplicate
     has probability ~1e-2 at this size), sampled k-mers regenerated by the oracle are present with count 1 and
     absent ones with 0; a second pass doubles every sampled count and leaves the distinct count unchanged."""
     lib = tsx._lib.load()
@@ -500,7 +489,8 @@ def test_large_default_path_properties(tsx):
                 st = hm.stats()
                 assert st["error_flags"] == 0 and st["kmers_added"] == rep * n_kmers
                 assert st["distinct"] == n_kmers
-                assert st["main_kernel_launches"] >= 4 * rep          # the two-phase path ran
+                assert st["main_kernel_launches"] >= 4 * rep          # the pipeline ran
+                assert st["radix_digit1_bits"] == 8 and st["radix_digit2_bits"] == 1
                 assert np.array_equal(hm.getKmerCounts(oc.keys_kw(1)), rep * oc.counts)
                 assert hm.getKmerCounts(other.keys_kw(1)).sum() == 0
     finally:

@@ -23,7 +23,7 @@ def test_library_exports_every_symbol_the_header_declares():
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, missing
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
-    assert lib.tsxc_abi_version() == 1
+    assert lib.tsxc_abi_version() == 2
 
 
 def test_no_cpu_fallback():

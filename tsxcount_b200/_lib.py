@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtsxcuda.so")
+LIB_PATH = os.environ.get("TSXC_LIB") or os.path.join(_HERE, "lib", "libtsxcuda.so")   # TSXC_LIB: A/B kernel builds
 
 TSXC_OK = 0
 TSXC_E_INVALID = 1
@@ -23,7 +23,8 @@ TSXC_FLAG_NONE = 0
 TSXC_FLAG_EXACT_S = 1
 TSXC_FLAG_NO_WARP_AGG = 2
 TSXC_FLAG_DIRECT = 4
-TSXC_FLAG_SKEWED = 8
+
+TSXC_IPC_HANDLE_BYTES = 64
 
 
 class TsxcStats(C.Structure):
@@ -37,6 +38,9 @@ class TsxcStats(C.Structure):
         ("max_reprobe", C.c_uint64), ("error_flags", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("main_kernel_launches", C.c_uint64), ("main_kernel_ms", C.c_double),
         ("partition_ms", C.c_double), ("insert_ms", C.c_double),
+        ("hist_ms", C.c_double), ("part1_ms", C.c_double), ("part2_ms", C.c_double),
+        ("chunk_cap_keys", C.c_uint64), ("group_cap_keys", C.c_uint64),
+        ("radix_digit1_bits", C.c_uint32), ("radix_digit2_bits", C.c_uint32),
     ]
 
     def as_dict(self):
@@ -50,11 +54,10 @@ class TsxcGenParams(C.Structure):
     ]
 
 
-class TsxcRouteLayout(C.Structure):
+class TsxcRouteInfo(C.Structure):
     _fields_ = [
-        ("n_shards", C.c_uint32), ("bins_per_shard", C.c_uint32), ("key_words", C.c_uint32),
-        ("spill_record_words", C.c_uint32), ("chunk_words", C.c_uint64), ("bin_cap", C.c_uint64),
-        ("block_words", C.c_uint64), ("spill_cap", C.c_uint64),
+        ("n_shards", C.c_uint32), ("shard_rank", C.c_uint32), ("bins", C.c_uint32), ("bins_per_shard", C.c_uint32),
+        ("key_words", C.c_uint32), ("reserved", C.c_uint32), ("recv_cap_keys", C.c_uint64),
     ]
 
 
@@ -73,6 +76,7 @@ PROTOTYPES = {
                                     C.POINTER(_vp)]),
     "tsxc_destroy": (C.c_int, [_vp]),
     "tsxc_clear": (C.c_int, [_vp]),
+    "tsxc_trim": (C.c_int, [_vp]),
     "tsxc_stream": (_vp, [_vp]),
     "tsxc_mark": (C.c_int, [_vp, C.c_int]),
     "tsxc_mark_elapsed_ms": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
@@ -87,12 +91,13 @@ PROTOTYPES = {
     "tsxc_dump": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _u64p]),
     "tsxc_dump_file": (C.c_int, [_vp, C.c_char_p]),
     "tsxc_stats": (C.c_int, [_vp, C.POINTER(TsxcStats)]),
-    "tsxc_route_layout": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.POINTER(TsxcRouteLayout)]),
-    "tsxc_route_prepare": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64]),
-    "tsxc_route_chunk": (C.c_int, [_vp, C.POINTER(TsxcRouteLayout), _vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
-    "tsxc_route_overflowed": (C.c_int, [_vp, C.POINTER(C.c_int)]),
-    "tsxc_insert_routed": (C.c_int, [_vp, C.POINTER(TsxcRouteLayout), _vp, _vp, C.c_uint32]),
-    "tsxc_add_hash_counts_device": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "tsxc_route_info": (C.c_int, [_vp, C.POINTER(TsxcRouteInfo)]),
+    "tsxc_route_recv_buffer": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp), _u64p]),
+    "tsxc_route_set_peers": (C.c_int, [_vp, C.POINTER(_vp), C.c_uint64]),
+    "tsxc_route_begin": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]),
+    "tsxc_route_hist": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "tsxc_route_send": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "tsxc_route_insert": (C.c_int, [_vp]),
     "tsxc_add_hashes_device": (C.c_int, [_vp, _vp, C.c_uint64]),
     "tsxc_pack_reads": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _u64p, _u64p]),
     "tsxc_gen_reads_device": (C.c_int, [C.POINTER(TsxcGenParams), C.c_uint64, C.c_uint64, C.c_int, _vp, _vp, _vp]),

@@ -15,6 +15,7 @@
 #include "../../include/tsxcount_cuda.h"
 #include "tsx_gen.cuh"
 #include "tsx_kernels.cuh"
+#include "tsx_radix.cuh"
 
 using namespace tsx;
 
@@ -29,6 +30,8 @@ struct Staging {
     cudaEvent_t copied = nullptr, done = nullptr;
     bool used = false;
 };
+
+enum { PH_HIST = 0, PH_PART1 = 1, PH_PART2 = 2, PH_INSERT = 3, PH_COUNT = 4 };
 
 }  // namespace
 
@@ -49,20 +52,33 @@ struct tsxc_table {
     uint64_t* d_keys = nullptr; size_t cap_keys = 0;      // words
     uint64_t* d_counts = nullptr; size_t cap_counts = 0;  // entries
     unsigned long long* d_nout = nullptr;
-    // region-partitioned insert (phase A bins)
-    uint64_t* d_part = nullptr; size_t cap_part = 0;          // words
-    uint64_t* d_spill = nullptr; size_t cap_spill = 0;        // words: (hash, count) records of the single-GPU two-phase path
-    unsigned long long* d_cursor = nullptr;                   // kMaxParts + 1 (last = ticket)
-    unsigned long long* d_subfill = nullptr; size_t cap_subfill = 0;   // static phase A: fill per (block, bin)
-    uint32_t pbits = 0;                                        // log2(#regions); 0 = direct path only
-    uint32_t region_log2 = 27;
-    bool part_static = false;                                  // EXPERIMENTAL phase A variant (TSXC_PART_STATIC=1 at creation)
+    // region-sorted insert pipeline (tsx_radix.cuh): S0 histogram, S1/S2 radix partition, phase B insert
+    RadixGeom rg{};
+    bool radix_on = false;                                     // tables this large take the pipeline by default
+    uint32_t region_log2 = 23;                                 // target size of a fine table region (bytes, log2)
+    RadixCtl* d_ctl = nullptr;
+    uint32_t* d_seghist = nullptr; size_t cap_seghist = 0;     // S0: counts per (segment, digit 1)
+    uint32_t* d_segtotal = nullptr; size_t cap_segtotal = 0;
+    uint64_t* d_segprefix = nullptr; size_t cap_segprefix = 0;
+    uint64_t* d_A = nullptr; uint64_t cap_A = 0;               // keys, sorted by digit 1 (multi-GPU: the receive buffer)
+    uint64_t* d_B = nullptr; uint64_t cap_B = 0;               // keys, one group of A sorted by fine region
+    bool cap_A_limited = false;                                // cap_A was set by free memory, not by a batch size
+    uint32_t* d_fhist = nullptr;                               // kMaxFine
+    unsigned long long* d_fcur = nullptr;                      // kMaxFine
+    // multi-GPU routing (tsxc_route_*)
+    uint64_t** d_peers = nullptr;                              // n_shards receive buffers as seen from this device
+    bool peers_set = false;
+    const uint64_t* route_packed = nullptr;
+    uint64_t route_n_words = 0, route_n_bases = 0;
+    uint32_t route_rounds = 0;
+    unsigned long long* d_ticket_k0 = nullptr;                 // K0r microbenchmark
     // launch accounting (bench.py's gpu_launches / roofline come from here)
     uint64_t n_launches = 0, n_main_launches = 0;
     double main_ms = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_part, ev_ins;  // per-phase pairs of the two-phase path
-    double part_ms = 0.0, ins_ms = 0.0;
+    struct PhaseEv { int ph; std::pair<cudaEvent_t, cudaEvent_t> ev; };
+    std::vector<PhaseEv> ev_phase;                             // per-phase pairs of the pipeline
+    double phase_ms[PH_COUNT] = {0.0, 0.0, 0.0, 0.0};
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     std::mutex mu;
@@ -86,18 +102,29 @@ void main_end(tsxc_table* t, cudaStream_t s, const std::pair<cudaEvent_t, cudaEv
     t->ev_pending.push_back(ev);
     t->n_main_launches += launches;
 }
+// One pipeline phase: RAII-free pair, begin/end around the launches of the phase.
+struct PhaseTimer {
+    tsxc_table* t; cudaStream_t s; int ph; std::pair<cudaEvent_t, cudaEvent_t> ev; bool on;
+    PhaseTimer(tsxc_table* t_, cudaStream_t s_, int ph_) : t(t_), s(s_), ph(ph_) { on = main_begin(t, s, &ev); }
+    void end(int launches) {
+        if (on) { cudaEventRecord(ev.second, s); t->ev_phase.push_back({ph, ev}); }
+        t->n_launches += launches;
+        t->n_main_launches += launches;
+    }
+};
 void collect_main_ms(tsxc_table* t) {  // caller has synchronized the stream
-    auto drain = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, double& acc) {
-        for (auto& ev : v) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) acc += ms;
-            t->ev_free.push_back(ev);
-        }
-        v.clear();
-    };
-    drain(t->ev_pending, t->main_ms);
-    drain(t->ev_part, t->part_ms);
-    drain(t->ev_ins, t->ins_ms);
+    for (auto& ev : t->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) t->main_ms += ms;
+        t->ev_free.push_back(ev);
+    }
+    t->ev_pending.clear();
+    for (auto& pe : t->ev_phase) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pe.ev.first, pe.ev.second) == cudaSuccess) { t->phase_ms[pe.ph] += ms; t->main_ms += ms; }
+        t->ev_free.push_back(pe.ev);
+    }
+    t->ev_phase.clear();
 }
 
 #define CU(call)                                                                                         \
@@ -108,12 +135,35 @@ void collect_main_ms(tsxc_table* t) {  // caller has synchronized the stream
                         std::string(#call) + ": " + cudaGetErrorString(e_));                             \
     } while (0)
 
+// The pipeline's key buffers take whatever HBM the table leaves free; anything else that needs memory later
+// (staging slots, lookup buffers) may claim it back: the buffers are re-sized at the next batch.
+int release_radix_buffers(tsxc_table* t) {
+    if (!t->d_A && !t->d_B) return TSXC_OK;
+    if (t->peers_set) return TSXC_OK;          // exported to peers: must stay where it is
+    CU(cudaStreamSynchronize(t->stream));
+    if (t->d_A) { CU(cudaFree(t->d_A)); t->d_A = nullptr; }
+    if (t->d_B) { CU(cudaFree(t->d_B)); t->d_B = nullptr; }
+    t->cap_A = t->cap_B = 0; t->cap_A_limited = false;
+    return TSXC_OK;
+}
+
+// Grows *p to exactly `need` elements (small buffers grow geometrically so that a sequence of slightly larger
+// batches does not reallocate every time; nothing above 64 MiB is over-allocated).
 template <typename T>
 int ensure(tsxc_table* t, T** p, size_t* cap, size_t need) {
     if (need <= *cap) return TSXC_OK;
     if (*p) { CU(cudaStreamSynchronize(t->stream)); CU(cudaStreamSynchronize(t->copy_stream)); CU(cudaFree(*p)); *p = nullptr; *cap = 0; }
-    const size_t want = std::max(need, *cap + *cap / 2);
-    CU(cudaMalloc(p, want * sizeof(T)));
+    size_t want = need;
+    if (need * sizeof(T) <= (64u << 20)) want = std::max(need, *cap + *cap / 2);
+    cudaError_t e = cudaMalloc(p, want * sizeof(T));
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        int rc = release_radix_buffers(t);
+        if (rc) return rc;
+        want = need;
+        e = cudaMalloc(p, want * sizeof(T));
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; return fail(t, e == cudaErrorMemoryAllocation ? TSXC_E_NOMEM : TSXC_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
     *cap = want;
     return TSXC_OK;
 }
@@ -134,186 +184,179 @@ int grid_for(const tsxc_table* t, uint64_t work_items, int per_sm = 8) {
         else return fail(t, TSXC_E_UNSUPPORTED, "no kernel for this entry class"); \
     } while (0)
 
+#define TSX_DISPATCH_KW(L, M)                                   \
+    do {                                                        \
+        if ((L).KW == 1) { M(1); }                              \
+        else if ((L).KW == 2) { M(2); }                         \
+        else { M(4); }                                          \
+    } while (0)
+
 int status_from_flags(tsxc_table* t, uint64_t flags) {
     if (flags & ERR_TABLE_FULL) return fail(t, TSXC_E_TABLE_FULL, "reprobe limit reached: table full (reference: exit(42))");
     if (flags & ERR_SATURATED) return fail(t, TSXC_E_COUNT_SATURATED, "overflow counter saturated");
-    if (flags & ERR_SEND_OVERFLOW) return fail(t, TSXC_E_INVALID, "send buffer of a shard overflowed");
+    if (flags & ERR_SEND_OVERFLOW) return fail(t, TSXC_E_INVALID, "receive buffer of a shard too small for a routing round");
     if (flags & ERR_WRONG_SHARD) return fail(t, TSXC_E_INVALID, "k-mer hash routed to the wrong shard");
+    if (flags & ERR_PLAN) return fail(t, TSXC_E_INVALID, "chunk planner: a segment of the batch exceeds the key buffer");
     return TSXC_OK;
 }
 
-// Geometry of phase A for P bins and chunks of chunk_words packed words.
-//   tile   : words a block handles between two run-rotation barriers; longer tiles for many bins, where the
-//            barrier (8 warps waiting for the slowest) otherwise shows up as 20 % of the stall samples
-//   run    : entries per private run; two runs must cover one tile's arrivals of a bin: mean m = 32*tile/P
-//            (every position valid), Poisson tail m + 6*sqrt(m)
-//   grid   : 8 blocks per SM for few bins, 4 for many (measured: 3 are resident, a finer grid-stride still
-//            balances better: 183-186 ms vs 196 ms at 4 and 217 ms at 3 per SM on config 2; every extra block
-//            costs 1.5 runs of holes per bin)
-//   cap    : bin capacity = mean + 1 % + 8 sigma + the hole tails of every block (2 runs each) + slack
-struct PartGeom { uint32_t tile_words, run; int grid, threads; uint64_t cap; };
+// ---- region-sorted pipeline: geometry, buffers, launch sequence -------------------------------------------------
 
-PartGeom part_geometry(const tsxc_table* t, uint32_t P, uint64_t chunk_words, double kmers_per_position = 1.0) {
-    PartGeom g{};
-    // many bins: one fat block per SM keeps the write frontier (one partially filled sector per resident
-    // (block, bin)) inside L2; few bins: small blocks, finer grid-stride
-    g.threads = P > 1024 ? 1024 : (P > 512 ? 512 : kBlockThreads);
-    if (const char* e = std::getenv("TSXC_PART_THREADS")) { const int v = std::atoi(e); if (v == 256 || v == 512 || v == 1024) g.threads = v; }
-    uint32_t iters = (P >= 4096 && g.threads == kBlockThreads) ? 4 : 2;
-    if (const char* e = std::getenv("TSXC_PART_ITERS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) iters = (uint32_t)v; }
-    int blocks_per_sm = g.threads == 1024 ? 2 : (g.threads == 512 ? 4 : 8);
-    if (const char* e = std::getenv("TSXC_PART_GRID")) { const int v = std::atoi(e); if (v >= 1 && v <= 16) blocks_per_sm = v; }
-    g.tile_words = (g.threads / 32) * 32 * iters;
-    const double m = 32.0 * g.tile_words / P;
-    g.run = (uint32_t)std::ceil((m + 6.0 * std::sqrt(m)) / 2.0);
-    g.run = (g.run + 3) & ~3u;           // whole 32-byte sectors
-    if (g.run < 8) g.run = 8;
-    if (const char* e = std::getenv("TSXC_PART_RUN")) { const int v = std::atoi(e); if (v >= 4 && v <= 65536) g.run = (uint32_t)v; }
-    const uint64_t tiles = (chunk_words + g.tile_words - 1) / g.tile_words;
-    g.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)t->sms * blocks_per_sm));
-    const uint64_t mean = (uint64_t)(32.0 * chunk_words * kmers_per_position / P) + 1;
-    // hash-uniform bins: sigma = sqrt(mean), so 1 % + 8 sigma on top of the mean is ample
-    g.cap = mean + mean / 100 + 8 * (uint64_t)std::sqrt((double)mean) + 2ULL * (uint64_t)g.grid * g.run + 2048;
-    g.cap = (g.cap + 7) & ~7ULL;
+// Digits for a shard of 2^LBl buckets (32 bytes each) and fine regions of 2^region_log2 bytes.
+RadixGeom make_radix_geom(const Layout& L, uint32_t region_log2, uint32_t seg_log2) {
+    RadixGeom g{};
+    const uint32_t table_log2 = L.LBl + 5;
+    uint32_t fb = table_log2 > region_log2 ? table_log2 - region_log2 : 0;   // fine-bin bits inside the shard
+    fb = std::min<uint32_t>(fb, std::min<uint32_t>(L.LBl, 16));
+    g.d1 = std::min<uint32_t>(8, L.shard_bits + fb);
+    g.d2 = std::min<uint32_t>(8, fb - (g.d1 - L.shard_bits));
+    g.nb1 = 1u << g.d1; g.nb2 = 1u << g.d2; g.nbl = 1u << (g.d1 - L.shard_bits);
+    g.shift1 = L.LBg - g.d1; g.shift2 = L.LBg - g.d1 - g.d2;
+    g.owner_shift = g.d1 - L.shard_bits;
+    g.seg_log2 = seg_log2;
     return g;
 }
 
-uint32_t slice_entries_cfg(uint32_t flags) {
-    static const uint32_t v = [] {
-        const char* e = std::getenv("TSXC_SLICE");
-        const int x = e ? std::atoi(e) : 0;
-        return (x >= 256 && x <= (1 << 20)) ? (uint32_t)x : 0u;
-    }();
-    if (v) return v;
-    return (flags & TSXC_FLAG_SKEWED) ? 16 * kSliceEntriesDefault : kSliceEntriesDefault;
+uint64_t env_u64(const char* name, uint64_t dflt) {
+    const char* e = std::getenv(name);
+    if (!e || !*e) return dflt;
+    return std::strtoull(e, nullptr, 10);
 }
 
-void launch_partition(uint32_t KW, int threads, int grid, cudaStream_t s, const TableView& tv, const PartView& pv,
-                      const uint64_t* d_packed, const uint32_t* d_ends, uint64_t w0, uint64_t w1, uint64_t n_words,
-                      uint64_t n_bases) {
-    // KW = 4 needs > 64 registers per thread: 1024-thread blocks are not launchable for it
-    if (KW == 4 && threads > 512) threads = 512;
-#define L_(KW_, T_) k_partition_reads<KW_, T_><<<grid, T_, 0, s>>>(tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases)
-    if (KW == 1) { if (threads == 1024) L_(1, 1024); else if (threads == 512) L_(1, 512); else L_(1, 256); }
-    else if (KW == 2) { if (threads == 1024) L_(2, 1024); else if (threads == 512) L_(2, 512); else L_(2, 256); }
-    else { if (threads == 512) L_(4, 512); else L_(4, 256); }
-#undef L_
-}
-
-void launch_partition_static(uint32_t KW, int threads, int grid, cudaStream_t s, const TableView& tv, const PartView& pv,
-                             const uint64_t* d_packed, const uint32_t* d_ends, uint64_t w0, uint64_t w1, uint64_t n_words,
-                             uint64_t n_bases) {
-    if (KW == 4 && threads > 512) threads = 512;
-#define L_(KW_, T_) k_partition_reads_static<KW_, T_><<<grid, T_, 0, s>>>(tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases)
-    if (KW == 1) { if (threads == 1024) L_(1, 1024); else if (threads == 512) L_(1, 512); else L_(1, 256); }
-    else if (KW == 2) { if (threads == 1024) L_(2, 1024); else if (threads == 512) L_(2, 512); else L_(2, 256); }
-    else { if (threads == 512) L_(4, 512); else L_(4, 256); }
-#undef L_
-}
-
-// EXPERIMENTAL (TSXC_PART_STATIC=1): slab capacity of the static phase A for a chunk of chunk_words words: the
-// positions of the block with the most tiles, spread over P bins, + 6 sigma.
-uint64_t static_sub_cap(const PartGeom& g, uint32_t P, uint64_t chunk_words) {
-    const uint64_t tiles = (chunk_words + g.tile_words - 1) / g.tile_words;
-    const uint64_t tiles_per_block = (tiles + g.grid - 1) / g.grid;
-    const double mean = 32.0 * (double)tiles_per_block * g.tile_words / P;
-    const uint64_t cap = (uint64_t)(mean + 6.0 * std::sqrt(mean)) + 16;
-    return (cap + 3) & ~3ULL;
-}
-
-// Two-phase path for tables much larger than the per-SM translation reach (see tsx_kernels.cuh).
-int launch_count_reads_partitioned(tsxc_table* t, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words,
-                                   uint64_t n_bases, cudaStream_t s) {
-    const Layout& L = t->L;
-    const uint32_t P = 1u << t->pbits;
-    // Chunk = the reads binned before one insert pass.  Larger chunks touch every table region more densely per
-    // pass, which phase B turns into DRAM row locality and L2 hits (insert 334 / 290 / 261 ms on config 2 for
-    // chunks of 2^24 / 2^25 / 2^26 words), so take the largest chunk (up to 2^27 words) whose bins + spill list fit in free HBM.
-    static const int chunk_log2_env = [] { const char* e = std::getenv("TSXC_CHUNK_LOG2"); const int v = e ? std::atoi(e) : 0; return (v >= 16 && v <= 30) ? v : 0; }();
-    const bool part_static = t->part_static;
-    int chunk_log2 = chunk_log2_env ? chunk_log2_env : 27;
-    uint64_t chunk_words = 0, cap = 0, spill_cap = 0, sub_cap = 0;
-    PartGeom geo{};
-    for (;; --chunk_log2) {
-        {   // equal chunks no larger than 2^chunk_log2 / KW words
-            const uint64_t max_words = (1ULL << chunk_log2) / L.KW;
-            const uint64_t n_chunks = (n_words + max_words - 1) / max_words;
-            chunk_words = ((n_words + n_chunks - 1) / n_chunks + 31) & ~31ULL;
-        }
-        geo = part_geometry(t, P, chunk_words);
-        cap = geo.cap;
-        if (part_static) {   // bins = grid slabs of sub_cap entries each
-            sub_cap = static_sub_cap(geo, P, chunk_words);
-            cap = (uint64_t)geo.grid * sub_cap;
-        }
-        // spill list: one record per 16 positions is far more than homopolymer runs and bin tails ever need;
-        // inputs that exceed it (a handful of k-mers making up most of a chunk) are redone by the fused kernel
-        spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 16);
-        const size_t need_part = (size_t)P * cap * L.KW, need_spill = (size_t)spill_cap * (L.KW + 1);
-        if (chunk_log2_env || chunk_log2 <= 20) break;
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); break; }
-        const size_t extra = (need_part > t->cap_part ? (need_part - t->cap_part) * 8 : 0) +
-                             (need_spill > t->cap_spill ? (need_spill - t->cap_spill) * 8 : 0);
-        if (extra + (3ULL << 30) <= free_b) break;   // keep 3 GiB free for staging buffers and the caller
-    }
-    int rc = ensure(t, &t->d_part, &t->cap_part, (size_t)P * cap * L.KW);
+// Sizes buffers A and B for a batch with at most `positions` k-mers.  A holds one chunk; as much as the batch
+// needs, at most what HBM leaves free (a denser chunk is a faster insert pass: more touches per table region).
+int radix_reserve(tsxc_table* t, uint64_t positions) {
+    const RadixGeom& g = t->rg;
+    const uint64_t seg_keys = 32ULL << g.seg_log2;
+    uint64_t want = std::max<uint64_t>(((positions + seg_keys - 1) / seg_keys) * seg_keys, 2 * seg_keys);
+    const uint64_t env_cap = env_u64("TSXC_CHUNK_KEYS", 0);
+    if (env_cap) want = std::min(want, std::max(env_cap, 2 * seg_keys));
+    if (t->d_A && (t->cap_A >= want || t->cap_A_limited)) return TSXC_OK;
+    if (t->peers_set) return fail(t, TSXC_E_INVALID, "receive buffer is exported to peers and cannot grow");
+    int rc = release_radix_buffers(t);
     if (rc) return rc;
-    if ((rc = ensure(t, &t->d_spill, &t->cap_spill, (size_t)spill_cap * (L.KW + 1)))) return rc;
-    if (part_static && (rc = ensure(t, &t->d_subfill, &t->cap_subfill, (size_t)geo.grid * P))) return rc;
-    unsigned long long* ticket = t->d_cursor + kMaxParts;
-    unsigned long long* spill_n = t->d_cursor + kMaxParts + 1;
-    unsigned int* overflow = reinterpret_cast<unsigned int*>(t->d_cursor + kMaxParts + 2);
-    PartView pv{};
-    pv.buf = t->d_part; pv.cursor = t->d_cursor; pv.cap = cap;
-    pv.pshift = L.LBl - t->pbits; pv.pmask = P - 1; pv.P = P; pv.run = geo.run; pv.tile_words = geo.tile_words;
-    pv.spill = t->d_spill; pv.spill_n = spill_n; pv.spill_cap = spill_cap; pv.bins_per_shard_log2 = t->pbits;
-    pv.overflow = overflow;
-    const uint32_t slice_entries = slice_entries_cfg(t->L.flags);
-    uint32_t slices = (uint32_t)((cap + slice_entries - 1) / slice_entries);
-    uint32_t n_sources = 1;
-    const bool agg = !(L.flags & TSXC_FLAG_NO_WARP_AGG);
-    std::pair<cudaEvent_t, cudaEvent_t> ev;
-    const bool timed = main_begin(t, s, &ev);
-    int main_launches = 0;
-    const PartView pv_bins = pv;   // phase A view; phase B's differs in the static variant
-    for (uint64_t w0 = 0; w0 < n_words; w0 += chunk_words) {
-        const uint64_t w1 = std::min(n_words, w0 + chunk_words);
-        CU(cudaMemsetAsync(t->d_cursor, 0, (kMaxParts + 8) * sizeof(unsigned long long), s));
-        const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w1 - w0 + geo.tile_words - 1) / geo.tile_words, (uint64_t)geo.grid));
-        static const int insert_blocks_per_sm = [] { const char* e = std::getenv("TSXC_INSERT_GRID"); const int v = e ? std::atoi(e) : 0; return (v >= 1 && v <= 16) ? v : 8; }();
-        const int grid_b = t->sms * insert_blocks_per_sm;
-        std::pair<cudaEvent_t, cudaEvent_t> eva, evb;
-        // phase A: bins + spill records, nothing inserted
-        const bool ta = main_begin(t, s, &eva);
-        if (part_static) {
-            PartView pa = pv_bins;                       // [block][bin][sub_cap] slabs, fills at d_subfill[block * P + bin]
-            pa.cap = sub_cap; pa.cursor = t->d_subfill;
-            launch_partition_static(L.KW, geo.threads, grid_a, s, t->tv, pa, d_packed, d_ends, w0, w1, n_words, n_bases);
-            pv = pa;                                     // phase B: every block of phase A is a source
-            pv.P = (uint32_t)grid_a * P;
-            n_sources = (uint32_t)grid_a;
-            slices = (uint32_t)((sub_cap + slice_entries - 1) / slice_entries);
-        } else {
-            launch_partition(L.KW, geo.threads, grid_a, s, t->tv, pv, d_packed, d_ends, w0, w1, n_words, n_bases);
-        }
-        if (ta) { cudaEventRecord(eva.second, s); t->ev_part.push_back(eva); }
-        // phase B: bins, then the spill records; both skip when the chunk overflowed its spill list ...
-        const bool tb = main_begin(t, s, &evb);
-#define M(KW_, W_)                                                                                                         \
-        if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, n_sources, ticket, overflow);  \
-        else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, n_sources, ticket, overflow);    \
-        k_add_hash_counts<KW_, W_><<<t->sms * 2, kBlockThreads, 0, s>>>(t->tv, t->d_spill, spill_cap, spill_n, overflow);  \
-        /* ... in which case the fused kernel redoes the whole chunk (it exits at once otherwise) */                       \
-        if (agg) k_count_reads<KW_, W_, true><<<t->sms * 8, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, w0, w1, n_words, n_bases, overflow); \
-        else k_count_reads<KW_, W_, false><<<t->sms * 8, kBlockThreads, 0, s>>>(t->tv, d_packed, d_ends, w0, w1, n_words, n_bases, overflow)
+    if (!t->d_fhist) {
+        CU(cudaMalloc(&t->d_fhist, kMaxFine * sizeof(uint32_t)));
+        CU(cudaMalloc(&t->d_fcur, kMaxFine * sizeof(unsigned long long)));
+    }
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t reserve = env_u64("TSXC_RESERVE_MB", 4096) << 20;     // staging slots, lookups, the caller
+    const uint64_t budget = free_b > reserve ? free_b - reserve : free_b / 2;
+    const uint32_t groups = g.d2 ? 8 : 0;                                // B holds 1/8 of A
+    const double bytes_per_key = 8.0 * t->L.KW * (1.0 + (groups ? 1.0 / groups : 0.0));
+    const uint64_t cap_max = (uint64_t)((double)budget / bytes_per_key);
+    uint64_t cap = std::min(want, cap_max);
+    if (cap < 2 * seg_keys) return fail(t, TSXC_E_NOMEM, "not enough free device memory for the key buffers of the insert pipeline");
+    uint64_t cap_b = 0;
+    if (groups) cap_b = std::min(cap, std::max<uint64_t>((cap + groups - 1) / groups, 4 * seg_keys));
+    if (const uint64_t e = env_u64("TSXC_GROUP_KEYS", 0)) cap_b = std::min(cap, std::max<uint64_t>(e, 4096));
+    CU(cudaMalloc(&t->d_A, cap * t->L.KW * sizeof(uint64_t)));
+    if (cap_b) {
+        cudaError_t e = cudaMalloc(&t->d_B, cap_b * t->L.KW * sizeof(uint64_t));
+        if (e != cudaSuccess) { cudaGetLastError(); cudaFree(t->d_A); t->d_A = nullptr; return fail(t, TSXC_E_NOMEM, "key buffer B allocation failed"); }
+    }
+    t->cap_A = cap; t->cap_B = cap_b; t->cap_A_limited = cap < want;
+    return TSXC_OK;
+}
+
+// S2 (when the geometry has a second digit) + phase B over the keys currently described by ctl->cur_coff.
+int launch_sort_insert(tsxc_table* t, cudaStream_t s) {
+    const RadixGeom& g = t->rg;
+    const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
+    static const int insert_blocks_per_sm = [] { const int v = (int)env_u64("TSXC_INSERT_GRID", 0); return (v >= 1 && v <= 16) ? v : 6; }();
+    const int grid_b = t->sms * insert_blocks_per_sm;
+    const int grid_p = t->sms * 2;
+#define INS_(KW_, W_, SRC_)                                                                         \
+    if (agg) k_insert_keys<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, t->d_ctl, SRC_);   \
+    else k_insert_keys<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, t->d_ctl, SRC_)
+    if (g.d2 == 0) {
+        PhaseTimer pt(t, s, PH_INSERT);
+#define M(KW_, W_) INS_(KW_, W_, t->d_A)
         TSX_DISPATCH(t->L, M);
 #undef M
-        if (tb) { cudaEventRecord(evb.second, s); t->ev_ins.push_back(evb); }
-        t->n_launches += 4;
-        main_launches += 4;
+        pt.end(1);
+        return TSXC_OK;
     }
-    if (timed) main_end(t, s, ev, main_launches);
+    const uint32_t n_groups = (uint32_t)((t->cap_A + t->cap_B - 1) / t->cap_B);
+    const uint32_t n_fine = g.nbl * g.nb2;
+    for (uint32_t gi = 0; gi < n_groups; ++gi) {
+        {
+            PhaseTimer pt(t, s, PH_PART2);
+#define M(KW_)                                                                                                    \
+            k_plan_group<KW_><<<1, kNB, 0, s>>>(t->d_ctl, gi, t->cap_B, g.nbl, t->d_fhist, n_fine);               \
+            k_hist_keys<KW_><<<grid_p, kRadixThreads, 0, s>>>(t->tv, g, t->d_ctl, t->d_A, t->d_fhist);            \
+            k_scan_fine<<<1, 1024, 0, s>>>(t->d_ctl, t->d_fhist, t->d_fcur, n_fine);                              \
+            k_part_keys<KW_><<<grid_p, kRadixThreads, 0, s>>>(t->tv, g, t->d_ctl, t->d_A, t->d_fcur, t->d_B)
+            TSX_DISPATCH_KW(t->L, M);
+#undef M
+            pt.end(4);
+        }
+        PhaseTimer pt(t, s, PH_INSERT);
+#define M(KW_, W_) INS_(KW_, W_, t->d_B)
+        TSX_DISPATCH(t->L, M);
+#undef M
+        pt.end(1);
+    }
+#undef INS_
+    return TSXC_OK;
+}
+
+// S0 + planner over segments [seg0, seg0 + n_segs) of the batch.
+int launch_hist_plan(tsxc_table* t, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words, uint64_t n_bases,
+                     uint64_t seg0, uint32_t n_segs, uint64_t cap, cudaStream_t s) {
+    const RadixGeom& g = t->rg;
+    int rc;
+    if ((rc = ensure(t, &t->d_seghist, &t->cap_seghist, (size_t)n_segs * g.nb1))) return rc;
+    if ((rc = ensure(t, &t->d_segtotal, &t->cap_segtotal, (size_t)n_segs))) return rc;
+    if ((rc = ensure(t, &t->d_segprefix, &t->cap_segprefix, (size_t)n_segs + 1))) return rc;
+    PhaseTimer pt(t, s, PH_HIST);
+    const int grid = (int)std::min<uint64_t>(n_segs, (uint64_t)t->sms * 2);
+#define M(KW_) k_hist_reads<KW_><<<grid, kRadixThreads, 0, s>>>(t->tv, g, d_packed, d_ends, n_words, n_bases, seg0, n_segs, t->d_seghist, t->d_segtotal)
+    TSX_DISPATCH_KW(t->L, M);
+#undef M
+    k_plan_chunks<<<1, kNB, 0, s>>>(t->d_ctl, t->d_seghist, t->d_segtotal, t->d_segprefix, n_segs, g.nb1, cap, 32ULL << g.seg_log2, t->d_ctr + CTR_ERRORS);
+    pt.end(2);
+    return TSXC_OK;
+}
+
+// How many segments one planner run may cover so that it never needs more than kMaxChunks chunks, and the
+// number of chunk slots to launch for n_segs segments.  The planner evens the chunks out, which at worst halves
+// them: a chunk holds at least fit/2 whole segments (fit = segments that always fit the key buffer).
+void plan_bounds(const RadixGeom& g, uint64_t cap, uint64_t* segs_per_run, uint32_t n_segs, uint32_t* max_chunks) {
+    const uint64_t seg_keys = 32ULL << g.seg_log2;
+    const uint64_t fit = std::max<uint64_t>(2, cap / seg_keys);
+    if (segs_per_run) *segs_per_run = std::max<uint64_t>(1, (uint64_t)(kMaxChunks - 2) * (fit / 2));
+    if (max_chunks) *max_chunks = (uint32_t)std::min<uint64_t>(kMaxChunks, (uint64_t)n_segs / (fit / 2) + 2);
+}
+
+int launch_count_reads_radix(tsxc_table* t, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words,
+                             uint64_t n_bases, cudaStream_t s) {
+    const RadixGeom& g = t->rg;
+    int rc = radix_reserve(t, n_words * 32);
+    if (rc) return rc;
+    const uint64_t seg_words = 1ULL << g.seg_log2;
+    const uint64_t n_segs_total = (n_words + seg_words - 1) / seg_words;
+    uint64_t segs_per_run = 0;
+    plan_bounds(g, t->cap_A, &segs_per_run, 0, nullptr);
+    const int grid_p = t->sms * 2;
+    for (uint64_t seg0 = 0; seg0 < n_segs_total; seg0 += segs_per_run) {
+        const uint32_t n_segs = (uint32_t)std::min<uint64_t>(segs_per_run, n_segs_total - seg0);
+        if ((rc = launch_hist_plan(t, d_packed, d_ends, n_words, n_bases, seg0, n_segs, t->cap_A, s))) return rc;
+        uint32_t max_chunks = 0;
+        plan_bounds(g, t->cap_A, nullptr, n_segs, &max_chunks);
+        for (uint32_t c = 0; c < max_chunks; ++c) {
+            {
+                PhaseTimer pt(t, s, PH_PART1);
+                k_chunk_begin<<<1, kNB, 0, s>>>(t->d_ctl, c);
+#define M(KW_) k_part_reads<KW_><<<grid_p, kRadixThreads, 0, s>>>(t->tv, g, t->d_ctl, c, d_packed, d_ends, n_words, n_bases, seg0, t->d_A, nullptr)
+                TSX_DISPATCH_KW(t->L, M);
+#undef M
+                pt.end(2);
+            }
+            if ((rc = launch_sort_insert(t, s))) return rc;
+        }
+    }
     CU(cudaGetLastError());
     return TSXC_OK;
 }
@@ -325,9 +368,9 @@ int launch_count_reads(tsxc_table* t, const uint64_t* d_packed, const uint64_t* 
     CU(cudaMemsetAsync(d_ends, 0, n_words * sizeof(uint32_t), s));
     k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, d_ends);
     t->n_launches++;
-    // the bins pay off once every region receives a few thousand k-mers per chunk
-    if (t->pbits > 0 && !(t->L.flags & TSXC_FLAG_DIRECT) && n_words >= (16ULL << t->pbits))
-        return launch_count_reads_partitioned(t, d_packed, d_ends, n_words, n_bases, s);
+    // the pipeline pays off once every table region receives a few thousand k-mers per pass
+    if (t->radix_on && !(t->L.flags & TSXC_FLAG_DIRECT) && n_words >= (uint64_t)t->rg.nbl * t->rg.nb2 * 4)
+        return launch_count_reads_radix(t, d_packed, d_ends, n_words, n_bases, s);
     const int grid = grid_for(t, n_words);
     const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -352,6 +395,7 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
     if (2 * k <= l) return fail(t, TSXC_E_INVALID, "Invalid lengths for hashmap size and value of k");  // TSXHashMap.h:93
     Layout L;
     if (!make_layout(k, l, s, flags, rank, n_shards, &L)) return fail(t, TSXC_E_UNSUPPORTED, "(k, l, s, shards) fits no entry class");
+    if (n_shards > (uint32_t)kNB) return fail(t, TSXC_E_UNSUPPORTED, "at most 256 shards");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(t, TSXC_E_CUDA, "no CUDA device (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(t, TSXC_E_INVALID, "device index out of range");
@@ -378,7 +422,10 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
         return bail(TSXC_E_NOMEM);
     }
     if ((e = cudaMalloc(&h->d_ctr, CTR_COUNT * sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaMalloc(&h->d_nout, sizeof(unsigned long long))) != cudaSuccess) {
+        (e = cudaMalloc(&h->d_nout, sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_ctl, sizeof(RadixCtl))) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_ticket_k0, sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_peers, kNB * sizeof(uint64_t*))) != cudaSuccess) {
         h->err = cudaGetErrorString(e);
         return bail(TSXC_E_NOMEM);
     }
@@ -389,26 +436,19 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
             return bail(TSXC_E_CUDA);
         }
     }
-    if ((e = cudaMalloc(&h->d_cursor, (kMaxParts + 8) * sizeof(unsigned long long))) != cudaSuccess) {
-        h->err = cudaGetErrorString(e);
-        return bail(TSXC_E_NOMEM);
-    }
-    if (const char* env = std::getenv("TSXC_L2_FETCH")) {  // experiment: L2 fetch granularity hint (32/64/128)
-        const int v = std::atoi(env);
-        if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
-    }
-    if (const char* env = std::getenv("TSXC_PART_STATIC")) h->part_static = std::atoi(env) == 1;
+    // Fine table regions of 2^region_log2 bytes (default 8 MiB: profiles/r02_k0r_fetch.md); tables of 512 MiB and
+    // more take the region-sorted pipeline.  TSXC_REGION_LOG2 overrides both (tests force tiny tables through it).
+    uint32_t min_table_log2 = 29;
     if (const char* env = std::getenv("TSXC_REGION_LOG2")) {
         const int v = std::atoi(env);
-        if (v >= 16 && v <= 40) h->region_log2 = (uint32_t)v;
+        if (v >= 12 && v <= 40) { h->region_log2 = (uint32_t)v; min_table_log2 = (uint32_t)v + 1; }
     }
-    {   // regions of 2^region_log2 bytes (default 128 MiB); a bucket is 32 bytes
-        const uint32_t table_log2 = L.LBl + 5;
-        h->pbits = table_log2 > h->region_log2 ? table_log2 - h->region_log2 : 0;
-        if (h->pbits > 12) h->pbits = 12;   // kMaxParts bins
-        if (h->pbits > L.LBl) h->pbits = L.LBl;
-    }
+    uint32_t seg_log2 = (uint32_t)env_u64("TSXC_SEG_LOG2", kSegWordsLog2Default);
+    seg_log2 = std::max<uint32_t>(kSegWordsLog2Min, std::min<uint32_t>(seg_log2, 20));
+    h->rg = make_radix_geom(L, h->region_log2, seg_log2);
+    h->radix_on = (L.LBl + 5 >= min_table_log2) && (h->rg.d1 > L.shard_bits);
     h->tv = make_view(L, h->d_words, h->d_ctr);
+    CU(cudaMemsetAsync(h->d_ctl, 0, sizeof(RadixCtl), h->stream));
     int rc = tsxc_clear(h);
     if (rc != TSXC_OK) return bail(rc);
     *out = h;
@@ -523,11 +563,12 @@ int tsxc_destroy(tsxc_table* t) {
         if (st.copied) cudaEventDestroy(st.copied);
         if (st.done) cudaEventDestroy(st.done);
     }
-    for (auto* v : {&t->ev_pending, &t->ev_part, &t->ev_ins})
-        for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto& ev : t->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto& pe : t->ev_phase) { cudaEventDestroy(pe.ev.first); cudaEventDestroy(pe.ev.second); }
     for (auto& ev : t->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& m : t->marks) if (m) cudaEventDestroy(m);
-    cudaFree(t->d_part); cudaFree(t->d_spill); cudaFree(t->d_cursor); cudaFree(t->d_subfill);
+    cudaFree(t->d_A); cudaFree(t->d_B); cudaFree(t->d_ctl); cudaFree(t->d_seghist); cudaFree(t->d_segtotal); cudaFree(t->d_segprefix);
+    cudaFree(t->d_fhist); cudaFree(t->d_fcur); cudaFree(t->d_peers); cudaFree(t->d_ticket_k0);
     cudaFree(t->d_ends); cudaFree(t->d_keys); cudaFree(t->d_counts); cudaFree(t->d_nout);
     cudaFree(t->d_ctr); cudaFree(t->d_words);
     if (t->stream) cudaStreamDestroy(t->stream);
@@ -543,12 +584,20 @@ int tsxc_clear(tsxc_table* t) {
     CU(cudaMemsetAsync(t->d_words, 0, t->L.table_bytes, t->stream));
     CU(cudaMemsetAsync(t->d_ctr, 0, CTR_COUNT * sizeof(unsigned long long), t->stream));
     t->err.clear();
-    for (auto* v : {&t->ev_pending, &t->ev_part, &t->ev_ins}) {
-        for (auto& ev : *v) t->ev_free.push_back(ev);
-        v->clear();
-    }
-    t->n_launches = t->n_main_launches = 0; t->main_ms = t->part_ms = t->ins_ms = 0.0;
+    for (auto& ev : t->ev_pending) t->ev_free.push_back(ev);
+    t->ev_pending.clear();
+    for (auto& pe : t->ev_phase) t->ev_free.push_back(pe.ev);
+    t->ev_phase.clear();
+    t->n_launches = t->n_main_launches = 0; t->main_ms = 0.0;
+    for (double& m : t->phase_ms) m = 0.0;
     return TSXC_OK;
+}
+
+int tsxc_trim(tsxc_table* t) {
+    if (!t) return TSXC_E_INVALID;
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    return release_radix_buffers(t);
 }
 
 void* tsxc_stream(tsxc_table* t) { return t ? (void*)t->stream : nullptr; }
@@ -563,8 +612,9 @@ int tsxc_mark(tsxc_table* t, int idx) {
 }
 
 int tsxc_mark_elapsed_ms(tsxc_table* t, int a, int b, float* ms_out) {
-    if (!t || !ms_out || a < 0 || a >= 8 || b < 0 || b >= 8 || !t->marks[a] || !t->marks[b]) return fail(t, TSXC_E_INVALID, "bad mark index");
+    if (!t || !ms_out || a < 0 || a >= 8 || b < 0 || b >= 8) return fail(t, TSXC_E_INVALID, "bad mark index");
     std::lock_guard<std::mutex> g(t->mu);
+    if (!t->marks[a] || !t->marks[b]) return fail(t, TSXC_E_INVALID, "mark not recorded");
     CU(cudaEventElapsedTime(ms_out, t->marks[a], t->marks[b]));
     return TSXC_OK;
 }
@@ -645,14 +695,11 @@ int tsxc_sync(tsxc_table* t) {
     CU(cudaStreamSynchronize(t->stream));
     unsigned long long flags = 0;
     CU(cudaMemcpy(&flags, t->d_ctr + CTR_ERRORS, sizeof flags, cudaMemcpyDeviceToHost));
+    collect_main_ms(t);          // recycle the timing event pairs of the batches that have completed
     return status_from_flags(t, flags);
 }
 
-int tsxc_lookup_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, uint64_t* d_counts_out) {
-    if (!t || ((!d_kmers || !d_counts_out) && n)) return fail(t, TSXC_E_INVALID, "null argument");
-    if (n == 0) return TSXC_OK;
-    std::lock_guard<std::mutex> g(t->mu);
-    CU(cudaSetDevice(t->device));
+static int lookup_device_locked(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, uint64_t* d_counts_out) {
     const int grid = grid_for(t, n);
 #define M(KW_, W_) k_lookup<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n, d_counts_out)
     TSX_DISPATCH(t->L, M);
@@ -662,21 +709,26 @@ int tsxc_lookup_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, uint6
     return TSXC_OK;
 }
 
+int tsxc_lookup_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, uint64_t* d_counts_out) {
+    if (!t || ((!d_kmers || !d_counts_out) && n)) return fail(t, TSXC_E_INVALID, "null argument");
+    if (n == 0) return TSXC_OK;
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    return lookup_device_locked(t, d_kmers, n, d_counts_out);
+}
+
 int tsxc_lookup(tsxc_table* t, const uint64_t* kmers, uint64_t n, uint64_t* counts_out) {
     if (!t || ((!kmers || !counts_out) && n)) return fail(t, TSXC_E_INVALID, "null argument");
     if (n == 0) return TSXC_OK;
-    {
-        std::lock_guard<std::mutex> g(t->mu);
-        CU(cudaSetDevice(t->device));
-        CU(cudaStreamSynchronize(t->stream));
-        int rc;
-        if ((rc = ensure(t, &t->d_keys, &t->cap_keys, (size_t)n * t->L.KW))) return rc;
-        if ((rc = ensure(t, &t->d_counts, &t->cap_counts, (size_t)n))) return rc;
-        CU(cudaMemcpyAsync(t->d_keys, kmers, n * t->L.KW * sizeof(uint64_t), cudaMemcpyHostToDevice, t->stream));
-    }
-    int rc = tsxc_lookup_device(t, t->d_keys, n, t->d_counts);
-    if (rc) return rc;
+    // one critical section: the staging buffers are shared with add_kmers / dump on the same handle
     std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->stream));
+    int rc;
+    if ((rc = ensure(t, &t->d_keys, &t->cap_keys, (size_t)n * t->L.KW))) return rc;
+    if ((rc = ensure(t, &t->d_counts, &t->cap_counts, (size_t)n))) return rc;
+    CU(cudaMemcpyAsync(t->d_keys, kmers, n * t->L.KW * sizeof(uint64_t), cudaMemcpyHostToDevice, t->stream));
+    if ((rc = lookup_device_locked(t, t->d_keys, n, t->d_counts))) return rc;
     CU(cudaMemcpyAsync(counts_out, t->d_counts, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, t->stream));
     CU(cudaStreamSynchronize(t->stream));
     return TSXC_OK;
@@ -702,7 +754,10 @@ int tsxc_stats(tsxc_table* t, tsxc_stats_t* out) {
     out->kmers_added = c[CTR_ADDED]; out->max_reprobe = c[CTR_MAXPROBE]; out->error_flags = c[CTR_ERRORS];
     collect_main_ms(t);
     out->kernel_launches = t->n_launches; out->main_kernel_launches = t->n_main_launches; out->main_kernel_ms = t->main_ms;
-    out->partition_ms = t->part_ms; out->insert_ms = t->ins_ms;
+    out->partition_ms = t->phase_ms[PH_HIST] + t->phase_ms[PH_PART1] + t->phase_ms[PH_PART2]; out->insert_ms = t->phase_ms[PH_INSERT];
+    out->hist_ms = t->phase_ms[PH_HIST]; out->part1_ms = t->phase_ms[PH_PART1]; out->part2_ms = t->phase_ms[PH_PART2];
+    out->chunk_cap_keys = t->cap_A; out->group_cap_keys = t->cap_B;
+    out->radix_digit1_bits = t->rg.d1; out->radix_digit2_bits = t->rg.d2;
     return TSXC_OK;
 }
 
@@ -760,130 +815,121 @@ int tsxc_dump_file(tsxc_table* t, const char* path) {
     return rc;
 }
 
-int tsxc_route_layout(tsxc_table* t, uint64_t max_chunk_words, uint32_t kmers_per_position_q16, tsxc_route_layout_t* out) {
+
+/* ---- multi-GPU routing -------------------------------------------------------------------------------------- */
+int tsxc_route_info(tsxc_table* t, tsxc_route_info_t* out) {
     if (!t || !out) return fail(t, TSXC_E_INVALID, "null argument");
-    const Layout& L = t->L;
-    const uint32_t n_shards = 1u << L.shard_bits;
-    // regions of 2^region_log2 bytes inside the shard, limited so that all shards' bins fit one partition kernel
-    uint32_t pb = t->pbits;
-    while (pb > 0 && ((uint64_t)n_shards << pb) > (uint64_t)kMaxParts) --pb;
-    if (n_shards > (uint32_t)kMaxParts) return fail(t, TSXC_E_UNSUPPORTED, "too many shards");
-    const uint64_t chunk_words = max_chunk_words ? max_chunk_words : (1ULL << 24) / L.KW;
-    const uint32_t P = n_shards << pb;
-    const double frac = kmers_per_position_q16 ? std::min(1.0, kmers_per_position_q16 / 65536.0) : 1.0;
-    const uint64_t cap = part_geometry(t, P, chunk_words, frac).cap;
     std::memset(out, 0, sizeof *out);
-    out->n_shards = n_shards; out->bins_per_shard = 1u << pb; out->key_words = L.KW; out->spill_record_words = L.KW + 1;
-    out->chunk_words = chunk_words; out->bin_cap = cap; out->block_words = ((uint64_t)1 << pb) * cap * L.KW;
-    out->spill_cap = std::max<uint64_t>(4096, 32 * chunk_words / 32 / n_shards * 2);   // per destination: twice its share of one record per 32 positions
+    out->n_shards = 1u << t->L.shard_bits; out->shard_rank = t->L.shard_rank;
+    out->bins = t->rg.nb1; out->bins_per_shard = t->rg.nbl; out->key_words = t->L.KW;
+    out->recv_cap_keys = t->cap_A;
     return TSXC_OK;
 }
 
-int tsxc_route_prepare(tsxc_table* t, const uint64_t* d_offsets, uint64_t n_reads, uint64_t n_bases) {
-    if (!t || !d_offsets) return fail(t, TSXC_E_INVALID, "null argument");
+int tsxc_route_recv_buffer(tsxc_table* t, uint64_t cap_keys, void** d_ptr_out, uint64_t* cap_keys_out) {
+    if (!t || !d_ptr_out) return fail(t, TSXC_E_INVALID, "null argument");
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
+    if (t->peers_set) return fail(t, TSXC_E_INVALID, "receive buffer already exported");
+    // cap_keys == 0: as much as free memory allows (radix_reserve's policy), else exactly what the caller asks for
+    int rc = radix_reserve(t, cap_keys ? cap_keys : ~0ULL >> 8);
+    if (rc) return rc;
+    *d_ptr_out = t->d_A;
+    if (cap_keys_out) *cap_keys_out = t->cap_A;
+    return TSXC_OK;
+}
+
+int tsxc_route_set_peers(tsxc_table* t, void* const* peer_buffers, uint64_t recv_cap_keys) {
+    if (!t || !peer_buffers) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    const uint32_t n = 1u << t->L.shard_bits;
+    if (!t->d_A || peer_buffers[t->L.shard_rank] != (void*)t->d_A) return fail(t, TSXC_E_INVALID, "peer_buffers[shard_rank] must be this handle's receive buffer");
+    if (recv_cap_keys == 0 || recv_cap_keys > t->cap_A) return fail(t, TSXC_E_INVALID, "common receive capacity exceeds this rank's buffer");
+    CU(cudaMemcpyAsync(t->d_peers, peer_buffers, n * sizeof(void*), cudaMemcpyHostToDevice, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    t->cap_A = recv_cap_keys;        // every rank plans against the smallest buffer of the group
+    if (t->cap_B > t->cap_A) t->cap_B = t->cap_A;
+    t->peers_set = true;
+    return TSXC_OK;
+}
+
+int tsxc_route_begin(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint64_t n_reads, uint64_t n_bases,
+                     uint32_t* rounds_out) {
+    if (!t || !rounds_out || (n_reads && !d_offsets) || (n_bases && !d_packed)) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    if (!t->peers_set) return fail(t, TSXC_E_INVALID, "tsxc_route_set_peers has not been called");
     const uint64_t n_words = (n_bases + 31) >> 5;
+    cudaStream_t s = t->stream;
     int rc = ensure(t, &t->d_ends, &t->cap_ends, (size_t)n_words + 8);
     if (rc) return rc;
-    CU(cudaMemsetAsync(t->d_ends, 0, (n_words + 8) * sizeof(uint32_t), t->stream));
+    CU(cudaMemsetAsync(t->d_ends, 0, (n_words + 8) * sizeof(uint32_t), s));
     if (n_reads) {
-        k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, t->stream>>>(d_offsets, n_reads, t->d_ends);
+        k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, t->d_ends);
         t->n_launches++;
     }
+    const RadixGeom& rg = t->rg;
+    const uint64_t seg_words = 1ULL << rg.seg_log2;
+    const uint64_t n_segs = (n_words + seg_words - 1) / seg_words;
+    // a rank sends chunks of at most 7/8 of the common receive capacity: owners are hash-uniform, so what a rank
+    // receives per round concentrates around the mean chunk size; k_route_offsets checks the exact totals
+    const uint64_t cap_send = std::max<uint64_t>(2 * (32ULL << rg.seg_log2), t->cap_A - t->cap_A / 8);
+    uint64_t segs_per_run = 0;
+    plan_bounds(rg, cap_send, &segs_per_run, 0, nullptr);
+    if (n_segs > segs_per_run) return fail(t, TSXC_E_INVALID, "batch too large for one routing plan: split it");
+    uint32_t max_chunks = 0;
+    if (n_segs) {
+        if ((rc = launch_hist_plan(t, d_packed, t->d_ends, n_words, n_bases, 0, (uint32_t)n_segs, cap_send, s))) return rc;
+        plan_bounds(rg, cap_send, nullptr, (uint32_t)n_segs, &max_chunks);
+    } else {
+        CU(cudaMemsetAsync(t->d_ctl, 0, 16, s));     // n_chunks = 0
+    }
+    t->route_packed = d_packed; t->route_n_words = n_words; t->route_n_bases = n_bases; t->route_rounds = max_chunks;
+    *rounds_out = max_chunks;
     CU(cudaGetLastError());
     return TSXC_OK;
 }
 
-int tsxc_route_chunk(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64_t* d_packed, uint64_t n_bases,
-                     uint64_t w_begin, uint64_t w_end, uint64_t* d_bins, unsigned long long* d_cursors,
-                     uint64_t* d_spill, unsigned long long* d_spill_n) {
-    if (!t || !lay || !d_bins || !d_cursors || !d_spill || !d_spill_n || (!d_packed && w_end > w_begin))
-        return fail(t, TSXC_E_INVALID, "null argument");
-    if (w_end < w_begin || w_end - w_begin > lay->chunk_words) return fail(t, TSXC_E_INVALID, "chunk larger than the layout allows");
+int tsxc_route_hist(tsxc_table* t, uint32_t round, uint32_t* d_hist_out) {
+    if (!t || !d_hist_out) return fail(t, TSXC_E_INVALID, "null argument");
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
-    const Layout& L = t->L;
-    const uint64_t n_words = (n_bases + 31) >> 5;
-    const uint32_t P = lay->n_shards * lay->bins_per_shard;
-    uint32_t pb = 0;
-    while ((1u << pb) < lay->bins_per_shard) ++pb;
+    k_round_hist<<<1, kNB, 0, t->stream>>>(t->d_ctl, round, t->rg.nb1, d_hist_out);
+    t->n_launches++;
+    CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
+int tsxc_route_send(tsxc_table* t, uint32_t round, const uint32_t* d_hist_all) {
+    if (!t || !d_hist_all) return fail(t, TSXC_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    if (!t->peers_set) return fail(t, TSXC_E_INVALID, "tsxc_route_set_peers has not been called");
+    const RadixGeom& rg = t->rg;
     cudaStream_t s = t->stream;
-    CU(cudaMemsetAsync(d_cursors, 0, (size_t)P * sizeof(unsigned long long), s));
-    CU(cudaMemsetAsync(d_spill_n, 0, (size_t)lay->n_shards * sizeof(unsigned long long), s));
-    if (w_end == w_begin) return TSXC_OK;
-    const PartGeom geo = part_geometry(t, P, lay->chunk_words);
-    PartView pv{};
-    pv.buf = d_bins; pv.cursor = d_cursors; pv.cap = lay->bin_cap;
-    pv.pshift = L.LBl - pb; pv.pmask = P - 1; pv.P = P;
-    pv.run = geo.run; pv.tile_words = geo.tile_words;
-    pv.spill = d_spill; pv.spill_n = d_spill_n; pv.spill_cap = lay->spill_cap; pv.bins_per_shard_log2 = pb;
-    pv.overflow = reinterpret_cast<unsigned int*>(t->d_cursor + kMaxParts + 3);   // read back by tsxc_route_overflowed
-    CU(cudaMemsetAsync(pv.overflow, 0, sizeof(unsigned long long), s));
-    const int grid_a = (int)std::max<uint64_t>(1, std::min<uint64_t>((w_end - w_begin + geo.tile_words - 1) / geo.tile_words, (uint64_t)geo.grid));
-    std::pair<cudaEvent_t, cudaEvent_t> ev;
-    const bool timed = main_begin(t, s, &ev);
-    launch_partition(L.KW, geo.threads, grid_a, s, t->tv, pv, d_packed, t->d_ends, w_begin, w_end, n_words, n_bases);
-    t->n_launches++;
-    if (timed) { cudaEventRecord(ev.second, s); t->ev_part.push_back(ev); t->n_main_launches++; }
-    CU(cudaGetLastError());
-    return TSXC_OK;
-}
-
-int tsxc_route_overflowed(tsxc_table* t, int* overflowed) {
-    if (!t || !overflowed) return fail(t, TSXC_E_INVALID, "null argument");
-    std::lock_guard<std::mutex> g(t->mu);
-    CU(cudaSetDevice(t->device));
-    CU(cudaStreamSynchronize(t->stream));
-    unsigned long long flag = 0;
-    CU(cudaMemcpy(&flag, t->d_cursor + kMaxParts + 3, sizeof flag, cudaMemcpyDeviceToHost));
-    *overflowed = flag ? 1 : 0;
-    if (flag) CU(cudaMemset(t->d_cursor + kMaxParts + 3, 0, sizeof flag));
-    return TSXC_OK;
-}
-
-int tsxc_insert_routed(tsxc_table* t, const tsxc_route_layout_t* lay, const uint64_t* d_bins,
-                       const unsigned long long* d_cursors, uint32_t n_sources) {
-    if (!t || !lay || !d_bins || !d_cursors) return fail(t, TSXC_E_INVALID, "null argument");
-    if (n_sources == 0) return TSXC_OK;
-    std::lock_guard<std::mutex> g(t->mu);
-    CU(cudaSetDevice(t->device));
-    cudaStream_t s = t->stream;
-    PartView pv{};
-    pv.buf = const_cast<uint64_t*>(d_bins); pv.cursor = const_cast<unsigned long long*>(d_cursors);
-    pv.cap = lay->bin_cap; pv.P = n_sources * lay->bins_per_shard;
-    const uint32_t slice_entries = slice_entries_cfg(t->L.flags);
-    const uint32_t slices = (uint32_t)((lay->bin_cap + slice_entries - 1) / slice_entries);
-    unsigned long long* ticket = t->d_cursor + kMaxParts;
-    CU(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s));
-    const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
-    const int grid_b = t->sms * 8;
-    std::pair<cudaEvent_t, cudaEvent_t> ev;
-    const bool timed = main_begin(t, s, &ev);
-#define M(KW_, W_)                                                                                        \
-    if (agg) k_insert_partitions<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, n_sources, ticket, nullptr); \
-    else k_insert_partitions<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, pv, slices, slice_entries, n_sources, ticket, nullptr)
-    TSX_DISPATCH(t->L, M);
+    PhaseTimer pt(t, s, PH_PART1);
+    k_route_offsets<<<1, kNB, 0, s>>>(t->d_ctl, round, d_hist_all, 1u << t->L.shard_bits, t->L.shard_rank, rg.nb1, rg.nbl, t->cap_A,
+                                      t->d_ctr + CTR_ERRORS);
+    const int grid_p = t->sms * 2;
+#define M(KW_) k_part_reads<KW_><<<grid_p, kRadixThreads, 0, s>>>(t->tv, rg, t->d_ctl, round, t->route_packed, t->d_ends, t->route_n_words, t->route_n_bases, 0, t->d_A, t->d_peers)
+    TSX_DISPATCH_KW(t->L, M);
 #undef M
-    t->n_launches++;
-    if (timed) { cudaEventRecord(ev.second, s); t->ev_ins.push_back(ev); t->n_main_launches++; }
+    pt.end(2);
     CU(cudaGetLastError());
     return TSXC_OK;
 }
 
-int tsxc_add_hash_counts_device(tsxc_table* t, const uint64_t* d_records, uint64_t n) {
-    if (!t || (!d_records && n)) return fail(t, TSXC_E_INVALID, "null argument");
-    if (n == 0) return TSXC_OK;
+int tsxc_route_insert(tsxc_table* t) {
+    if (!t) return TSXC_E_INVALID;
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
-    const int grid = grid_for(t, n);
-#define M(KW_, W_) k_add_hash_counts<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_records, n, nullptr, nullptr)
-    TSX_DISPATCH(t->L, M);
-#undef M
-    t->n_launches++;
+    int rc = launch_sort_insert(t, t->stream);
+    if (rc) return rc;
     CU(cudaGetLastError());
     return TSXC_OK;
 }
+
 
 int tsxc_gen_reads_device(const tsxc_gen_params* p, uint64_t first, uint64_t count, int device, void* stream,
                           uint64_t* d_packed, uint64_t* d_offsets) {
@@ -1065,7 +1111,7 @@ int tsxc_k0_region_sweep(tsxc_table* t, uint64_t footprint_bytes, uint64_t regio
     uint64_t fw = 32, rw = 32;
     while (fw * 2 * 8 <= std::min<uint64_t>(footprint_bytes, t->L.table_bytes)) fw *= 2;
     while (rw * 2 * 8 <= region_bytes && rw * 2 <= fw) rw *= 2;
-    unsigned long long* ticket = t->d_cursor + kMaxParts;
+    unsigned long long* ticket = t->d_ticket_k0;
     CU(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), t->stream));
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));

@@ -1,0 +1,815 @@
+// tsx_radix.cuh — the region-sorted insert pipeline for tables far larger than L2 / TLB reach.
+//
+// Measured on B200 (profiles/r01_k0_random_access.md, profiles/r02_k0r_fetch.md): a dependent sector load +
+// atomic runs at 4 G/s when spread uniformly over 128 GiB, at 45 G/s when all SMs work inside one 128 MiB
+// region at a time and at 65-69 G/s for 8-16 MiB regions.  So k-mer hashes are sorted by table region first,
+// with a two-digit most-significant-digit radix partition whose every store is a coalesced run, and inserted in
+// region order afterwards:
+//
+//   S0  k_hist_reads   extract + hash every k-mer, count per (segment of the read stream, digit 1)
+//       k_plan_chunks  device-side planner: cuts the batch into chunks of at most `cap` k-mers and turns the
+//                      counts into exact bin offsets  ->  nothing is sized by guesswork, no bin can overflow,
+//                      whatever the skew of the input
+//   S1  k_part_reads   extract + hash again, block-local counting sort of a tile by digit 1 in shared memory,
+//                      coalesced runs into buffer A (exact positions reserved with one atomicAdd per (tile, bin));
+//                      in the multi-GPU path the runs go straight into the owning rank's peer-mapped buffer
+//   S2a k_hist_keys    digit-2 histogram of a group of A           (exact sizes of the fine bins)
+//       k_scan_fine    exclusive scan -> fine-bin offsets
+//   S2b k_part_keys    the same tile sort on digit 2: A -> B, B is ordered by fine table region
+//   B   k_insert_keys  blocks take consecutive slices of B through a ticket, so the whole chip probes one or two
+//                      8-16 MiB table regions at a time; duplicates inside a slice are combined in shared memory
+//                      before they reach the table (heavy hitters cost one atomic per slice, not one per k-mer)
+//
+// Ranking inside a tile uses warp-private counters and a per-digit-bit ballot match (no shared-memory atomics:
+// at 2 cycles per lane they would cost more than everything else in these kernels together).
+//
+// Reference semantics: extraction src/mains/testExecution.h:15-36, encoding src/utils/SequenceUtils.h:86-123,
+// insert src/tsxcount/TSXHashMapPerf.h:56-205 (paths relative to mjoppich/tsxCount).  Nothing here has a
+// counterpart in the reference: it inserts k-mer by k-mer in input order (src/mains/main.cpp:159-192).
+#pragma once
+
+#include <cstdint>
+
+#include "tsx_kernels.cuh"
+#include "tsx_table.cuh"
+
+namespace tsx {
+
+constexpr int kRadixThreads = 512;
+constexpr int kRadixWarps = kRadixThreads / 32;
+constexpr int kNB = 256;                    // bins per digit (digits are at most 8 bits wide)
+constexpr int kSegWordsLog2Default = 15;    // planner granularity: 2^15 packed words = 2^20 base positions
+constexpr int kSegWordsLog2Min = 9;         // one block round (16 warps x 32 words)
+constexpr int kMaxChunks = 64;
+constexpr int kMaxFine = kNB * kNB;
+constexpr int kCombSlots = 1024;            // shared-memory combiner of phase B
+
+// Digit geometry, derived once per handle on the host.
+//   global bucket index bg = H.w[0] & lbg_mask  (LBg bits; its top shard_bits select the owning shard)
+//   digit 1 = top d1 bits of bg                 (includes the owner bits: bins of S1 are owner-major)
+//   local coarse bin = digit 1 without the owner bits (nbl = 2^(d1 - shard_bits) per shard)
+//   digit 2 = the next d2 bits; fine bin (local) = local coarse bin * nb2 + digit 2
+struct RadixGeom {
+    uint32_t d1, d2;
+    uint32_t nb1, nb2, nbl;
+    uint32_t shift1, shift2;     // bg >> shift1 = digit 1 ; (bg >> shift2) & (nb2-1) = digit 2
+    uint32_t owner_shift;        // digit 1 >> owner_shift = owning shard
+    uint32_t seg_log2;           // packed words per planner segment, log2 (>= kSegWordsLog2Min)
+};
+
+struct ChunkDesc {
+    uint64_t seg_begin, seg_end;           // segments [seg_begin, seg_end) of the batch
+    uint64_t n_keys;
+    uint64_t coff[kNB + 1];                // exclusive prefix of the digit-1 counts
+};
+
+struct GroupDesc {
+    uint64_t a0, a1;                       // keys [a0, a1) of A
+    uint32_t n_items, active;
+    uint32_t itemstart[kNB + 1];           // tiles of local coarse bin b are items [itemstart[b], itemstart[b+1])
+};
+
+struct RadixCtl {
+    uint32_t n_chunks, chunk_active;
+    uint32_t plan_error, recv_overflow;
+    unsigned long long ticket[4];          // 0: S2a, 1: S2b, 2: phase B
+    unsigned long long cursor1[kNB];       // S1 reservation cursors: position inside the destination buffer
+    unsigned long long n_insert;           // keys phase B has to insert (group size, or everything when d2 == 0)
+    uint64_t cur_coff[kNB + 1];            // local coarse-bin offsets of the buffer A that S2 / phase B read
+    GroupDesc group;
+    ChunkDesc chunk[kMaxChunks];
+};
+
+#if defined(__CUDACC__)
+
+template <int KW> struct RadixCfg {
+    static constexpr int OPT = 8 / KW;                       // keys per thread per tile
+    static constexpr int TILE = kRadixThreads * OPT;         // 4096 / 2048 / 1024 keys = 32 KB of shared memory
+    static constexpr int MINB = KW == 4 ? 1 : 2;
+};
+
+__device__ __forceinline__ uint32_t digit1_of(const RadixGeom& rg, uint64_t lbg_mask, uint64_t h0) {
+    return (uint32_t)((h0 & lbg_mask) >> rg.shift1);
+}
+__device__ __forceinline__ uint32_t digit2_of(const RadixGeom& rg, uint64_t lbg_mask, uint64_t h0) {
+    return (uint32_t)((h0 & lbg_mask) >> rg.shift2) & (rg.nb2 - 1);
+}
+
+// ---- one lane's view of the packed read stream ---------------------------------------------------------------
+// Lane `lane` of a warp owns stream word base+lane and enumerates the k-mers that START in it, offsets 31..0
+// (descending: the distance to the next read end is carried from the right).
+template <int KW>
+struct KmerLane {
+    static constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
+    uint64_t win[KW + 1];
+    uint64_t g0, limit;
+    uint32_t ends_cur, dist;
+    __device__ __forceinline__ void load(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ends,
+                                         uint64_t base, uint64_t n_words, uint64_t w_end, uint64_t n_bases, unsigned lane) {
+        uint32_t ewin[NE + 1];
+        load_window<KW, uint64_t>(packed, base, n_words, lane, win);
+        load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
+        ends_cur = ewin[0];
+        dist = first_end_after<NE>(ewin);
+        g0 = (base + lane) << 5;
+        limit = (base + lane < w_end) ? n_bases : 0;     // lanes past the range emit nothing
+    }
+    __device__ __forceinline__ bool kmer_at(int o, uint32_t k, const HashParams& hp, Key<KW>& key) {
+        dist = ((ends_cur >> o) & 1u) ? 0u : (dist == 0xffffffffu ? dist : dist + 1u);
+        const bool valid = (dist >= k - 1) && (g0 + (uint64_t)o + k <= limit);
+        const unsigned sh = 2u * (unsigned)o;
+#pragma unroll
+        for (int j = 0; j < KW; ++j)
+            key.w[j] = (sh ? ((win[j] >> sh) | (win[j + 1] << (64 - sh))) : win[j]) & word_mask<KW>(j, hp);
+        return valid;
+    }
+};
+
+// ---- warp-private ranking -------------------------------------------------------------------------------------
+// Lanes holding the same digit form a group; the group's first lane bumps the warp's own counter by the group
+// size, every lane's rank is the old counter value + its position inside the group.  No atomics: the counter row
+// belongs to this warp alone.  TSX_RANK_MATCH selects MATCH.ANY instead of one ballot per digit bit.
+__device__ __forceinline__ unsigned match_digit(bool valid, uint32_t digit, uint32_t bits) {
+    const unsigned full = 0xffffffffu;
+#if defined(TSX_RANK_MATCH)
+    (void)bits;
+    const unsigned vm = __ballot_sync(full, valid);
+    return valid ? __match_any_sync(vm, digit) : 0u;
+#else
+    // one ballot per digit bit; lanes whose bit is clear take the complement.  Hand-written so that a bit costs four
+    // instructions (test -> predicate, vote, two predicated ANDs): these kernels are bound by the integer ALU pipe.
+    unsigned peers = __ballot_sync(full, valid);
+#pragma unroll
+    for (uint32_t b = 0; b < 8; ++b) {
+        if (b >= bits) break;
+        asm volatile("{\n\t"
+                     ".reg .pred p;\n\t"
+                     ".reg .b32 t, v;\n\t"
+                     "and.b32 t, %1, %2;\n\t"
+                     "setp.ne.u32 p, t, 0;\n\t"
+                     "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+                     "@p and.b32 %0, %0, v;\n\t"
+                     "@!p lop3.b32 %0, %0, v, 0, 0x30;\n\t"     // a & ~b
+                     "}"
+                     : "+r"(peers) : "r"(digit), "r"(1u << b));
+    }
+    return valid ? peers : 0u;
+#endif
+}
+
+template <typename CT>
+__device__ __forceinline__ uint32_t rank_in_warp(CT* __restrict__ wcnt, bool valid, uint32_t digit, unsigned lane, uint32_t bits) {
+    const unsigned full = 0xffffffffu;
+    const unsigned peers = match_digit(valid, digit, bits);
+    const int leader = valid ? (__ffs(peers) - 1) : (int)lane;
+    uint32_t old = 0;
+    if (valid && (unsigned)leader == lane) {
+        old = wcnt[digit];
+        wcnt[digit] = (CT)(old + __popc(peers));
+    }
+    old = __shfl_sync(full, old, leader);
+    __syncwarp();
+    return old + __popc(peers & ((1u << lane) - 1u));
+}
+
+// Exclusive scan of v over the first 256 threads of the block (the others pass 0).  scratch: 8 words of shared
+// memory.  Contains two __syncthreads; every thread of the block must call it.
+__device__ __forceinline__ uint32_t block_exscan_256(uint32_t v, uint32_t* scratch, uint32_t* total) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(full, inc, d);
+        if (lane >= (unsigned)d) inc += y;
+    }
+    if (warp < 8 && lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t s = scratch[w];
+        if ((unsigned)w < warp) pre += s;
+        tot += s;
+    }
+    __syncthreads();
+    if (total) *total = tot;
+    return pre + inc - v;
+}
+
+// 64-bit variant for values below 2^40 each: the low 23 bits and the rest are scanned separately (their prefix
+// sums over 256 entries fit 32 bits) and recombined, which is exact.
+__device__ __forceinline__ uint64_t block_exscan_256_u64(uint64_t v, uint32_t* scratch, uint64_t* total) {
+    uint32_t tlo = 0, thi = 0;
+    const uint32_t plo = block_exscan_256((uint32_t)(v & 0x7fffffULL), scratch, &tlo);
+    const uint32_t phi = block_exscan_256((uint32_t)(v >> 23), scratch, &thi);
+    if (total) *total = ((uint64_t)thi << 23) + tlo;
+    return ((uint64_t)phi << 23) + plo;
+}
+
+template <int KW>
+struct TileSmem {
+    uint64_t sorted[RadixCfg<KW>::TILE * KW];
+    long long gdelta[kNB];            // position of a bin's run in its destination minus its start inside the tile
+    uint32_t binstart[kNB];
+    uint32_t scratch[8];
+    uint16_t cnt[kRadixWarps][kNB];
+};
+
+template <int KW>
+__device__ __forceinline__ void tile_smem_init(TileSmem<KW>& sm) {
+    for (uint32_t i = threadIdx.x; i < kRadixWarps * kNB / 2; i += kRadixThreads) reinterpret_cast<uint32_t*>(&sm.cnt[0][0])[i] = 0u;
+}
+
+// Block-local counting sort of one tile by an 8-bit digit and coalesced write of every bin's run.
+//   Hs / vmask : the thread's OPT keys and which of them exist
+//   digit      : key word 0 -> digit
+//   reserve    : (bin, n) -> first position of a run of n keys of `bin` in its destination   (thread `bin`, n > 0)
+//   dst        : bin -> base pointer of its destination buffer
+// On entry sm.cnt is all zero (and visible to the block); on exit it is zero again.
+template <int KW, typename DigitFn, typename ReserveFn, typename DstFn>
+__device__ __forceinline__ void tile_partition(TileSmem<KW>& sm, const Key<KW> (&Hs)[RadixCfg<KW>::OPT], uint32_t vmask,
+                                               uint32_t bits, DigitFn digit, ReserveFn reserve, DstFn dst) {
+    constexpr int OPT = RadixCfg<KW>::OPT;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t rk[OPT];
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) {
+        const bool v = (vmask >> j) & 1u;
+        const uint32_t d = v ? digit(Hs[j].w[0]) : 0u;
+        rk[j] = rank_in_warp<uint16_t>(sm.cnt[warp], v, d, lane, bits) | (d << 16);
+    }
+    __syncthreads();
+    // per bin: totals over the warps; the counters become each warp's offset inside the bin
+    uint32_t total = 0;
+    if (threadIdx.x < kNB) {
+#pragma unroll
+        for (int w = 0; w < kRadixWarps; ++w) {
+            const uint32_t c = sm.cnt[w][threadIdx.x];
+            sm.cnt[w][threadIdx.x] = (uint16_t)total;
+            total += c;
+        }
+    }
+    uint32_t n_tile = 0;
+    const uint32_t start = block_exscan_256(total, sm.scratch, &n_tile);
+    if (threadIdx.x < kNB) {
+        sm.binstart[threadIdx.x] = start;
+        if (total) sm.gdelta[threadIdx.x] = (long long)reserve(threadIdx.x, total) - (long long)start;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) {
+        if ((vmask >> j) & 1u) {
+            const uint32_t d = rk[j] >> 16;
+            const uint32_t pos = sm.binstart[d] + sm.cnt[warp][d] + (rk[j] & 0xffffu);
+#pragma unroll
+            for (int w = 0; w < KW; ++w) sm.sorted[pos * KW + w] = Hs[j].w[w];
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_tile; i += kRadixThreads) {
+        uint64_t h[KW];
+#pragma unroll
+        for (int w = 0; w < KW; ++w) h[w] = sm.sorted[i * KW + w];
+        const uint32_t d = digit(h[0]);
+        uint64_t* out = dst(d) + (uint64_t)(sm.gdelta[d] + (long long)i) * KW;
+        if constexpr (KW == 1) {
+            __stcg(out, h[0]);
+        } else {
+#pragma unroll
+            for (int w = 0; w < KW; w += 2) __stcg(reinterpret_cast<ulonglong2*>(out + w), make_ulonglong2(h[w], h[w + 1]));
+        }
+    }
+    tile_smem_init<KW>(sm);
+    __syncthreads();
+}
+
+// ---- S0: digit-1 histogram per segment of the read stream ------------------------------------------------------
+// Segments [seg0, seg0 + n_segs) of the batch; seghist / segtotal are indexed relative to seg0.
+template <int KW>
+__global__ void __launch_bounds__(kRadixThreads, RadixCfg<KW>::MINB)
+k_hist_reads(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, const uint64_t* __restrict__ packed,
+             const uint32_t* __restrict__ ends, uint64_t n_words, uint64_t n_bases, uint64_t seg0, uint32_t n_segs,
+             uint32_t* __restrict__ seghist, uint32_t* __restrict__ segtotal) {
+    __shared__ uint32_t cnt[kRadixWarps][kNB];
+    __shared__ uint32_t scratch[8];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t seg_words = 1ULL << rg.seg_log2;
+    for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < kRadixWarps * kNB; i += kRadixThreads) (&cnt[0][0])[i] = 0u;
+        __syncthreads();
+        const uint64_t w0 = (seg0 + seg) << rg.seg_log2;
+        const uint64_t w1 = w0 + seg_words < n_words ? w0 + seg_words : n_words;
+        for (uint64_t base = w0 + warp * 32; base < w1; base += kRadixWarps * 32) {
+            KmerLane<KW> kl;
+            kl.load(packed, ends, base, n_words, w1, n_bases, lane);
+#pragma unroll 4
+            for (int o = 31; o >= 0; --o) {
+                Key<KW> key;
+                const bool valid = kl.kmer_at(o, tv.L.k, tv.hp, key);
+                const Key<KW> H = hash_key<KW>(key, tv.hp);
+                (void)rank_in_warp<uint32_t>(cnt[warp], valid, digit1_of(rg, tv.lbg_mask, H.w[0]), lane, rg.d1);
+            }
+        }
+        __syncthreads();
+        uint32_t total = 0;
+        if (threadIdx.x < kNB) {
+#pragma unroll
+            for (int w = 0; w < kRadixWarps; ++w) total += cnt[w][threadIdx.x];
+            if (threadIdx.x < rg.nb1) seghist[(uint64_t)seg * rg.nb1 + threadIdx.x] = total;
+        }
+        uint32_t seg_sum = 0;
+        (void)block_exscan_256(total, scratch, &seg_sum);
+        if (threadIdx.x == 0) segtotal[seg] = seg_sum;
+    }
+}
+
+// ---- planner: chunks of at most cap keys, exact digit-1 offsets per chunk ----------------------------------------
+// segprefix: n_segs + 1 words of scratch.  Chunk c = the longest run of segments after chunk c-1 whose k-mers fit cap.
+__global__ void __launch_bounds__(kNB) k_plan_chunks(RadixCtl* __restrict__ ctl, const uint32_t* __restrict__ seghist,
+                                                     const uint32_t* __restrict__ segtotal, uint64_t* __restrict__ segprefix,
+                                                     uint32_t n_segs, uint32_t nb1, uint64_t cap, uint64_t seg_keys,
+                                                     unsigned long long* __restrict__ err_ctr) {
+    __shared__ uint32_t scratch[8];
+    __shared__ uint32_t n_chunks_s;
+    // inclusive prefix of the segment totals: segprefix[s] = keys of segments [0, s)
+    const uint32_t per = (n_segs + kNB - 1) / kNB;
+    const uint32_t i0 = threadIdx.x * per, i1 = i0 + per < n_segs ? i0 + per : n_segs;
+    uint64_t mine = 0;
+    for (uint32_t i = i0; i < i1; ++i) mine += segtotal[i];
+    uint64_t run = block_exscan_256_u64(mine, scratch, nullptr);
+    for (uint32_t i = i0; i < i1; ++i) { segprefix[i] = run; run += segtotal[i]; }
+    if (i1 == n_segs && i0 < n_segs) segprefix[n_segs] = run;
+    if (n_segs == 0 && threadIdx.x == 0) segprefix[0] = 0;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t c = 0, s0 = 0;
+        bool err = false;
+        // equal passes instead of full ones and a remainder: the fewest chunks that fit, then share the k-mers evenly
+        const uint64_t total = segprefix[n_segs];
+        const uint64_t n_min = total ? (total + cap - 1) / cap : 1;
+        const uint64_t even = (total + n_min - 1) / n_min + seg_keys;
+        if (even < cap) cap = even;
+        while (s0 < n_segs && !err) {
+            // largest s1 > s0 with segprefix[s1] - segprefix[s0] <= cap
+            const uint64_t base = segprefix[s0];
+            uint32_t lo = s0, hi = n_segs + 1;           // invariant: prefix[lo] - base <= cap, prefix[hi] - base > cap (virtually)
+            while (hi - lo > 1) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (segprefix[mid] - base <= cap) lo = mid; else hi = mid;
+            }
+            if (lo == s0) { err = true; break; }         // one segment alone exceeds cap
+            if (c < kMaxChunks) { ctl->chunk[c].seg_begin = s0; ctl->chunk[c].seg_end = lo; ctl->chunk[c].n_keys = segprefix[lo] - base; }
+            ++c;
+            s0 = lo;
+        }
+        if (c > kMaxChunks) err = true;
+        if (err) { ctl->plan_error = 1u; c = 0; atomicOr(err_ctr, (unsigned long long)ERR_PLAN); }   // nothing is processed; reported at the next sync
+        ctl->n_chunks = c;
+        n_chunks_s = c;
+    }
+    __syncthreads();
+    const uint32_t nc = n_chunks_s;
+    for (uint32_t c = 0; c < nc; ++c) {
+        const uint64_t s0 = ctl->chunk[c].seg_begin, s1 = ctl->chunk[c].seg_end;
+        uint64_t sum = 0;
+        if (threadIdx.x < nb1) {
+#pragma unroll 8
+            for (uint64_t s = s0; s < s1; ++s) sum += seghist[s * nb1 + threadIdx.x];
+        }
+        uint64_t tot = 0;
+        const uint64_t pre = block_exscan_256_u64(sum, scratch, &tot);
+        ctl->chunk[c].coff[threadIdx.x] = pre;
+        if (threadIdx.x == kNB - 1) ctl->chunk[c].coff[kNB] = tot;
+    }
+}
+
+// per chunk, single GPU: arm the S1 cursors; A's coarse offsets are the chunk's own
+__global__ void __launch_bounds__(kNB) k_chunk_begin(RadixCtl* __restrict__ ctl, uint32_t c) {
+    const bool active = c < ctl->n_chunks;
+    const uint64_t off = active ? ctl->chunk[c].coff[threadIdx.x] : 0ULL;
+    ctl->cursor1[threadIdx.x] = off;
+    ctl->cur_coff[threadIdx.x] = off;
+    if (threadIdx.x == 0) {
+        ctl->cur_coff[kNB] = active ? ctl->chunk[c].coff[kNB] : 0ULL;
+        ctl->chunk_active = active ? 1u : 0u;
+        ctl->n_insert = active ? ctl->chunk[c].n_keys : 0ULL;
+        ctl->ticket[0] = ctl->ticket[1] = ctl->ticket[2] = 0ULL;
+    }
+}
+
+// per round, multi-GPU: this rank's digit-1 counts of round c (zeros once its own chunks are used up), the payload of
+// the all-gather that precedes k_route_offsets
+__global__ void __launch_bounds__(kNB) k_round_hist(const RadixCtl* __restrict__ ctl, uint32_t c, uint32_t nb1, uint32_t* __restrict__ out) {
+    if (threadIdx.x >= nb1) return;
+    uint32_t v = 0;
+    if (c < ctl->n_chunks) v = (uint32_t)(ctl->chunk[c].coff[threadIdx.x + 1] - ctl->chunk[c].coff[threadIdx.x]);
+    out[threadIdx.x] = v;
+}
+
+// per chunk, multi-GPU: hist_all[s * nb1 + d] = k-mers rank s has for digit-1 bin d in this round (all-gathered).
+// Bin d = (owner o, local coarse bin lc).  Owner o's receive buffer is laid out bin-major, source-minor, so every
+// local coarse bin is one contiguous range there, exactly like buffer A of the single-GPU path:
+//   position of (source s, bin d) in o's buffer = sum_{lc' < lc} sum_s' hist[s'][o, lc'] + sum_{s' < s} hist[s'][d]
+// Every rank evaluates the capacity check for every owner on the same data, so all ranks skip the round together.
+__global__ void __launch_bounds__(kNB) k_route_offsets(RadixCtl* __restrict__ ctl, uint32_t c, const uint32_t* __restrict__ hist_all,
+                                                       uint32_t n_ranks, uint32_t my_rank, uint32_t nb1, uint32_t nbl, uint64_t cap_recv,
+                                                       unsigned long long* __restrict__ err_ctr) {
+    __shared__ uint32_t scratch[8];
+    __shared__ uint64_t ex_s[kNB + 1];
+    __shared__ uint32_t over_s;
+    if (threadIdx.x == 0) over_s = 0u;
+    uint64_t col = 0, before = 0;
+    if (threadIdx.x < nb1)
+        for (uint32_t s = 0; s < n_ranks; ++s) {
+            const uint32_t h = hist_all[(uint64_t)s * nb1 + threadIdx.x];
+            if (s < my_rank) before += h;
+            col += h;
+        }
+    uint64_t tot = 0;
+    const uint64_t ex = block_exscan_256_u64(col, scratch, &tot);
+    ex_s[threadIdx.x] = ex;
+    if (threadIdx.x == kNB - 1) ex_s[kNB] = tot;
+    __syncthreads();
+    if (threadIdx.x < nb1 && (threadIdx.x % nbl) == 0) {       // first bin of an owner: what that owner receives
+        const uint32_t last = threadIdx.x + nbl;
+        if (ex_s[last] - ex_s[threadIdx.x] > cap_recv) over_s = 1u;
+    }
+    __syncthreads();
+    const bool over = over_s != 0u;
+    const bool mine_active = c < ctl->n_chunks;
+    if (threadIdx.x < nb1) {
+        const uint32_t owner_first = threadIdx.x - (threadIdx.x % nbl);
+        ctl->cursor1[threadIdx.x] = ex - ex_s[owner_first] + before;
+    }
+    if (threadIdx.x <= nbl) {                                   // my own receive layout
+        const uint32_t first = my_rank * nbl;
+        ctl->cur_coff[threadIdx.x] = over ? 0ULL : ex_s[first + threadIdx.x] - ex_s[first];
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t first = my_rank * nbl;
+        ctl->chunk_active = (!over && mine_active) ? 1u : 0u;   // gates S1 (sending)
+        ctl->n_insert = over ? 0ULL : ex_s[first + nbl] - ex_s[first];
+        if (over) { ctl->recv_overflow = 1u; atomicOr(err_ctr, (unsigned long long)ERR_SEND_OVERFLOW); }
+        ctl->ticket[0] = ctl->ticket[1] = ctl->ticket[2] = 0ULL;
+    }
+}
+
+// ---- S1: extract + hash + tile sort by digit 1 -> buffer A --------------------------------------------------------
+// dst_of_owner == nullptr: everything goes to A.  Otherwise (multi-GPU) the run of bin d goes to
+// dst_of_owner[owner of d], the owner's receive buffer (peer-mapped over NVLink for the other ranks): the routing
+// kernel IS the exchange.
+template <int KW>
+__global__ void __launch_bounds__(kRadixThreads, RadixCfg<KW>::MINB)
+k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, RadixCtl* __restrict__ ctl, uint32_t c,
+             const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ends, uint64_t n_words, uint64_t n_bases,
+             uint64_t seg0, uint64_t* __restrict__ A, uint64_t* const* __restrict__ dst_of_owner) {
+    constexpr int OPT = RadixCfg<KW>::OPT;
+    __shared__ TileSmem<KW> sm;
+    __shared__ uint64_t* owner_base[kNB];
+    if (!ctl->chunk_active) return;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    tile_smem_init<KW>(sm);
+    if (threadIdx.x < kNB) owner_base[threadIdx.x] = dst_of_owner ? dst_of_owner[threadIdx.x >> rg.owner_shift] : A;
+    __syncthreads();
+    const uint64_t seg_begin = ctl->chunk[c].seg_begin, seg_end = ctl->chunk[c].seg_end;
+    const uint64_t seg_words = 1ULL << rg.seg_log2;
+    const uint64_t lbg_mask = tv.lbg_mask;
+    auto digit = [&](uint64_t h0) { return digit1_of(rg, lbg_mask, h0); };
+    auto reserve = [&](uint32_t bin, uint32_t n) { return (uint64_t)atomicAdd(&ctl->cursor1[bin], (unsigned long long)n); };
+    auto dst = [&](uint32_t d) { return owner_base[d]; };
+    for (uint64_t seg = seg_begin + blockIdx.x; seg < seg_end; seg += gridDim.x) {
+        const uint64_t w0 = (seg0 + seg) << rg.seg_log2;
+        const uint64_t w1 = w0 + seg_words < n_words ? w0 + seg_words : n_words;
+        for (uint64_t round = w0; round < w1; round += kRadixWarps * 32) {
+            KmerLane<KW> kl;
+            kl.load(packed, ends, round + warp * 32, n_words, w1, n_bases, lane);
+#pragma unroll 1
+            for (int o0 = 31; o0 >= 0; o0 -= OPT) {
+                Key<KW> Hs[OPT];
+                uint32_t vmask = 0;
+#pragma unroll
+                for (int j = 0; j < OPT; ++j) {
+                    Key<KW> key;
+                    if (kl.kmer_at(o0 - j, tv.L.k, tv.hp, key)) vmask |= 1u << j;
+                    Hs[j] = hash_key<KW>(key, tv.hp);
+                }
+                tile_partition<KW>(sm, Hs, vmask, rg.d1, digit, reserve, dst);
+            }
+        }
+    }
+}
+
+// ---- per group of A: work items, histogram reset -------------------------------------------------------------------
+// Group g = keys [g*capb, (g+1)*capb) of A.  Items are tiles that do not cross a coarse-bin boundary, so all keys
+// of a tile share digit 1 and are told apart by digit 2 alone.
+template <int KW>
+__global__ void __launch_bounds__(kNB) k_plan_group(RadixCtl* __restrict__ ctl, uint32_t g, uint64_t capb, uint32_t nbl,
+                                                    uint32_t* __restrict__ fhist, uint32_t n_fine) {
+    constexpr uint32_t TILE = RadixCfg<KW>::TILE;
+    __shared__ uint32_t scratch[8];
+    GroupDesc& G = ctl->group;
+    const uint64_t n_keys = ctl->cur_coff[nbl];
+    const uint64_t a0 = (uint64_t)g * capb, a1 = a0 + capb < n_keys ? a0 + capb : n_keys;
+    const bool active = a0 < n_keys;
+    uint32_t tiles = 0;
+    if (active && threadIdx.x < nbl) {
+        const uint64_t lo0 = ctl->cur_coff[threadIdx.x], hi0 = ctl->cur_coff[threadIdx.x + 1];
+        const uint64_t lo = lo0 > a0 ? lo0 : a0, hi = hi0 < a1 ? hi0 : a1;
+        if (hi > lo) tiles = (uint32_t)((hi - lo + TILE - 1) / TILE);
+    }
+    uint32_t n_items = 0;
+    const uint32_t pre = block_exscan_256(tiles, scratch, &n_items);
+    G.itemstart[threadIdx.x] = pre;
+    if (threadIdx.x == kNB - 1) G.itemstart[kNB] = pre + tiles;
+    if (threadIdx.x == 0) {
+        G.a0 = a0; G.a1 = active ? a1 : a0; G.n_items = active ? n_items : 0u; G.active = active ? 1u : 0u;
+        ctl->n_insert = active ? a1 - a0 : 0ULL;
+        ctl->ticket[0] = ctl->ticket[1] = ctl->ticket[2] = 0ULL;
+    }
+    if (active) for (uint32_t i = threadIdx.x; i < n_fine; i += kNB) fhist[i] = 0u;
+}
+
+// Item -> (local coarse bin, key range).  The group's tables are copied to shared memory once; thread 0 holds the
+// ticket of the NEXT item (its atomicAdd round trip overlaps the current tile), searches and broadcasts.
+struct ItemRange { uint32_t bin; uint32_t pad; uint64_t lo, hi; };
+
+template <int KW>
+struct ItemFeed {
+    uint64_t coff[kNB + 1];
+    uint32_t itemstart[kNB + 1];
+    uint64_t a0, a1;
+    uint32_t n_items;
+    ItemRange cur;
+};
+
+template <int KW>
+__device__ __forceinline__ void item_feed_init(ItemFeed<KW>& f, const RadixCtl* __restrict__ ctl, uint32_t nbl) {
+    for (uint32_t i = threadIdx.x; i <= kNB; i += blockDim.x) {
+        f.coff[i] = i <= nbl ? ctl->cur_coff[i] : 0ULL;
+        f.itemstart[i] = ctl->group.itemstart[i];
+    }
+    if (threadIdx.x == 0) { f.a0 = ctl->group.a0; f.a1 = ctl->group.a1; f.n_items = ctl->group.n_items; }
+    __syncthreads();
+}
+
+// `ahead` lives in thread 0's registers: the ticket already taken for the next call.
+template <int KW>
+__device__ __forceinline__ bool next_item(ItemFeed<KW>& f, RadixCtl* __restrict__ ctl, int ticket_idx, uint32_t nbl,
+                                          unsigned long long& ahead) {
+    constexpr uint32_t TILE = RadixCfg<KW>::TILE;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long item = ahead;
+        if (item >= f.n_items) {
+            f.cur.bin = 0xffffffffu;
+        } else {
+            ahead = atomicAdd(&ctl->ticket[ticket_idx], 1ULL);       // consumed by the next call
+            uint32_t lo_b = 0, hi_b = nbl;     // largest b with itemstart[b] <= item (empty bins share their successor's start)
+            while (hi_b - lo_b > 1) {
+                const uint32_t mid = (lo_b + hi_b) >> 1;
+                if (f.itemstart[mid] <= item) lo_b = mid; else hi_b = mid;
+            }
+            const uint64_t lo0 = f.coff[lo_b], hi0 = f.coff[lo_b + 1];
+            const uint64_t lo = (lo0 > f.a0 ? lo0 : f.a0) + (uint64_t)(item - f.itemstart[lo_b]) * TILE;
+            const uint64_t hi_lim = hi0 < f.a1 ? hi0 : f.a1;
+            f.cur.bin = lo_b; f.cur.lo = lo; f.cur.hi = lo + TILE < hi_lim ? lo + TILE : hi_lim;
+        }
+    }
+    __syncthreads();
+    return f.cur.bin != 0xffffffffu;
+}
+
+// ---- S2a: digit-2 histogram of the group ---------------------------------------------------------------------------
+template <int KW>
+__global__ void __launch_bounds__(kRadixThreads, 2)
+k_hist_keys(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, RadixCtl* __restrict__ ctl,
+            const uint64_t* __restrict__ A, uint32_t* __restrict__ fhist) {
+    constexpr int OPT = RadixCfg<KW>::OPT;
+    __shared__ uint16_t cnt[kRadixWarps][kNB];
+    __shared__ ItemFeed<KW> feed;
+    if (!ctl->group.active) return;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < kRadixWarps * kNB / 2; i += kRadixThreads) reinterpret_cast<uint32_t*>(&cnt[0][0])[i] = 0u;
+    item_feed_init<KW>(feed, ctl, rg.nbl);
+    unsigned long long ahead = threadIdx.x == 0 ? atomicAdd(&ctl->ticket[0], 1ULL) : 0ULL;
+    while (next_item<KW>(feed, ctl, 0, rg.nbl, ahead)) {
+        const uint64_t lo = feed.cur.lo, hi = feed.cur.hi;
+        const uint32_t bin = feed.cur.bin;
+        uint64_t h0[OPT];
+#pragma unroll
+        for (int j = 0; j < OPT; ++j) {          // all loads first: the ranking below is a dependent chain per key
+            const uint64_t i = lo + (uint64_t)j * kRadixThreads + threadIdx.x;
+            h0[j] = i < hi ? __ldcg(A + i * KW) : 0ULL;
+        }
+#pragma unroll
+        for (int j = 0; j < OPT; ++j) {
+            const uint64_t i = lo + (uint64_t)j * kRadixThreads + threadIdx.x;
+            (void)rank_in_warp<uint16_t>(cnt[warp], i < hi, digit2_of(rg, tv.lbg_mask, h0[j]), lane, rg.d2);
+        }
+        __syncthreads();
+        if (threadIdx.x < rg.nb2) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < kRadixWarps; ++w) { total += cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = 0; }
+            if (total) atomicAdd(fhist + bin * rg.nb2 + threadIdx.x, total);
+        }
+    }
+}
+
+// fine-bin offsets inside B: exclusive scan of fhist (n_fine <= 65536 entries, one block of 1024 threads)
+__global__ void __launch_bounds__(1024) k_scan_fine(const RadixCtl* __restrict__ ctl, const uint32_t* __restrict__ fhist,
+                                                    unsigned long long* __restrict__ fcur, uint32_t n_fine) {
+    __shared__ unsigned long long wsum[32];
+    if (!ctl->group.active) return;
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t per = (n_fine + 1023) / 1024;
+    const uint32_t i0 = threadIdx.x * per;
+    unsigned long long sum = 0;
+    for (uint32_t i = i0; i < i0 + per && i < n_fine; ++i) sum += fhist[i];
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(full, inc, d);
+        if (lane >= (unsigned)d) inc += y;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned long long pre = 0;
+    for (unsigned w = 0; w < warp; ++w) pre += wsum[w];
+    unsigned long long run = pre + inc - sum;
+    for (uint32_t i = i0; i < i0 + per && i < n_fine; ++i) { fcur[i] = run; run += fhist[i]; }
+}
+
+// ---- S2b: tile sort by digit 2: A -> B -----------------------------------------------------------------------------
+template <int KW>
+__global__ void __launch_bounds__(kRadixThreads, RadixCfg<KW>::MINB)
+k_part_keys(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, RadixCtl* __restrict__ ctl,
+            const uint64_t* __restrict__ A, unsigned long long* __restrict__ fcur, uint64_t* __restrict__ B) {
+    constexpr int OPT = RadixCfg<KW>::OPT;
+    __shared__ TileSmem<KW> sm;
+    __shared__ ItemFeed<KW> feed;
+    if (!ctl->group.active) return;
+    tile_smem_init<KW>(sm);
+    item_feed_init<KW>(feed, ctl, rg.nbl);
+    const uint64_t lbg_mask = tv.lbg_mask;
+    auto digit = [&](uint64_t h0) { return digit2_of(rg, lbg_mask, h0); };
+    auto dst = [&](uint32_t) { return B; };
+    unsigned long long ahead = threadIdx.x == 0 ? atomicAdd(&ctl->ticket[1], 1ULL) : 0ULL;
+    while (next_item<KW>(feed, ctl, 1, rg.nbl, ahead)) {
+        const uint64_t lo = feed.cur.lo, hi = feed.cur.hi;
+        unsigned long long* cur = fcur + (uint64_t)feed.cur.bin * rg.nb2;
+        Key<KW> Hs[OPT];
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int j = 0; j < OPT; ++j) {
+            const uint64_t i = lo + (uint64_t)j * kRadixThreads + threadIdx.x;
+            const bool v = i < hi;
+            if (v) vmask |= 1u << j;
+#pragma unroll
+            for (int w = 0; w < KW; ++w) Hs[j].w[w] = v ? __ldcs(A + i * KW + w) : 0ULL;
+        }
+        auto reserve = [&](uint32_t bin, uint32_t n) { return (uint64_t)atomicAdd(cur + bin, (unsigned long long)n); };
+        tile_partition<KW>(sm, Hs, vmask, rg.d2, digit, reserve, dst);
+    }
+}
+
+// ---- phase B: insert keys in region order ---------------------------------------------------------------------------
+// Work item = one slice of consecutive keys of `src` (ticket order = table-region order).
+//
+// What was measured about this kernel (profiles/r02_k0r_modes.md, profiles/r02_pipeline_c2_scaled_summary.txt):
+//  * all blocks sweeping 8 MiB regions, sector loads alone run at 150 G/s, a load followed by a fire-and-forget atomic
+//    at 64-73 G/s, a load followed by an atomic whose result the thread needs (the insert's claim) at 43-49 G/s;
+//  * merging equal keys of a warp with __match_any_sync on every step kept the XU pipe 93 % busy (MATCH.ANY.U64);
+//  * issuing several probes and claims per thread before looking at any result made it SLOWER (439 vs 257 ms on
+//    config 2): at load factors near 0.5 almost every warp has a lane whose home bucket is full, and that lane's
+//    re-probe chain then runs with the other 31 lanes idle.
+// So: one key per thread and step, all keys of the slice loaded up front, and the duplicate handling only where it
+// pays.  A slice in which two neighbouring keys are equal (with a k-mer that makes up a few per cent of the input this
+// is all but certain) is "skewed": equal keys of a warp are merged with __match_any_sync and the warp's keys go
+// through a shared-memory combiner: slot word = index of the first key that claimed it (+1) in the low 16 bits | 48
+// fingerprint bits of hash word 0; a later key with the same fingerprint compares itself with the claimer's key in
+// `src` and, if equal, just adds to the slot's count.  The slots are flushed once per slice, so a k-mer that dominates
+// the input costs one table update per slice instead of one per occurrence.  All other slices take every key straight
+// to insert_hashed().
+#ifndef TSX_INSERT_MINB
+#define TSX_INSERT_MINB 6
+#endif
+template <int KW, int W, bool WARP_AGG>
+__global__ void __launch_bounds__(kBlockThreads, TSX_INSERT_MINB)
+k_insert_keys(const __grid_constant__ TableView tv, RadixCtl* __restrict__ ctl, const uint64_t* __restrict__ src) {
+    constexpr int R = KW == 1 ? 4 : (KW == 2 ? 2 : 1);          // keys per thread per slice
+    constexpr uint32_t SLICE = kBlockThreads * R;
+    const unsigned full = 0xffffffffu;
+    __shared__ unsigned long long item_s;
+    __shared__ unsigned long long comb_key[kCombSlots];
+    __shared__ unsigned int comb_cnt[kCombSlots];
+    __shared__ unsigned int comb_used;
+    const unsigned long long n = ctl->n_insert;
+    if (n == 0) return;
+    LocalStats st;
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t i = threadIdx.x; i < kCombSlots; i += kBlockThreads) { comb_key[i] = 0ULL; comb_cnt[i] = 0u; }
+    if (threadIdx.x == 0) comb_used = 0u;
+    const unsigned long long n_items = (n + SLICE - 1) / SLICE;
+    // thread 0 keeps the ticket of the next slice in flight while the block works on the current one
+    unsigned long long ahead = threadIdx.x == 0 ? atomicAdd(&ctl->ticket[2], 1ULL) : 0ULL;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            item_s = ahead;
+            if (ahead < n_items) ahead = atomicAdd(&ctl->ticket[2], 1ULL);
+        }
+        __syncthreads();
+        const unsigned long long item = item_s;
+        if (item >= n_items) break;
+        const uint64_t lo = item * SLICE;
+        const uint64_t hi = lo + SLICE < n ? lo + SLICE : n;
+        Key<KW> Hs[R];
+        bool dup = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint64_t i = lo + (uint64_t)r * kBlockThreads + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) Hs[r].w[j] = i < hi ? __ldcs(src + i * KW + j) : 0ULL;
+        }
+        if (WARP_AGG) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint64_t i = lo + (uint64_t)r * kBlockThreads + threadIdx.x;
+                const uint64_t nb = __shfl_down_sync(full, Hs[r].w[0], 1);
+                dup |= (lane < 31u) && (i + 1 < hi) && (nb == Hs[r].w[0]);
+            }
+        }
+        const bool skew = WARP_AGG && __syncthreads_or(dup ? 1 : 0);
+        if (!skew) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint64_t i = lo + (uint64_t)r * kBlockThreads + threadIdx.x;
+                if (i < hi) insert_hashed<KW, W>(tv, Hs[r], 1, st);
+            }
+            continue;
+        }
+        // ---- skewed slice ----
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint64_t i = lo + (uint64_t)r * kBlockThreads + threadIdx.x;
+            const bool valid = i < hi;
+            const Key<KW> H = Hs[r];
+            uint64_t cnt = 1;
+            bool lead = valid;
+            unsigned dups = 0;
+            const unsigned vm = __ballot_sync(full, valid);
+            if (valid) {
+                unsigned peers = __match_any_sync(vm, H.w[0]);
+#pragma unroll
+                for (int j = 1; j < KW; ++j) peers &= __match_any_sync(vm, H.w[j]);
+                cnt = (uint64_t)__popc(peers);
+                lead = (unsigned)(__ffs(peers) - 1) == lane;
+            }
+            dups = __popc(vm) - __popc(__ballot_sync(full, lead));
+            if (!lead) continue;
+            if (dups >= 4) {
+                // combine across the block before touching the table
+                const uint32_t slot = (uint32_t)(H.w[0] ^ (H.w[0] >> 40)) & (kCombSlots - 1);
+                const unsigned long long tagged = (H.w[0] & ~0xffffULL) | (unsigned long long)((i - lo) + 1);
+                const unsigned long long oldk = atomicCAS(&comb_key[slot], 0ULL, tagged);
+                bool absorbed = (oldk == 0ULL);
+                if (!absorbed && ((oldk ^ tagged) & ~0xffffULL) == 0ULL) {
+                    const uint64_t other = lo + (oldk & 0xffffULL) - 1;
+                    absorbed = true;
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) absorbed &= (__ldcg(src + other * KW + j) == H.w[j]);
+                }
+                if (absorbed) {
+                    atomicAdd(&comb_cnt[slot], (unsigned int)cnt);
+                    comb_used = 1u;
+                    continue;
+                }
+            }
+            insert_hashed<KW, W>(tv, H, cnt, st);
+        }
+        __syncthreads();
+        if (comb_used) {
+            for (uint32_t s = threadIdx.x; s < kCombSlots; s += kBlockThreads) {
+                const unsigned long long tagged = comb_key[s];
+                if (tagged == 0ULL) continue;
+                const uint64_t idx = lo + (tagged & 0xffffULL) - 1;
+                Key<KW> H;
+#pragma unroll
+                for (int j = 0; j < KW; ++j) H.w[j] = __ldcg(src + idx * KW + j);
+                insert_hashed<KW, W>(tv, H, (uint64_t)comb_cnt[s], st);
+                comb_key[s] = 0ULL; comb_cnt[s] = 0u;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) comb_used = 0u;
+        }
+    }
+    flush_stats(tv, st);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace tsx

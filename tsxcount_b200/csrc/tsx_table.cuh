@@ -42,6 +42,7 @@ enum : uint32_t {
     ERR_SATURATED = 2u,
     ERR_SEND_OVERFLOW = 4u,
     ERR_WRONG_SHARD = 8u,
+    ERR_PLAN = 16u,
 };
 
 enum : int { CTR_DISTINCT = 0, CTR_OVERFLOW = 1, CTR_ADDED = 2, CTR_MAXPROBE = 3, CTR_ERRORS = 4, CTR_COUNT = 8 };
@@ -151,10 +152,10 @@ inline TableView make_view(const Layout& L, uint64_t* words, unsigned long long*
 // ---- memory primitives --------------------------------------------------------------------------
 // Table words are written by atomics from every SM: reads must come from L2 (ld.global.cg), never a
 // stale L1 line.
+// One 256-bit load (sm_100: LDG.E.256) instead of two 128-bit ones: a scattered warp-wide load costs the LSU one
+// wavefront per lane PER INSTRUCTION, and phase B is bound by exactly that (profiles/r02_pipeline_c2_scaled_summary.txt).
 __device__ __forceinline__ void load_bucket(const uint64_t* b, uint64_t (&w)[4]) {
-    const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(b));
-    const ulonglong2 c = __ldcg(reinterpret_cast<const ulonglong2*>(b) + 1);
-    w[0] = a.x; w[1] = a.y; w[2] = c.x; w[3] = c.y;
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(b) : "memory");
 }
 
 __device__ __forceinline__ void prefetch_bucket_l2(const uint64_t* b) {
@@ -300,6 +301,7 @@ __device__ __forceinline__ void insert_hashed(const TableView& tv, const Key<KW>
     constexpr int SPB = 4 / W;
     const Stored<KW, W> s = make_stored<KW, W>(tv, H);
     if (!s.owned) { st.errors |= ERR_WRONG_SHARD; return; }
+    if (st.errors & ERR_TABLE_FULL) return;        // this thread already hit the reprobe limit: the run is lost (exit 42)
     st.added += count;
     const uint64_t vmask = low_mask(tv.L.V);
     for (uint32_t i = 1; i <= tv.L.max_probe; ++i) {
@@ -352,8 +354,11 @@ __device__ __forceinline__ void insert_hashed(const TableView& tv, const Key<KW>
                 bool same = true;
                 if (W == 4) {
                     if (h & tv.f_busy) { retry_bucket = true; break; }  // key words not published yet
-                    // body words in w[] may predate the publication: reload them
+                    // body words in w[] may predate the publication: reload them.  The fence is the acquire side of
+                    // the publication (body stores, fence, BUSY cleared): without it these loads could be satisfied
+                    // before the head load that showed BUSY == 0 and return the stale zero body.
                     if (tv.L.Q > tv.L.Qh) {
+                        __threadfence();
 #pragma unroll
                         for (int j = 0; j < W - 1; ++j) same &= (__ldcg(ep + j) == s.body[j]);
                     }

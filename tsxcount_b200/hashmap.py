@@ -59,6 +59,10 @@ class TSXHashMapCUDA:
     def sync(self):
         _lib.check(self._lib.tsxc_sync(self._h), self._h)
 
+    def trim(self):
+        """Release the insert pipeline's key buffers (re-sized by the next batch)."""
+        _lib.check(self._lib.tsxc_trim(self._h), self._h)
+
     def mark(self, idx):
         _lib.check(self._lib.tsxc_mark(self._h, idx), self._h)
 
@@ -121,29 +125,34 @@ class TSXHashMapCUDA:
         _lib.check(self._lib.tsxc_add_hashes_device(self._h, d_hashes, n), self._h)
 
     # -- multi-GPU routing (see include/tsxcount_cuda.h "multi-GPU routing") ------------------------
-    def routeLayout(self, max_chunk_words=0, kmers_per_position=1.0):
-        lay = _lib.TsxcRouteLayout()
-        q16 = max(1, min(65536, int(round(kmers_per_position * 65536))))
-        _lib.check(self._lib.tsxc_route_layout(self._h, max_chunk_words, q16, C.byref(lay)), self._h)
-        return lay
+    def routeInfo(self):
+        info = _lib.TsxcRouteInfo()
+        _lib.check(self._lib.tsxc_route_info(self._h, C.byref(info)), self._h)
+        return info
 
-    def routePrepare(self, d_offsets, n_reads, n_bases):
-        _lib.check(self._lib.tsxc_route_prepare(self._h, d_offsets, n_reads, n_bases), self._h)
+    def routeRecvBuffer(self, cap_keys=0):
+        """-> (device pointer, capacity in k-mers) of this shard's receive buffer"""
+        p, cap = C.c_void_p(), C.c_uint64(0)
+        _lib.check(self._lib.tsxc_route_recv_buffer(self._h, cap_keys, C.byref(p), C.byref(cap)), self._h)
+        return p.value, cap.value
 
-    def routeChunk(self, lay, d_packed, n_bases, w_begin, w_end, d_bins, d_cursors, d_spill, d_spill_n):
-        _lib.check(self._lib.tsxc_route_chunk(self._h, C.byref(lay), d_packed, n_bases, w_begin, w_end, d_bins,
-                                              d_cursors, d_spill, d_spill_n), self._h)
+    def routeSetPeers(self, peer_ptrs, recv_cap_keys):
+        arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        _lib.check(self._lib.tsxc_route_set_peers(self._h, arr, recv_cap_keys), self._h)
 
-    def routeOverflowed(self):
-        flag = C.c_int(0)
-        _lib.check(self._lib.tsxc_route_overflowed(self._h, C.byref(flag)), self._h)
-        return bool(flag.value)
+    def routeBegin(self, d_packed, d_offsets, n_reads, n_bases):
+        rounds = C.c_uint32(0)
+        _lib.check(self._lib.tsxc_route_begin(self._h, d_packed, d_offsets, n_reads, n_bases, C.byref(rounds)), self._h)
+        return rounds.value
 
-    def insertRouted(self, lay, d_bins, d_cursors, n_sources):
-        _lib.check(self._lib.tsxc_insert_routed(self._h, C.byref(lay), d_bins, d_cursors, n_sources), self._h)
+    def routeHist(self, rnd, d_hist):
+        _lib.check(self._lib.tsxc_route_hist(self._h, rnd, d_hist), self._h)
 
-    def addHashCountsDevice(self, d_records, n):
-        _lib.check(self._lib.tsxc_add_hash_counts_device(self._h, d_records, n), self._h)
+    def routeSend(self, rnd, d_hist_all):
+        _lib.check(self._lib.tsxc_route_send(self._h, rnd, d_hist_all), self._h)
+
+    def routeInsert(self):
+        _lib.check(self._lib.tsxc_route_insert(self._h), self._h)
 
     # -- query path -------------------------------------------------------------------------------
     def getKmerCount(self, kmer=None):

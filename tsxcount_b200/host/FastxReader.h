@@ -16,6 +16,8 @@
 // offsets array — the layout tsxc_pack_reads takes.  ~0.8 GB/s of FASTQ text per thread.
 #pragma once
 
+#include <cerrno>
+#include <cstring>
 #include <fcntl.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -171,10 +173,24 @@ private:
             m_end = got;
         }
     }
+    // 0 = clean end of file.  I/O errors and damaged / truncated gzip streams throw: a partial count with exit
+    // code 0 would look like a result.
     size_t readSome(char* dst, size_t n) {
-        if (m_gz) { const int r = gzread(m_gz, dst, (unsigned)n); return r > 0 ? (size_t)r : 0; }
-        const ssize_t r = ::read(m_fd, dst, n);
-        return r > 0 ? (size_t)r : 0;
+        if (m_gz) {
+            const int r = gzread(m_gz, dst, (unsigned)n);
+            if (r > 0) return (size_t)r;
+            int errnum = Z_OK;
+            const char* msg = gzerror(m_gz, &errnum);
+            if (r < 0 || (errnum != Z_OK && errnum != Z_STREAM_END))
+                throw std::runtime_error(std::string("FastxReader: gzip stream damaged or truncated: ") + (msg ? msg : "?"));
+            return 0;
+        }
+        for (;;) {
+            const ssize_t r = ::read(m_fd, dst, n);
+            if (r >= 0) return (size_t)r;
+            if (errno == EINTR) continue;
+            throw std::runtime_error(std::string("FastxReader: read failed: ") + std::strerror(errno));
+        }
     }
     // Positions the reader on the first record boundary at or after the current line (see the constructor).
     void syncToRecord() {
