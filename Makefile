@@ -31,7 +31,7 @@ $(INGEST): $(HOST)/tools/ingest_check.cpp $(HOST)/FastxReader.h include/tsxcount
 
 $(CLI): $(wildcard $(HOST)/*.cpp) $(wildcard $(HOST)/*.h) include/tsxcount_cuda.h $(LIB)
 	@mkdir -p $(BINDIR)
-	$(HOSTCXX) -O2 -std=c++17 -Wall -pthread -Iinclude -o $@ $(wildcard $(HOST)/*.cpp) -L$(LIBDIR) -ltsxcuda -lz -Wl,-rpath,'$$ORIGIN/../lib'
+	$(HOSTCXX) -O2 -std=c++17 -Wall -pthread -Iinclude -I/usr/local/cuda/include -o $@ $(wildcard $(HOST)/*.cpp) -L$(LIBDIR) -ltsxcuda -lnccl -lz -Wl,-rpath,'$$ORIGIN/../lib'
 
 oracle:
 	$(MAKE) -C oracle all

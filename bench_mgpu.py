@@ -175,8 +175,8 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None, extra_work
         res = {"name": w["name"], "value": args.steps * n_kmers * world / T / 1e9, "ms_per_step": 1e3 * T / args.steps,
                "device_ms_per_step": 1e3 * T_dev / args.steps, "kmers_per_step": n_kmers * world, "distinct": total_distinct,
                "launches": launches, "clocks": clocks, "layout": layout, "rounds_per_step": sc.rounds // max(1, sc.batches),
-               "phase_ms_rank0": {"hist": st["hist_ms"] / args.steps, "route": st["part1_ms"] / args.steps,
-                                  "sort": st["part2_ms"] / args.steps, "insert": st["insert_ms"] / args.steps},
+               # of the LAST timed step (tsxc_clear resets the accounting): CUDA events around each phase's launches
+               "phase_ms_rank0": {"hist": st["hist_ms"], "route": st["part1_ms"], "sort": st["part2_ms"], "insert": st["insert_ms"]},
                "n_kmers_rank": n_kmers, "read_len": read_len, "k": k, "l_global": l_global,
                "recv_cap_keys": sc.recv_cap}
         # e2e: the rank's reads start in pinned host memory; H2D copy + routed counting + global distinct read-back
@@ -227,8 +227,8 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None, extra_work
         in_b = 0.25 * read_len / max(1, read_len - k + 1)
         import bench as _bench
         peak, peak_src = _bench.read_peaks()
-        step_s = main["ms_per_step"] * 1e-3
-        achieved = n_kmers * (2 * E + in_b) / step_s / 1e9                # per GPU: this rank's k-mers over the step time
+        route_ms = main["phase_ms_rank0"]["route"]
+        achieved = n_kmers * (2 * E + in_b) / (main["ms_per_step"] * 1e-3) / 1e9   # per GPU: this rank's k-mers over the step time
         sent = n_kmers * E * (world - 1) // world                         # bytes a rank stores into its peers per step
         line = {
             "metric": "k-mers counted/sec", "value": main["value"], "unit": "Gk-mer/s", "n_gpus": world, "steps": args.steps,
@@ -249,8 +249,8 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None, extra_work
                          "kernel": "k_part_reads (routing, peer stores) + k_part_keys + k_insert_keys (per GPU)",
                          "algorithmic_bytes_per_kmer": 2 * E + in_b, "phase_ms_rank0": main["phase_ms_rank0"]},
             "nvlink": {"sent_bytes_per_gpu_per_step": sent,
-                       "GB_s_per_gpu_per_direction_during_routing": (sent / (main["phase_ms_rank0"]["route"] * 1e-3) / 1e9)
-                       if main["phase_ms_rank0"]["route"] else None,
+                       "GB_s_per_gpu_per_direction_during_routing": (sent / (route_ms * 1e-3) / 1e9) if route_ms else None,
+                       "routing_share_of_step": route_ms / main["device_ms_per_step"] if route_ms else None,
                        "note": "payload the routing kernel stores into peer memory, over the routing kernel's own device time"},
             "parity": parity, "variants": extras,
             "cpu_baseline": None, "e2e": main.get("e2e"), "gpu_launches": main["launches"], "clocks": main["clocks"],

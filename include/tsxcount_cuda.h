@@ -134,7 +134,11 @@ int tsxc_mark_elapsed_ms(tsxc_table* t, int idx_from, int idx_to, float* ms_out)
 /* ---- insert path ------------------------------------------------------------------------- */
 /* createKMers + fromSequence + addKmer for a whole batch of reads — main.cpp:159-192,
  * testExecution.h:15-36, SequenceUtils.h:86-160, TSXHashMapPerf.h:56-205 / TSXHashMapCAS.h:268-508.
- * offsets[r]..offsets[r+1] are the bases of read r in the packed stream (offsets[0] == 0). */
+ * offsets[r]..offsets[r+1] are the bases of read r in the packed stream (offsets[0] == 0).
+ * The host variant copies the batch to the device at once (asynchronously from pinned memory).  For tables large
+ * enough to take the region-sorted pipeline the batches are appended to a device-side stream and counted when they
+ * fill an insert pass — or at tsxc_sync, or before any call that reads the table — so the caller is free to cut its
+ * input into batches of any size. */
 int tsxc_add_reads(tsxc_table* t, const uint64_t* packed, const uint64_t* offsets, uint64_t n_reads);
 int tsxc_add_reads_device(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint64_t n_reads,
                           uint64_t n_bases);
@@ -202,6 +206,9 @@ int tsxc_add_hashes_device(tsxc_table* t, const uint64_t* d_hashes, uint64_t n);
 /* ---- peer-memory plumbing for the multi-GPU exchange (one process per GPU) ------------------------ */
 /* The owner exports its receive buffer (CUDA IPC), the other ranks open it and pass the mapped pointers to
  * tsxc_route_set_peers.  All handles are 64 opaque bytes (cudaIpcMemHandle_t / cudaIpcEventHandle_t). */
+/* Within ONE process that drives several devices (the C++ CLI's --gpus=N) no IPC is needed: enable peer access from
+ * `device` to `peer` (cudaDeviceEnablePeerAccess) and pass the other shards' buffer pointers as they are. */
+int tsxc_enable_peer_access(int device, int peer);
 #define TSXC_IPC_HANDLE_BYTES 64
 int tsxc_ipc_export_mem(int device, void* dptr, unsigned char* handle_out);
 int tsxc_ipc_open_mem(int device, const unsigned char* handle, void** dptr_out);

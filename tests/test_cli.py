@@ -246,3 +246,44 @@ def test_feeder_rejects_truncated_gzip(tmp_path):
     bad.write_bytes(data[: len(data) // 2])
     p = subprocess.run([INGEST, str(bad)], capture_output=True, text=True)
     assert p.returncode != 0
+
+
+@pytest.mark.gpu
+def test_reference_tree_binding_drives_addkmer_and_getkmercount():
+    """The subclass of the reference's own TSXHashMap (host/ref_binding/TSXHashMapCUDA_ref.h), compiled against
+    the reference headers in the build container, driven through the base-class pointer with the reference's own
+    createKMers / fromSequence / UBigInt: counts come back exactly (oracle/ref_adapter_main.cpp)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_adapter_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_adapter_check was not built (reference tree absent at build time)")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "total errors0" in p.stdout
+
+
+def test_cli_new_options_are_listed_and_n_policy_is_explicit():
+    out = subprocess.run([CLI, "--help"], capture_output=True, text=True).stdout
+    for opt in ("--gpus=", "--n-policy=", "--dump=", "--readers="):
+        assert opt in out, opt
+    p = subprocess.run([CLI, "--input=x.fastq", "--mode=CUDA", "--n-policy=random"], capture_output=True, text=True)
+    assert p.returncode == 2 and "only 'skip' exists" in p.stderr
+
+
+@pytest.mark.gpu
+def test_cli_multi_gpu_count_check_dump(tmp_path):
+    """--gpus=N: one host process, the table hash-sharded over N GPUs, NCCL all-gather / barrier and peer stores
+    (host/MultiGpuCounter.h).  Small batches so that several super-batches and rounds happen."""
+    import tsxcount_b200 as tsx
+    n = tsx._lib.load().tsxc_device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    fastq = orc.golden_path("c1_bundled_k14.fastq", tmp_path)
+    golden = orc.golden_path("c1_bundled_k14.fastq.14.count", tmp_path)
+    dump = tmp_path / "out.count"
+    p = subprocess.run([CLI, f"--input={fastq}", "--mode=CUDA", "--gpus=2", "--batch-reads=40", "--check", f"--dump={dump}"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "GPUs=2" in p.stderr
+    assert "Added a total of 194697 different kmers" in p.stdout and "total errors0" in p.stdout
+    assert "queried (Xor) kmer count: 0" in p.stdout
+    assert sorted(open(dump).read().splitlines()) == sorted(open(golden).read().splitlines())

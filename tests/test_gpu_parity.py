@@ -370,6 +370,7 @@ def small_regions(monkeypatch, request):
     """Tables of 512 MiB and more take the pipeline; shrink the fine regions so that small tables do too
     (4 KiB regions: both radix digits; 64 KiB regions: digit 1 only)."""
     monkeypatch.setenv("TSXC_REGION_LOG2", request.param)
+    monkeypatch.setenv("TSXC_LOOKUP_SORT_MIN", "1000")      # batched lookups of these tests are sorted by region too
 
 
 PART_CASES = [c for c in CASES if c[0] in (
@@ -434,6 +435,47 @@ def test_pipeline_one_kmer_is_the_whole_input(tsx, small_regions):
         check_against_oracle(tsx, hm, oc)
         hm.addSequences(seqs[:50])                         # and the table stays usable afterwards
         assert hm.getKmerCount() == 24
+
+
+@pytest.mark.parametrize("k,l,region,acc_words", [(5, 9, "8", "1024"), (14, 20, "12", "2048"), (31, 20, "12", "1024"),
+                                                  (63, 20, "14", "4096")])
+def test_host_batches_are_accumulated_into_insert_passes(tsx, monkeypatch, k, l, region, acc_words):
+    """Many small tsxc_add_reads calls without a sync in between: the library appends them to a device-side stream
+    (word aligned; the padding bits between two batches must never yield a k-mer, not even for k smaller than the
+    padding) and counts a buffer when it is full, at a sync, or before anything reads the table."""
+    monkeypatch.setenv("TSXC_REGION_LOG2", region)
+    monkeypatch.setenv("TSXC_ACC_WORDS", acc_words)
+    rng = np.random.default_rng(k)
+    # k = 5: reads over {A, C} only (32 possible 5-mers fit the 512-slot table; the padding bits read as poly-A, a k-mer
+    # that really occurs here, so a leak would change its count)
+    alphabet = np.frombuffer(b"AC" if k < 8 else b"ACGT", dtype=np.uint8)
+    seqs = [bytes(rng.choice(alphabet, size=int(n))) for n in rng.integers(1, 300, size=3000)]
+    oc = orc.count_seqs(seqs, k)
+    keep = []
+    with tsx.TSXHashMapCUDA(l, 4, k, flags=tsx.TSXC_FLAG_EXACT_S) as hm:
+        for i in range(0, len(seqs), 37):                       # batches end at arbitrary bit positions of a word
+            ascii_, offsets = tsx.sequtils.concat_reads(seqs[i:i + 37])
+            packed, seg, _ = tsx.sequtils.pack_reads(ascii_, offsets)
+            keep.append(hm.addReads(packed, seg, sync=False))
+        # no explicit sync: the lookup / dump / distinct calls below must see every batch
+        check_against_oracle(tsx, hm, oc)
+        assert hm.stats()["main_kernel_launches"] >= 4
+
+
+def test_sorted_lookup_handles_absent_duplicate_and_out_of_range_queries(tsx, small_regions):
+    seqs = orc.gen_reads(seed=11, n_reads=3000, read_len=150, mode=3, genome_len=40_000, sub_rate_q16=328)
+    oc = orc.count_seqs(seqs, 31)
+    other = orc.count_seqs(orc.gen_reads(seed=12, n_reads=50, read_len=150, mode=0), 31)
+    with tsx.TSXHashMapCUDA(20, 0, 31) as hm:
+        hm.addSequences(seqs)
+        q = np.concatenate([oc.keys_kw(1), other.keys_kw(1), oc.keys_kw(1)[:500], np.full((3, 1), 2**63, dtype=np.uint64)])
+        want = np.concatenate([oc.counts, np.zeros(other.n_distinct, dtype=np.uint64), oc.counts[:500], np.zeros(3, dtype=np.uint64)])
+        perm = np.random.default_rng(0).permutation(len(q))
+        got = hm.getKmerCounts(q[perm])
+        assert np.array_equal(got, want[perm])
+        before = hm.stats()["kernel_launches"]
+        hm.getKmerCounts(q[:2000])
+        assert hm.stats()["kernel_launches"] - before >= 7      # hash, partition passes, probe
 
 
 def test_direct_flag_forces_single_kernel(tsx, small_regions):

@@ -210,3 +210,18 @@ def test_pack_reads_randomized_against_numpy_packer():
                     start = g
             bounds.append(int(kept_before[e]))
         assert seg.tolist() == bounds
+
+
+def test_reference_tree_binding_compiles_against_the_reference_headers():
+    """INTEGRATION.md §2 is code, not prose: tsxcount_b200/host/ref_binding/TSXHashMapCUDA_ref.h derives from the
+    reference's TSXHashMap (src/tsxcount/TSXHashMap.h:68) and overrides addKmer / getKmerCount; oracle/Makefile
+    compiles it against the reference's own headers where the tree is mounted (this container).  No GPU needed."""
+    import subprocess
+    if not os.path.exists("/root/reference/src/tsxcount/TSXHashMap.h"):
+        pytest.skip("reference tree not mounted")
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_adapter_check")
+    assert os.path.exists(exe)
+    out = subprocess.run([exe, "--no-gpu"], capture_output=True, text=True, check=True).stdout
+    assert "ref-adapter built" in out

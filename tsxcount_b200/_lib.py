@@ -110,6 +110,7 @@ PROTOTYPES = {
     "tsxc_device_alloc": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(_vp)]),
     "tsxc_device_free": (C.c_int, [C.c_int, _vp]),
     "tsxc_memcpy": (C.c_int, [C.c_int, _vp, _vp, C.c_uint64, C.c_int]),
+    "tsxc_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
     "tsxc_ipc_export_mem": (C.c_int, [C.c_int, _vp, _vp]),
     "tsxc_ipc_open_mem": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
     "tsxc_ipc_close_mem": (C.c_int, [C.c_int, _vp]),

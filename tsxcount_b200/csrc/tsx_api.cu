@@ -46,12 +46,24 @@ struct tsxc_table {
     unsigned long long* d_ctr = nullptr;
     Staging stage[2];
     int next_stage = 0;
+    // host batches of a large table are accumulated on the device (packed words + read-end bitmap) until they fill an
+    // insert pass: the pipeline's cost per pass does not depend on how the caller cut its input into batches
+    struct Accum {
+        uint64_t* d_packed = nullptr; uint32_t* d_ends = nullptr;
+        uint64_t fill_words = 0;
+        cudaEvent_t consumed = nullptr; bool busy = false;         // the pipeline may still be reading it
+    } acc[2];
+    int acc_cur = 0;
+    uint64_t acc_cap_words = 0;
+    cudaEvent_t acc_copied = nullptr;
     // device-variant scratch (ends bitmap for caller-resident reads)
     uint32_t* d_ends = nullptr; size_t cap_ends = 0;
     // k-mer / count staging for add_kmers / lookup / dump
     uint64_t* d_keys = nullptr; size_t cap_keys = 0;      // words
     uint64_t* d_counts = nullptr; size_t cap_counts = 0;  // entries
     unsigned long long* d_nout = nullptr;
+    char* d_text = nullptr; size_t cap_text = 0;            // dump lines formatted on the device
+    uint64_t* d_pairs[2] = {nullptr, nullptr}; size_t cap_pairs[2] = {0, 0};   // region-sorted lookups: (hash, index) records
     // region-sorted insert pipeline (tsx_radix.cuh): S0 histogram, S1/S2 radix partition, phase B insert
     RadixGeom rg{};
     bool radix_on = false;                                     // tables this large take the pipeline by default
@@ -361,13 +373,9 @@ int launch_count_reads_radix(tsxc_table* t, const uint64_t* d_packed, const uint
     return TSXC_OK;
 }
 
-int launch_count_reads(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint32_t* d_ends,
-                       uint64_t n_reads, uint64_t n_bases, cudaStream_t s) {
-    if (n_bases == 0 || n_reads == 0) return TSXC_OK;
-    const uint64_t n_words = (n_bases + 31) >> 5;
-    CU(cudaMemsetAsync(d_ends, 0, n_words * sizeof(uint32_t), s));
-    k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, d_ends);
-    t->n_launches++;
+// Counts the k-mers of a packed stream whose read-end bitmap is already in place.
+int launch_count_marked(tsxc_table* t, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words, uint64_t n_bases,
+                        cudaStream_t s) {
     // the pipeline pays off once every table region receives a few thousand k-mers per pass
     if (t->radix_on && !(t->L.flags & TSXC_FLAG_DIRECT) && n_words >= (uint64_t)t->rg.nbl * t->rg.nb2 * 4)
         return launch_count_reads_radix(t, d_packed, d_ends, n_words, n_bases, s);
@@ -383,6 +391,60 @@ int launch_count_reads(tsxc_table* t, const uint64_t* d_packed, const uint64_t* 
     t->n_launches++;
     if (timed) main_end(t, s, ev);
     CU(cudaGetLastError());
+    return TSXC_OK;
+}
+
+int launch_count_reads(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_offsets, uint32_t* d_ends,
+                       uint64_t n_reads, uint64_t n_bases, cudaStream_t s) {
+    if (n_bases == 0 || n_reads == 0) return TSXC_OK;
+    const uint64_t n_words = (n_bases + 31) >> 5;
+    CU(cudaMemsetAsync(d_ends, 0, n_words * sizeof(uint32_t), s));
+    k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, d_ends, 0);
+    t->n_launches++;
+    return launch_count_marked(t, d_packed, d_ends, n_words, n_bases, s);
+}
+
+// ---- accumulation of host batches (see tsxc_table::Accum) ---------------------------------------------------------
+int ensure_acc(tsxc_table* t) {
+    if (t->acc[0].d_packed) return TSXC_OK;
+    int rc = release_radix_buffers(t);            // plan the memory again with the accumulation buffers in place
+    if (rc) return rc;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t reserve = env_u64("TSXC_RESERVE_MB", 4096) << 20;
+    const uint64_t budget = free_b > reserve ? free_b - reserve : free_b / 2;
+    // per base position: a key in A (+1/8 in B) if it starts a k-mer, 2 bits + 1 end bit in each of the two buffers
+    const double per_pos = 9.0 * t->L.KW + 0.75;
+    uint64_t pos = (uint64_t)((double)budget / per_pos);
+    pos = std::min<uint64_t>(pos, std::max<uint64_t>(1ULL << 22, 4 * t->L.n_slots));   // more than ~4 k-mers per slot per pass is pointless
+    uint64_t words = std::min<uint64_t>(pos / 32, 1ULL << 28);
+    if (const uint64_t e = env_u64("TSXC_ACC_WORDS", 0)) words = e;
+    words = std::max<uint64_t>(words & ~511ULL, 1024);
+    for (auto& a : t->acc) {
+        CU(cudaMalloc(&a.d_packed, (words + 8) * sizeof(uint64_t)));
+        CU(cudaMalloc(&a.d_ends, (words + 8) * sizeof(uint32_t)));
+        if (!a.consumed) CU(cudaEventCreateWithFlags(&a.consumed, cudaEventDisableTiming));
+        a.fill_words = 0; a.busy = false;
+    }
+    if (!t->acc_copied) CU(cudaEventCreateWithFlags(&t->acc_copied, cudaEventDisableTiming));
+    t->acc_cap_words = words;
+    return TSXC_OK;
+}
+
+// Hand the accumulated reads to the counting kernels (asynchronous) and switch to the other buffer.
+int flush_acc(tsxc_table* t) {
+    if (!t->acc_cap_words) return TSXC_OK;
+    tsxc_table::Accum& a = t->acc[t->acc_cur];
+    if (a.fill_words == 0) return TSXC_OK;
+    CU(cudaEventRecord(t->acc_copied, t->copy_stream));
+    CU(cudaStreamWaitEvent(t->stream, t->acc_copied, 0));
+    // padding between batches and after the last one is marked as read ends, so the stream simply ends at a word boundary
+    int rc = launch_count_marked(t, a.d_packed, a.d_ends, a.fill_words, a.fill_words * 32, t->stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(a.consumed, t->stream));
+    a.busy = true;
+    a.fill_words = 0;
+    t->acc_cur ^= 1;
     return TSXC_OK;
 }
 
@@ -441,7 +503,7 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
     uint32_t min_table_log2 = 29;
     if (const char* env = std::getenv("TSXC_REGION_LOG2")) {
         const int v = std::atoi(env);
-        if (v >= 12 && v <= 40) { h->region_log2 = (uint32_t)v; min_table_log2 = (uint32_t)v + 1; }
+        if (v >= 6 && v <= 40) { h->region_log2 = (uint32_t)v; min_table_log2 = (uint32_t)v + 1; }
     }
     uint32_t seg_log2 = (uint32_t)env_u64("TSXC_SEG_LOG2", kSegWordsLog2Default);
     seg_log2 = std::max<uint32_t>(kSegWordsLog2Min, std::min<uint32_t>(seg_log2, 20));
@@ -479,6 +541,7 @@ static int add_keys_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, b
 template <typename Emit>
 static int dump_chunks(tsxc_table* t, Emit&& emit) {
     CU(cudaSetDevice(t->device));
+    { const int frc = flush_acc(t); if (frc) return frc; }
     CU(cudaStreamSynchronize(t->copy_stream));
     CU(cudaStreamSynchronize(t->stream));
     const Layout& L = t->L;
@@ -567,9 +630,11 @@ int tsxc_destroy(tsxc_table* t) {
     for (auto& pe : t->ev_phase) { cudaEventDestroy(pe.ev.first); cudaEventDestroy(pe.ev.second); }
     for (auto& ev : t->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& m : t->marks) if (m) cudaEventDestroy(m);
+    for (auto& a : t->acc) { cudaFree(a.d_packed); cudaFree(a.d_ends); if (a.consumed) cudaEventDestroy(a.consumed); }
+    if (t->acc_copied) cudaEventDestroy(t->acc_copied);
     cudaFree(t->d_A); cudaFree(t->d_B); cudaFree(t->d_ctl); cudaFree(t->d_seghist); cudaFree(t->d_segtotal); cudaFree(t->d_segprefix);
     cudaFree(t->d_fhist); cudaFree(t->d_fcur); cudaFree(t->d_peers); cudaFree(t->d_ticket_k0);
-    cudaFree(t->d_ends); cudaFree(t->d_keys); cudaFree(t->d_counts); cudaFree(t->d_nout);
+    cudaFree(t->d_ends); cudaFree(t->d_keys); cudaFree(t->d_counts); cudaFree(t->d_nout); cudaFree(t->d_text); cudaFree(t->d_pairs[0]); cudaFree(t->d_pairs[1]);
     cudaFree(t->d_ctr); cudaFree(t->d_words);
     if (t->stream) cudaStreamDestroy(t->stream);
     if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
@@ -581,6 +646,8 @@ int tsxc_clear(tsxc_table* t) {
     if (!t) return TSXC_E_INVALID;
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
+    for (auto& a : t->acc) a.fill_words = 0;          // reads accumulated but not yet counted are dropped with the table
+    CU(cudaStreamSynchronize(t->copy_stream));
     CU(cudaMemsetAsync(t->d_words, 0, t->L.table_bytes, t->stream));
     CU(cudaMemsetAsync(t->d_ctr, 0, CTR_COUNT * sizeof(unsigned long long), t->stream));
     t->err.clear();
@@ -597,7 +664,16 @@ int tsxc_trim(tsxc_table* t) {
     if (!t) return TSXC_E_INVALID;
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
-    return release_radix_buffers(t);
+    { const int frc = flush_acc(t); if (frc) return frc; }
+    int rc = release_radix_buffers(t);
+    if (rc) return rc;
+    if (t->acc_cap_words) {
+        CU(cudaStreamSynchronize(t->stream));
+        CU(cudaStreamSynchronize(t->copy_stream));
+        for (auto& a : t->acc) { cudaFree(a.d_packed); cudaFree(a.d_ends); a.d_packed = nullptr; a.d_ends = nullptr; a.fill_words = 0; a.busy = false; }
+        t->acc_cap_words = 0;
+    }
+    return TSXC_OK;
 }
 
 void* tsxc_stream(tsxc_table* t) { return t ? (void*)t->stream : nullptr; }
@@ -642,9 +718,31 @@ int tsxc_add_reads(tsxc_table* t, const uint64_t* packed, const uint64_t* offset
     const uint64_t n_words = (n_bases + 31) >> 5;
     Staging& st = t->stage[t->next_stage];
     t->next_stage ^= 1;
+    int rc;
+    if (t->radix_on && !(t->L.flags & TSXC_FLAG_DIRECT)) {
+        if ((rc = ensure_acc(t))) return rc;
+        if (2 * n_words <= t->acc_cap_words) {
+            // accumulate: append the batch to the current buffer (word aligned), mark its read ends and the padding
+            if (t->acc[t->acc_cur].fill_words + n_words > t->acc_cap_words && (rc = flush_acc(t))) return rc;
+            tsxc_table::Accum& a = t->acc[t->acc_cur];
+            if (a.fill_words == 0 && a.busy) { CU(cudaStreamWaitEvent(t->copy_stream, a.consumed, 0)); a.busy = false; }
+            // the offsets are only needed by k_mark_ends on the copy stream: stream order protects the slot's reuse
+            if ((rc = ensure(t, &st.d_offsets, &st.cap_offsets, (size_t)n_reads + 1))) return rc;
+            const uint64_t base = a.fill_words * 32;
+            CU(cudaMemcpyAsync(a.d_packed + a.fill_words, packed, n_words * sizeof(uint64_t), cudaMemcpyHostToDevice, t->copy_stream));
+            CU(cudaMemcpyAsync(st.d_offsets, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, t->copy_stream));
+            CU(cudaMemsetAsync(a.d_ends + a.fill_words, 0, n_words * sizeof(uint32_t), t->copy_stream));
+            k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, t->copy_stream>>>(st.d_offsets, n_reads, a.d_ends, base);
+            if (n_bases & 31) k_mark_padding<<<1, 32, 0, t->copy_stream>>>(a.d_ends, base + n_bases, base + n_words * 32);
+            t->n_launches += 2;
+            a.fill_words += n_words;
+            CU(cudaGetLastError());
+            return TSXC_OK;
+        }
+        if ((rc = flush_acc(t))) return rc;        // a batch this large is a pass of its own; keep the order of submission
+    }
     // the slot may still be read by the kernel of two calls ago
     if (st.used) CU(cudaStreamWaitEvent(t->copy_stream, st.done, 0));
-    int rc;
     if ((rc = ensure(t, &st.d_packed, &st.cap_packed, (size_t)n_words + 8))) return rc;
     if ((rc = ensure(t, &st.d_offsets, &st.cap_offsets, (size_t)n_reads + 1))) return rc;
     if ((rc = ensure(t, &st.d_ends, &st.cap_ends, (size_t)n_words + 8))) return rc;
@@ -679,6 +777,7 @@ int tsxc_add_kmers(tsxc_table* t, const uint64_t* kmers, uint64_t n) {
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
     const size_t words = (size_t)n * t->L.KW;
+    { const int frc = flush_acc(t); if (frc) return frc; }
     // the staging buffer is shared with other calls: order against the compute stream
     CU(cudaStreamSynchronize(t->stream));
     int rc = ensure(t, &t->d_keys, &t->cap_keys, words);
@@ -691,6 +790,7 @@ int tsxc_sync(tsxc_table* t) {
     if (!t) return TSXC_E_INVALID;
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
+    { const int frc = flush_acc(t); if (frc) return frc; }
     CU(cudaStreamSynchronize(t->copy_stream));
     CU(cudaStreamSynchronize(t->stream));
     unsigned long long flags = 0;
@@ -700,8 +800,44 @@ int tsxc_sync(tsxc_table* t) {
 }
 
 static int lookup_device_locked(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, uint64_t* d_counts_out) {
+    const RadixGeom& rg = t->rg;
+    cudaStream_t s = t->stream;
+    const uint64_t sorted_min = env_u64("TSXC_LOOKUP_SORT_MIN", 1ULL << 18);
+    if (t->radix_on && rg.d1 > 0 && t->L.shard_bits == 0 && !(t->L.flags & TSXC_FLAG_DIRECT) && n >= sorted_min && t->d_fhist) {
+        // sort the queries by table region (same partition passes as the insert), then probe in that order
+        int rc;
+        for (int i = 0; i < 2; ++i) if ((rc = ensure(t, &t->d_pairs[i], &t->cap_pairs[i], (size_t)n * 2))) return rc;
+        const int grid_q = grid_for(t, n), grid_p = t->sms * 2;
+#define M(KW_) k_hash_queries<KW_><<<grid_q, kBlockThreads, 0, s>>>(t->tv, d_kmers, n, t->d_pairs[0])
+        TSX_DISPATCH_KW(t->L, M);
+#undef M
+        RadixGeom g1 = rg;                    // pass 1: the whole array is one bin, split by digit 1
+        g1.nbl = 1; g1.d2 = rg.d1; g1.nb2 = rg.nb1; g1.shift2 = rg.shift1;
+        k_single_bin<<<1, kNB + 32, 0, s>>>(t->d_ctl, n);
+        k_plan_group<2><<<1, kNB, 0, s>>>(t->d_ctl, 0, n, 1, t->d_fhist, g1.nb2);
+        k_hist_keys<2><<<grid_p, kRadixThreads, 0, s>>>(t->tv, g1, t->d_ctl, t->d_pairs[0], t->d_fhist);
+        k_scan_fine<<<1, 1024, 0, s>>>(t->d_ctl, t->d_fhist, t->d_fcur, g1.nb2);
+        k_part_keys<2><<<grid_p, kRadixThreads, 0, s>>>(t->tv, g1, t->d_ctl, t->d_pairs[0], t->d_fcur, t->d_pairs[1]);
+        const uint64_t* sorted = t->d_pairs[1];
+        t->n_launches += 6;
+        if (rg.d2) {                          // pass 2: digit 2 inside every digit-1 bin
+            k_coff_from_cursors<<<1, kNB + 32, 0, s>>>(t->d_ctl, t->d_fcur, rg.nb1, n);
+            k_plan_group<2><<<1, kNB, 0, s>>>(t->d_ctl, 0, n, rg.nbl, t->d_fhist, rg.nbl * rg.nb2);
+            k_hist_keys<2><<<grid_p, kRadixThreads, 0, s>>>(t->tv, rg, t->d_ctl, t->d_pairs[1], t->d_fhist);
+            k_scan_fine<<<1, 1024, 0, s>>>(t->d_ctl, t->d_fhist, t->d_fcur, rg.nbl * rg.nb2);
+            k_part_keys<2><<<grid_p, kRadixThreads, 0, s>>>(t->tv, rg, t->d_ctl, t->d_pairs[1], t->d_fcur, t->d_pairs[0]);
+            sorted = t->d_pairs[0];
+            t->n_launches += 5;
+        }
+#define M(KW_, W_) k_lookup_pairs<KW_, W_><<<grid_q, kBlockThreads, 0, s>>>(t->tv, sorted, n, d_kmers, d_counts_out)
+        TSX_DISPATCH(t->L, M);
+#undef M
+        t->n_launches++;
+        CU(cudaGetLastError());
+        return TSXC_OK;
+    }
     const int grid = grid_for(t, n);
-#define M(KW_, W_) k_lookup<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n, d_counts_out)
+#define M(KW_, W_) k_lookup<KW_, W_><<<grid, kBlockThreads, 0, s>>>(t->tv, d_kmers, n, d_counts_out)
     TSX_DISPATCH(t->L, M);
 #undef M
     t->n_launches++;
@@ -714,6 +850,7 @@ int tsxc_lookup_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, uint6
     if (n == 0) return TSXC_OK;
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
+    { const int frc = flush_acc(t); if (frc) return frc; }
     return lookup_device_locked(t, d_kmers, n, d_counts_out);
 }
 
@@ -723,6 +860,7 @@ int tsxc_lookup(tsxc_table* t, const uint64_t* kmers, uint64_t n, uint64_t* coun
     // one critical section: the staging buffers are shared with add_kmers / dump on the same handle
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
+    { const int frc = flush_acc(t); if (frc) return frc; }
     CU(cudaStreamSynchronize(t->stream));
     int rc;
     if ((rc = ensure(t, &t->d_keys, &t->cap_keys, (size_t)n * t->L.KW))) return rc;
@@ -738,6 +876,7 @@ int tsxc_stats(tsxc_table* t, tsxc_stats_t* out) {
     if (!t || !out) return fail(t, TSXC_E_INVALID, "null argument");
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
+    { const int frc = flush_acc(t); if (frc) return frc; }
     CU(cudaStreamSynchronize(t->copy_stream));
     CU(cudaStreamSynchronize(t->stream));
     unsigned long long c[CTR_COUNT];
@@ -789,32 +928,52 @@ int tsxc_dump(tsxc_table* t, uint64_t* kmers_out, uint64_t* counts_out, uint64_t
     return TSXC_OK;
 }
 
+// Table scan -> (k-mer, count) -> text, all on the device; the host only copies and writes the bytes.
 int tsxc_dump_file(tsxc_table* t, const char* path) {
     if (!t || !path) return fail(t, TSXC_E_INVALID, "null argument");
     std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    { const int frc = flush_acc(t); if (frc) return frc; }
+    CU(cudaStreamSynchronize(t->copy_stream));
+    CU(cudaStreamSynchronize(t->stream));
     FILE* f = std::fopen(path, "wb");
     if (!f) return fail(t, TSXC_E_IO, std::string("cannot open ") + path);
-    const uint32_t KW = t->L.KW, k = t->L.k;
-    std::vector<char> buf;
-    int rc = dump_chunks(t, [&](const uint64_t* keys, const uint64_t* cnt, uint64_t n) {
-        static const char LUT[4] = {'A', 'C', 'G', 'T'};  // SequenceUtils.h:65-75
-        buf.clear();
-        buf.reserve((size_t)n * (k + 22));
-        char num[24];
-        for (uint64_t i = 0; i < n; ++i) {
-            const uint64_t* kw = keys + i * KW;
-            for (uint32_t b = 0; b < k; ++b) buf.push_back(LUT[(kw[(2 * b) >> 6] >> ((2 * b) & 63)) & 3]);
-            buf.push_back('\t');
-            int len = std::snprintf(num, sizeof num, "%llu\n", (unsigned long long)cnt[i]);
-            buf.insert(buf.end(), num, num + len);
-        }
-        return std::fwrite(buf.data(), 1, buf.size(), f) == buf.size() ? 0 : (int)TSXC_E_IO;
-    });
-    if (std::fclose(f) != 0 && rc == TSXC_OK) rc = TSXC_E_IO;
-    if (rc == TSXC_E_IO) return fail(t, rc, "write failed");
-    return rc;
+    const Layout& L = t->L;
+    const uint64_t chunk_slots = std::min<uint64_t>(L.n_slots, 1ULL << 24);
+    const uint64_t chunk_buckets = std::max<uint64_t>(1, chunk_slots / L.SPB);
+    const size_t line_max = (size_t)L.k + 22;
+    int rc;
+    auto done = [&](int code) { std::fclose(f); return code; };
+    if ((rc = ensure(t, &t->d_keys, &t->cap_keys, (size_t)chunk_slots * L.KW))) return done(rc);
+    if ((rc = ensure(t, &t->d_counts, &t->cap_counts, (size_t)chunk_slots))) return done(rc);
+    if ((rc = ensure(t, &t->d_text, &t->cap_text, (size_t)chunk_slots * line_max))) return done(rc);
+    std::vector<char> host;
+    unsigned long long* d_nbytes = t->d_ticket_k0;      // scratch counter
+    for (uint64_t b0 = 0; b0 < L.n_buckets; b0 += chunk_buckets) {
+        const uint64_t b1 = std::min(L.n_buckets, b0 + chunk_buckets);
+        CU(cudaMemsetAsync(t->d_nout, 0, sizeof(unsigned long long), t->stream));
+        CU(cudaMemsetAsync(d_nbytes, 0, sizeof(unsigned long long), t->stream));
+        const int grid = grid_for(t, (b1 - b0) * L.SPB);
+#define M(KW_, W_) k_dump<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, b0, b1, t->d_keys, t->d_counts, chunk_slots, t->d_nout)
+        TSX_DISPATCH(t->L, M);
+#undef M
+        unsigned long long n = 0, n_bytes = 0;
+        CU(cudaMemcpyAsync(&n, t->d_nout, sizeof n, cudaMemcpyDeviceToHost, t->stream));
+        CU(cudaStreamSynchronize(t->stream));
+        t->n_launches++;
+        if (n == 0) continue;
+        k_format_dump<<<grid_for(t, n), kBlockThreads, 0, t->stream>>>(t->d_keys, t->d_counts, n, L.k, L.KW, t->d_text, d_nbytes);
+        t->n_launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&n_bytes, d_nbytes, sizeof n_bytes, cudaMemcpyDeviceToHost, t->stream));
+        CU(cudaStreamSynchronize(t->stream));
+        host.resize((size_t)n_bytes);
+        CU(cudaMemcpy(host.data(), t->d_text, (size_t)n_bytes, cudaMemcpyDeviceToHost));
+        if (std::fwrite(host.data(), 1, host.size(), f) != host.size()) return done(fail(t, TSXC_E_IO, "write failed"));
+    }
+    if (std::fclose(f) != 0) return fail(t, TSXC_E_IO, "write failed");
+    return TSXC_OK;
 }
-
 
 /* ---- multi-GPU routing -------------------------------------------------------------------------------------- */
 int tsxc_route_info(tsxc_table* t, tsxc_route_info_t* out) {
@@ -866,7 +1025,7 @@ int tsxc_route_begin(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_
     if (rc) return rc;
     CU(cudaMemsetAsync(t->d_ends, 0, (n_words + 8) * sizeof(uint32_t), s));
     if (n_reads) {
-        k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, t->d_ends);
+        k_mark_ends<<<grid_for(t, n_reads), kBlockThreads, 0, s>>>(d_offsets, n_reads, t->d_ends, 0);
         t->n_launches++;
     }
     const RadixGeom& rg = t->rg;
@@ -984,6 +1143,18 @@ int tsxc_memcpy(int device, void* dst, const void* src, uint64_t bytes, int kind
     CU(cudaSetDevice(device));
     const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : (kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
     CU(cudaMemcpy(dst, src, bytes, k));
+    return TSXC_OK;
+}
+
+int tsxc_enable_peer_access(int device, int peer) {
+    tsxc_table* t = nullptr;
+    CU(cudaSetDevice(device));
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) return fail(t, TSXC_E_CUDA, "no peer access between these devices");
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return TSXC_OK; }
+    CU(e);
     return TSXC_OK;
 }
 

@@ -28,12 +28,21 @@ constexpr int kBlockThreads = 256;
 // bit g of `ends` is set iff base g is the last base of a read.  A k-mer starting at g is valid iff
 // no end bit lies in [g, g+k-2] (it may end exactly on a boundary) and g+k <= n_bases.
 __global__ void __launch_bounds__(kBlockThreads) k_mark_ends(const uint64_t* __restrict__ offsets, uint64_t n_reads,
-                                                             uint32_t* __restrict__ ends) {
+                                                             uint32_t* __restrict__ ends, uint64_t base) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
         const uint64_t b = offsets[r], e = offsets[r + 1];
-        if (e > b) atomicOr(ends + ((e - 1) >> 5), 1u << ((e - 1) & 31));
+        if (e > b) atomicOr(ends + ((base + e - 1) >> 5), 1u << ((base + e - 1) & 31));
     }
+}
+
+// Positions [from, to) (fewer than 32, inside one word) are padding between two batches of an accumulated stream:
+// every one of them is marked as a read end, so no k-mer (k >= 2) starts in or runs through the padding.
+__global__ void k_mark_padding(uint32_t* __restrict__ ends, uint64_t from, uint64_t to) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || to <= from) return;
+    const uint32_t lo = (uint32_t)(from & 31), n = (uint32_t)(to - from);
+    const uint32_t mask = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << lo;
+    atomicOr(ends + (from >> 5), mask);
 }
 
 // ---- warp-level window loader -----------------------------------------------------------------
@@ -269,6 +278,49 @@ __global__ void __launch_bounds__(kBlockThreads) k_dump(const __grid_constant__ 
                 counts_out[pos] = cnt;
             }
         }
+    }
+}
+
+// ---- K5b: (k-mer, count) pairs -> text lines "KMER<TAB>COUNT\n" on the device ---------------------------------------
+// Format of count_kmers.py:32-34 of the reference; bases decoded like TSXSeqUtils::toSequence (SequenceUtils.h:47-84).
+// One thread per pair: line length = k + 2 + decimal digits; a block-wide scan places the block's lines back to
+// back, one atomicAdd per block claims its range of the output (line order = table order, unspecified anyway).
+__global__ void __launch_bounds__(kBlockThreads) k_format_dump(const uint64_t* __restrict__ kmers, const uint64_t* __restrict__ counts,
+                                                               uint64_t n, uint32_t k, uint32_t KW, char* __restrict__ text,
+                                                               unsigned long long* __restrict__ n_bytes) {
+    __shared__ uint32_t wsum[kBlockThreads / 32];
+    __shared__ unsigned long long base_s;
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t n_round = (n + kBlockThreads - 1) / kBlockThreads * kBlockThreads;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * kBlockThreads; i0 < n_round; i0 += (uint64_t)gridDim.x * kBlockThreads) {
+        const uint64_t i = i0 + threadIdx.x;
+        uint64_t c = i < n ? counts[i] : 0;
+        uint32_t digits = 1;
+        for (uint64_t x = c; x >= 10; x /= 10) ++digits;
+        const uint32_t len = i < n ? k + 2 + digits : 0;
+        uint32_t inc = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(full, inc, d);
+            if (lane >= (unsigned)d) inc += y;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kBlockThreads / 32; ++w) { const uint32_t x = wsum[w]; if ((unsigned)w < warp) pre += x; tot += x; }
+        if (threadIdx.x == 0) base_s = atomicAdd(n_bytes, (unsigned long long)tot);
+        __syncthreads();
+        if (i < n) {
+            char* out = text + base_s + pre + inc - len;
+            const uint64_t* kw = kmers + i * KW;
+            for (uint32_t b = 0; b < k; ++b) out[b] = "ACGT"[(kw[(2 * b) >> 6] >> ((2 * b) & 63)) & 3];
+            out[k] = '\t';
+            for (uint32_t d = digits; d > 0; --d) { out[k + d] = (char)('0' + c % 10); c /= 10; }
+            out[k + 1 + digits] = '\n';
+        }
+        __syncthreads();
     }
 }
 

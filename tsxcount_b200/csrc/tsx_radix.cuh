@@ -810,6 +810,60 @@ k_insert_keys(const __grid_constant__ TableView tv, RadixCtl* __restrict__ ctl, 
     flush_stats(tv, st);
 }
 
+// ---- region-sorted batched lookup -------------------------------------------------------------------------------------
+// getKmerCount(kmer) for millions of k-mers against a table far larger than TLB reach: unsorted, the probes run at the
+// uniformly-random rate (5 G/s on 128 GiB); sorted by table region with the same two partition passes as the insert
+// they run at the region-sweep rate.  Records are (hash word 0, query index) pairs, i.e. keys of two words.
+template <int KW>
+__global__ void __launch_bounds__(kBlockThreads) k_hash_queries(const __grid_constant__ TableView tv, const uint64_t* __restrict__ kmers,
+                                                                uint64_t n, uint64_t* __restrict__ pairs) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Key<KW> key;
+        bool in_range = true;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+            key.w[j] = __ldg(kmers + i * KW + j);
+            in_range &= (key.w[j] & ~word_mask<KW>(j, tv.hp)) == 0;
+        }
+        const Key<KW> H = hash_key<KW>(key, tv.hp);
+        pairs[2 * i] = H.w[0];
+        pairs[2 * i + 1] = i | (in_range ? 0ULL : 1ULL << 63);      // bits beyond 2k set: not a k-mer, count 0
+    }
+}
+
+template <int KW, int W>
+__global__ void __launch_bounds__(kBlockThreads) k_lookup_pairs(const __grid_constant__ TableView tv, const uint64_t* __restrict__ pairs,
+                                                                uint64_t n, const uint64_t* __restrict__ kmers,
+                                                                uint64_t* __restrict__ counts) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint64_t tag = __ldcs(pairs + 2 * j + 1);
+        const uint64_t idx = tag & ~(1ULL << 63);
+        uint64_t c = 0;
+        if (!(tag >> 63)) {
+            Key<KW> key;
+#pragma unroll
+            for (int w = 0; w < KW; ++w) key.w[w] = __ldg(kmers + idx * KW + w);
+            c = lookup_hashed<KW, W>(tv, hash_key<KW>(key, tv.hp));
+        }
+        counts[idx] = c;
+    }
+}
+
+// one coarse "bin" holding all n records (first partition pass of an unsorted array)
+__global__ void k_single_bin(RadixCtl* __restrict__ ctl, uint64_t n) {
+    if (threadIdx.x > kNB) return;
+    ctl->cur_coff[threadIdx.x] = threadIdx.x == 0 ? 0ULL : n;
+}
+
+// after a scatter the cursors of the fine bins stand at the bins' ends: they are the coarse offsets of the next pass
+__global__ void k_coff_from_cursors(RadixCtl* __restrict__ ctl, const unsigned long long* __restrict__ fcur, uint32_t nb, uint64_t n) {
+    const uint32_t b = threadIdx.x;
+    if (b > kNB) return;
+    ctl->cur_coff[b] = b == 0 ? 0ULL : (b <= nb ? (uint64_t)fcur[b - 1] : n);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace tsx

@@ -10,7 +10,9 @@
 //   statistics        :479     print_stats()
 // New: --mode=CUDA (the only mode this binary implements — the CPU modes are the reference's own),
 //      --dump=FILE (KMER<TAB>COUNT, format of count_kmers.py:32-34), --device=N, --widevalue (use every
-//      spare bit of the entry for the value field instead of exactly s bits).
+//      spare bit of the entry for the value field instead of exactly s bits), --gpus=N (table hash-sharded over N
+//      GPUs, NCCL + peer stores: MultiGpuCounter.h), --n-policy=skip (what happens to k-mers spanning a non-ACGT
+//      base; the reference substitutes unseeded random bits, SequenceUtils.h:126-137, which cannot be reproduced).
 // The count phase streams FASTQ through a reader thread (FastxReader), packer threads (tsxc_pack_reads into
 // pinned buffers) and tsxc_add_reads; see countKMers.
 #include <argp.h>
@@ -31,6 +33,7 @@
 #include <sys/stat.h>
 
 #include "FastxReader.h"
+#include "MultiGpuCounter.h"
 #include "TSXHashMapCUDA.h"
 
 const char* argp_program_version = "tsxCount-b200 1.0";
@@ -49,6 +52,9 @@ static struct argp_option options[] = {
     {"device", 'g', "N", 0, "CUDA device index"},
     {"widevalue", 'w', 0, 0, "widen the value field to every spare entry bit (default: exactly s bits)"},
     {"readers", 'r', "N", 0, "reader threads on disjoint byte ranges of a plain (not gzip) well-formed input (default 1)"},
+    {"gpus", 'G', "N", 0, "shard the table over N GPUs of this box (power of two; default 1)"},
+    {"batch-reads", 'B', "N", 0, "reads per GPU and super-batch with --gpus (default 4194304)"},
+    {"n-policy", 'N', "POLICY", 0, "k-mers spanning a non-ACGT base: skip (the only policy; default)"},
     {0}};
 
 struct arguments {
@@ -58,6 +64,9 @@ struct arguments {
     bool check = false, checkabort = false, wide = false;
     int device = 0;
     int readers = 1;
+    int gpus = 1;
+    uint64_t batch_reads = 1u << 22;
+    std::string n_policy = "skip";
 };
 
 static error_t parse_opt(int key, char* arg, struct argp_state* state) {
@@ -75,6 +84,9 @@ static error_t parse_opt(int key, char* arg, struct argp_state* state) {
         case 'g': a->device = atoi(arg); break;
         case 'w': a->wide = true; break;
         case 'r': a->readers = atoi(arg); break;
+        case 'G': a->gpus = atoi(arg); break;
+        case 'B': a->batch_reads = std::max<uint64_t>(1, std::strtoull(arg, nullptr, 10)); break;
+        case 'N': a->n_policy = arg ? arg : ""; break;
         case ARGP_KEY_ARG: return 0;
         default: return ARGP_ERR_UNKNOWN;
     }
@@ -254,7 +266,72 @@ void countKMers(TSXHashMapCUDA& map, const arguments& args) {
     std::cout << "Added a total of " << map.getKmerCount() << " different kmers" << std::endl;   // main.cpp:222
 }
 
-int checkCounts(TSXHashMapCUDA& map, const arguments& args) {
+// Count phase with --gpus=N: a super-batch gives every GPU one batch of reads; the batches are packed in parallel
+// and counted collectively (MultiGpuCounter::addSuperBatch).  Reading is sequential (one FastxReader).
+void countKMersMulti(MultiGpuCounter& mg, const arguments& args) {
+    const int N = mg.gpus();
+    const bool multi_fasta = FastxReader::sniff(args.input_path) == '>';
+    FastxReader rd(args.input_path, multi_fasta ? 0 : 4, 8u << 20);
+    if (multi_fasta) rd.setFastaSplit(1u << 20, args.k - 1);
+    struct Raw { std::string bases; std::vector<uint64_t> offsets; size_t n = 0; };
+    std::vector<Raw> raw(N);
+    std::vector<PinnedBatch> pin(N);
+    std::vector<MultiGpuCounter::HostBatch> hb(N);
+    uint64_t n_reads_total = 0, n_bad_total = 0;
+    for (;;) {
+        size_t got_any = 0;
+        for (int d = 0; d < N; ++d) {
+            // a batch is read in pieces so that the reader's buffers stay small; pieces are appended
+            Raw& r = raw[d];
+            r.bases.clear(); r.offsets.assign(1, 0); r.n = 0;
+            std::string b; std::vector<uint64_t> o;
+            while (r.n < args.batch_reads) {
+                const size_t n = rd.nextBatch(std::min<uint64_t>(1u << 18, args.batch_reads - r.n), b, o);
+                if (!n) break;
+                const uint64_t base = r.bases.size();
+                r.bases += b;
+                for (size_t i = 1; i <= n; ++i) r.offsets.push_back(base + o[i]);
+                r.n += n;
+            }
+            got_any += r.n;
+        }
+        if (!got_any) break;
+        std::vector<std::thread> th;
+        std::vector<uint64_t> nseg(N, 0), nbad(N, 0);
+        std::exception_ptr failure;
+        std::mutex fmu;
+        for (int d = 0; d < N; ++d) th.emplace_back([&, d] {
+            try {
+                Raw& r = raw[d];
+                if (!r.n) return;
+                pin[d].ensure(r.bases.size() / 32 + 2, r.n + 2);
+                int prc = tsxc_pack_reads(r.bases.data(), r.offsets.data(), r.n, pin[d].packed, pin[d].offsets, pin[d].off_cap, &nseg[d], &nbad[d]);
+                if (prc == TSXC_E_INVALID) {
+                    size_t bad_upper = 0;
+                    for (char c : r.bases) bad_upper += !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+                    pin[d].ensure(r.bases.size() / 32 + 2, r.n + bad_upper + 2);
+                    prc = tsxc_pack_reads(r.bases.data(), r.offsets.data(), r.n, pin[d].packed, pin[d].offsets, pin[d].off_cap, &nseg[d], &nbad[d]);
+                }
+                if (prc != TSXC_OK) throw TSXException("tsxc_pack_reads failed");
+            } catch (...) { std::lock_guard<std::mutex> lk(fmu); if (!failure) failure = std::current_exception(); }
+        });
+        for (auto& t : th) t.join();
+        if (failure) std::rethrow_exception(failure);
+        for (int d = 0; d < N; ++d) {
+            hb[d].packed = pin[d].packed; hb[d].offsets = pin[d].offsets; hb[d].n_reads = raw[d].n ? nseg[d] : 0;
+            n_reads_total += raw[d].n; n_bad_total += nbad[d];
+        }
+        mg.addSuperBatch(hb);
+        mg.sync();                                   // the pinned buffers are refilled by the next super-batch
+    }
+    std::cerr << "Reads: " << n_reads_total << std::endl;
+    if (n_bad_total)
+        std::cerr << "Non-ACGT bases: " << n_bad_total << " (k-mers spanning them are skipped; the reference substitutes random bits)" << std::endl;
+    std::cout << "Added a total of " << mg.getKmerCount() << " different kmers" << std::endl;   // main.cpp:222
+}
+
+template <typename Map>
+int checkCounts(Map& map, const arguments& args) {
     const std::string ref = args.input_path + "." + std::to_string(args.k) + ".count";         // main.cpp:226
     std::cout << "Checking kmer counts against manual hashmap ..." << std::endl;
     std::cerr << "Loading reference file: " << ref << std::endl;
@@ -329,12 +406,38 @@ int main(int argc, char* argv[]) {
     if (args.readers > 1) std::cerr << "Readers=" << args.readers << std::endl;
     std::cerr << "Mode=" << args.mode << std::endl;
 
+    if (args.gpus > 1) std::cerr << "GPUs=" << args.gpus << std::endl;
+    if (args.n_policy != "skip") {
+        std::cerr << "--n-policy=" << args.n_policy << ": only 'skip' exists (no k-mer spans a non-ACGT base); the reference's random "
+                  << "substitution (SequenceUtils.h:126-137) is not reproducible and is not offered." << std::endl;
+        return 2;
+    }
     if (args.mode != "CUDA") {
         std::cerr << "Mode " << args.mode << " is one of the reference's CPU serialization backends; this binary implements "
                   << "--mode=CUDA only (there is no CPU fallback)." << std::endl;
         return 2;
     }
     try {
+        if (args.gpus > 1) {
+            std::cerr << "Creating TSXHashMap CUDA, hash-sharded over " << args.gpus << " GPUs" << std::endl;
+            // receive buffers: room for what one super-batch can bring to a shard (the batches are hash-uniform)
+            const uint64_t recv_cap = args.batch_reads * 400 + (1u << 22);
+            MultiGpuCounter mg(args.k, args.l, args.storagebits, args.gpus, args.wide ? TSXC_FLAG_NONE : TSXC_FLAG_EXACT_S, recv_cap);
+            const auto t0 = std::chrono::steady_clock::now();
+            countKMersMulti(mg, args);
+            const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const tsxc_stats_t st = mg.stats();
+            std::cerr << "Counted " << st.kmers_added << " kmers in " << secs << " s (" << (secs > 0 ? st.kmers_added / secs / 1e6 : 0.0)
+                      << " M kmers/s incl. parsing)" << std::endl;
+            int rc = 0;
+            if (args.check) rc = checkCounts(mg, args);
+            if (!args.dump_path.empty()) mg.dump(args.dump_path);
+            std::cerr << "Used fields: " << st.used_slots << std::endl;                         // print_stats, TSXHashMap.h:390-395
+            std::cerr << "Available fields: " << (double)st.n_slots << std::endl;
+            std::cerr << "adds: " << st.kmers_added << std::endl;
+            std::cerr << "overflow entries: " << st.overflow_entries << std::endl;
+            return rc;
+        }
         std::cerr << "Creating TSXHashMap CUDA" << std::endl;
         TSXHashMapCUDA map((uint8_t)args.l, args.storagebits, args.k, args.device, args.wide ? TSXC_FLAG_NONE : TSXC_FLAG_EXACT_S);
         const auto t0 = std::chrono::steady_clock::now();
