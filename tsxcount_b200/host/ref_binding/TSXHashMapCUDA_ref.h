@@ -4,7 +4,7 @@
 //     g++ -std=c++14 -I<reference> -I<reference>/src -I<repo>/include ... -ltsxcuda
 // It derives from TSXHashMap (src/tsxcount/TSXHashMap.h:68) and overrides the virtual per-k-mer interface the
 // reference's driver and --check use: addKmer (:182), getKmerCount(kmer) (:548); getKmerCount() (:645) is shadowed.
-// oracle/Makefile builds oracle/_ref/ref_adapter_check from it (test infrastructure; the reference sources stay where
+// The test-side Makefile builds a small check binary from it (test infrastructure; the reference sources stay where
 // they are), tests/test_cli.py runs that binary on the GPU.
 #pragma once
 
