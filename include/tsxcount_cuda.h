@@ -267,7 +267,10 @@ int tsxc_k0_random_rmw(tsxc_table* t, uint64_t table_bytes, uint64_t n_ops, int 
 int tsxc_k0_windowed(tsxc_table* t, uint64_t footprint_bytes, uint64_t window_bytes, uint64_t n_ops, int mode,
                      int blocks, int threads, float* ms_out);
 
-/* K0r: all blocks sweep the footprint region by region, ops_per_region random RMWs each (L2-blocked variant). */
+/* K0r: all blocks sweep the footprint region by region, ops_per_region random RMWs each (L2-blocked variant).
+ * mode (low byte): 0 RED, 1 sector load, 2 sector load + RED, 3 sector load + CAS (result consumed late),
+ * 4 returning atomic, 5 sector load + CAS + branch on the result (the thread waits: the insert's claim).
+ * mode >> 8: resident 256-thread blocks per SM, 1..8 (0 = 8). */
 int tsxc_k0_region_sweep(tsxc_table* t, uint64_t footprint_bytes, uint64_t region_bytes, uint64_t ops_per_region,
                          uint32_t ops_per_item, int mode, float* ms_out);
 

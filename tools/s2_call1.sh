@@ -20,6 +20,6 @@ mkdir -p gpurun_out
   export TSXC_CHUNK_KEYS=250000000
   CMD="python bench.py --workload c2 --scale 0.0625 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-variants"
   timeout 300 $CMD > gpurun_out/s2_scaled_plain.log 2>&1; echo "rc=$?"; grep "timed steps" gpurun_out/s2_scaled_plain.log
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_insert_keys|k_part_reads|k_part_keys|k_hist_keys|k_hist_reads" --launch-skip 22 -c 12 -o gpurun_out/r02_pipeline_c2_scaled -f $CMD > gpurun_out/s2_ncu_full.log 2>&1
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_insert_keys|k_part_reads|k_part_keys|k_hist_keys|k_hist_reads" --launch-skip 51 -c 8 -o gpurun_out/r02_pipeline_c2_scaled -f $CMD > gpurun_out/s2_ncu_full.log 2>&1
   echo "rc=$?"; tail -3 gpurun_out/s2_ncu_full.log
 } 2>&1 | tee gpurun_out/s2_call1.txt

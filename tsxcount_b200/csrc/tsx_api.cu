@@ -465,6 +465,10 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(t, TSXC_E_CUDA, "device is not sm_100 class");
     CU(cudaSetDevice(device));
+    if (const uint64_t fetch = env_u64("TSXC_L2_FETCH", 0)) {     // experiment: 32 / 64 / 128 bytes per L2 miss (a hint to the driver)
+        if (fetch == 32 || fetch == 64 || fetch == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch);
+        cudaGetLastError();
+    }
     tsxc_table* h = new (std::nothrow) tsxc_table();
     if (!h) return fail(t, TSXC_E_NOMEM, "host allocation failed");
     t = h;
@@ -1287,7 +1291,8 @@ int tsxc_k0_region_sweep(tsxc_table* t, uint64_t footprint_bytes, uint64_t regio
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
     CU(cudaEventRecord(a, t->stream));
-    k_k0_region_sweep<<<t->sms * 8, kBlockThreads, 0, t->stream>>>(t->d_words, rw, fw / rw, ops_per_region, ops_per_item, mode, ticket);
+    const int blocks_per_sm = (mode >> 8) >= 1 && (mode >> 8) <= 8 ? (mode >> 8) : 8;      // bits 8..: resident blocks per SM (default 8)
+    k_k0_region_sweep<<<t->sms * blocks_per_sm, kBlockThreads, 0, t->stream>>>(t->d_words, rw, fw / rw, ops_per_region, ops_per_item, mode & 0xff, ticket);
     CU(cudaEventRecord(b, t->stream));
     CU(cudaEventSynchronize(b));
     CU(cudaGetLastError());

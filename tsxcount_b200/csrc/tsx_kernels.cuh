@@ -413,6 +413,13 @@ __global__ void __launch_bounds__(kBlockThreads) k_k0_region_sweep(uint64_t* __r
                 unsigned long long* p = (unsigned long long*)(words + ((a & ~3ULL) | ((a + pick) & 3ULL)));
                 const unsigned long long old = atomicCAS(p, w[(a + pick) & 3ULL], w[(a + pick) & 3ULL] + (1ULL << 40));
                 sink += old;
+            } else if (mode == 5) {                           // sector load -> CAS -> branch on its result: the thread really waits
+                uint64_t w[4];
+                load_bucket(words + (a & ~3ULL), w);
+                const uint64_t pick = (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x5a5a5a5a5a5a5a5aULL ? 1 : 0;
+                unsigned long long* p = (unsigned long long*)(words + ((a & ~3ULL) | ((a + pick) & 3ULL)));
+                const unsigned long long old = atomicCAS(p, w[(a + pick) & 3ULL], w[(a + pick) & 3ULL] + (1ULL << 40));
+                if (old == 0x5a5a5a5a5a5a5a5aULL) break;
             } else if (mode == 4) {                           // returning atomic only
                 sink += atomicAdd((unsigned long long*)(words + a), 1ULL << 40);
             } else {                                          // sector load only

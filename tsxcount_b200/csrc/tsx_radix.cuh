@@ -157,19 +157,50 @@ __device__ __forceinline__ unsigned match_digit(bool valid, uint32_t digit, uint
 #endif
 }
 
+#ifndef TSX_RANK_CD
+#define TSX_RANK_CD 1
+#endif
+// Digits of 7-8 bits (128-256 bins) rarely collide inside a warp, so two optimistic rounds come first: every
+// pending lane writes its lane id to tag[digit], the lane that reads its own id back owns the counter for this
+// round, takes the old value as its rank and bumps it.  Lanes still pending after two rounds (three or more lanes
+// share a digit: 8 % of the warp steps at 256 bins, nearly always at 64) are ranked by the ballot match.  Ranks are
+// unique per (warp, digit), which is all the counting sort needs (keys are a multiset, stability is irrelevant).
+// ~30 instructions per step instead of ~85: the partition kernels are bound by the integer pipe.
 template <typename CT>
-__device__ __forceinline__ uint32_t rank_in_warp(CT* __restrict__ wcnt, bool valid, uint32_t digit, unsigned lane, uint32_t bits) {
+__device__ __forceinline__ uint32_t rank_in_warp(CT* wcnt, uint8_t* wtag_, bool valid, uint32_t digit, unsigned lane, uint32_t bits) {
+    volatile uint8_t* wtag = wtag_;      // written and read back by different lanes between two __syncwarp()
+    volatile CT* vcnt = wcnt;
     const unsigned full = 0xffffffffu;
-    const unsigned peers = match_digit(valid, digit, bits);
-    const int leader = valid ? (__ffs(peers) - 1) : (int)lane;
+    uint32_t rank = 0;
+    bool pend = valid;
+#if TSX_RANK_CD
+    if (bits >= 7) {
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+            if (pend) wtag[digit] = (uint8_t)lane;
+            __syncwarp();
+            if (pend && wtag[digit] == (uint8_t)lane) {
+                rank = vcnt[digit];
+                vcnt[digit] = (CT)(rank + 1);
+                pend = false;
+            }
+            __syncwarp();
+        }
+        if (!__any_sync(full, pend)) return rank;
+    }
+#else
+    (void)wtag; (void)vcnt;
+#endif
+    const unsigned peers = match_digit(pend, digit, bits);
+    const int leader = pend ? (__ffs(peers) - 1) : (int)lane;
     uint32_t old = 0;
-    if (valid && (unsigned)leader == lane) {
+    if (pend && (unsigned)leader == lane) {
         old = wcnt[digit];
         wcnt[digit] = (CT)(old + __popc(peers));
     }
     old = __shfl_sync(full, old, leader);
     __syncwarp();
-    return old + __popc(peers & ((1u << lane) - 1u));
+    return pend ? old + __popc(peers & ((1u << lane) - 1u)) : rank;
 }
 
 // Exclusive scan of v over the first 256 threads of the block (the others pass 0).  scratch: 8 words of shared
@@ -232,12 +263,14 @@ __device__ __forceinline__ void tile_partition(TileSmem<KW>& sm, const Key<KW> (
                                                uint32_t bits, DigitFn digit, ReserveFn reserve, DstFn dst) {
     constexpr int OPT = RadixCfg<KW>::OPT;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // the ranking's tag rows live in `sorted`, which is idle until the scatter below (a barrier lies in between)
+    uint8_t* tag = reinterpret_cast<uint8_t*>(sm.sorted) + warp * kNB;
     uint32_t rk[OPT];
 #pragma unroll
     for (int j = 0; j < OPT; ++j) {
         const bool v = (vmask >> j) & 1u;
         const uint32_t d = v ? digit(Hs[j].w[0]) : 0u;
-        rk[j] = rank_in_warp<uint16_t>(sm.cnt[warp], v, d, lane, bits) | (d << 16);
+        rk[j] = rank_in_warp<uint16_t>(sm.cnt[warp], tag, v, d, lane, bits) | (d << 16);
     }
     __syncthreads();
     // per bin: totals over the warps; the counters become each warp's offset inside the bin
@@ -292,6 +325,7 @@ k_hist_reads(const __grid_constant__ TableView tv, const __grid_constant__ Radix
              const uint32_t* __restrict__ ends, uint64_t n_words, uint64_t n_bases, uint64_t seg0, uint32_t n_segs,
              uint32_t* __restrict__ seghist, uint32_t* __restrict__ segtotal) {
     __shared__ uint32_t cnt[kRadixWarps][kNB];
+    __shared__ uint8_t tag[kRadixWarps][kNB];
     __shared__ uint32_t scratch[8];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t seg_words = 1ULL << rg.seg_log2;
@@ -308,7 +342,7 @@ k_hist_reads(const __grid_constant__ TableView tv, const __grid_constant__ Radix
                 Key<KW> key;
                 const bool valid = kl.kmer_at(o, tv.L.k, tv.hp, key);
                 const Key<KW> H = hash_key<KW>(key, tv.hp);
-                (void)rank_in_warp<uint32_t>(cnt[warp], valid, digit1_of(rg, tv.lbg_mask, H.w[0]), lane, rg.d1);
+                (void)rank_in_warp<uint32_t>(cnt[warp], tag[warp], valid, digit1_of(rg, tv.lbg_mask, H.w[0]), lane, rg.d1);
             }
         }
         __syncthreads();
@@ -588,6 +622,7 @@ k_hist_keys(const __grid_constant__ TableView tv, const __grid_constant__ RadixG
             const uint64_t* __restrict__ A, uint32_t* __restrict__ fhist) {
     constexpr int OPT = RadixCfg<KW>::OPT;
     __shared__ uint16_t cnt[kRadixWarps][kNB];
+    __shared__ uint8_t tag[kRadixWarps][kNB];
     __shared__ ItemFeed<KW> feed;
     if (!ctl->group.active) return;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -606,7 +641,7 @@ k_hist_keys(const __grid_constant__ TableView tv, const __grid_constant__ RadixG
 #pragma unroll
         for (int j = 0; j < OPT; ++j) {
             const uint64_t i = lo + (uint64_t)j * kRadixThreads + threadIdx.x;
-            (void)rank_in_warp<uint16_t>(cnt[warp], i < hi, digit2_of(rg, tv.lbg_mask, h0[j]), lane, rg.d2);
+            (void)rank_in_warp<uint16_t>(cnt[warp], tag[warp], i < hi, digit2_of(rg, tv.lbg_mask, h0[j]), lane, rg.d2);
         }
         __syncthreads();
         if (threadIdx.x < rg.nb2) {
@@ -697,6 +732,84 @@ k_part_keys(const __grid_constant__ TableView tv, const __grid_constant__ RadixG
 #ifndef TSX_INSERT_MINB
 #define TSX_INSERT_MINB 6
 #endif
+#ifndef TSX_INS_PREFETCH
+#define TSX_INS_PREFETCH 0          // measured: prefetching the next slice's buckets into L2 costs 10 % (221 -> 242 ms on config 2)
+#endif
+
+struct CombSmem {
+    unsigned long long key[kCombSlots];
+    unsigned int cnt[kCombSlots];
+    unsigned int used;
+};
+
+// A slice in which neighbouring keys are equal.  Out of line and with its own statistics, so that the common path of
+// k_insert_keys keeps its registers (inlined, this code cost the kernel ~110 bytes of spills per thread, and spill
+// stores go through to L2: 1.3 sectors per k-mer next to the 2 the insert itself needs).
+template <int KW, int W>
+__device__ __noinline__ void insert_slice_skewed(const TableView& tv, const uint64_t* __restrict__ src, uint64_t lo, uint64_t hi,
+                                                 CombSmem& comb) {
+    constexpr int R = KW == 1 ? 4 : (KW == 2 ? 2 : 1);
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    LocalStats st;
+#pragma unroll 1
+    for (int r = 0; r < R; ++r) {
+        const uint64_t i = lo + (uint64_t)r * kBlockThreads + threadIdx.x;
+        const bool valid = i < hi;
+        Key<KW> H;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) H.w[j] = valid ? __ldcg(src + i * KW + j) : 0ULL;
+        uint64_t cnt = 1;
+        bool lead = valid;
+        unsigned dups = 0;
+        const unsigned vm = __ballot_sync(full, valid);
+        if (valid) {
+            unsigned peers = __match_any_sync(vm, H.w[0]);
+#pragma unroll
+            for (int j = 1; j < KW; ++j) peers &= __match_any_sync(vm, H.w[j]);
+            cnt = (uint64_t)__popc(peers);
+            lead = (unsigned)(__ffs(peers) - 1) == lane;
+        }
+        dups = __popc(vm) - __popc(__ballot_sync(full, lead));
+        if (!lead) continue;
+        if (dups >= 4) {
+            // combine across the block before touching the table
+            const uint32_t slot = (uint32_t)(H.w[0] ^ (H.w[0] >> 40)) & (kCombSlots - 1);
+            const unsigned long long tagged = (H.w[0] & ~0xffffULL) | (unsigned long long)((i - lo) + 1);
+            const unsigned long long oldk = atomicCAS(&comb.key[slot], 0ULL, tagged);
+            bool absorbed = (oldk == 0ULL);
+            if (!absorbed && ((oldk ^ tagged) & ~0xffffULL) == 0ULL) {
+                const uint64_t other = lo + (oldk & 0xffffULL) - 1;
+                absorbed = true;
+#pragma unroll
+                for (int j = 0; j < KW; ++j) absorbed &= (__ldcg(src + other * KW + j) == H.w[j]);
+            }
+            if (absorbed) {
+                atomicAdd(&comb.cnt[slot], (unsigned int)cnt);
+                comb.used = 1u;
+                continue;
+            }
+        }
+        insert_hashed<KW, W, true>(tv, H, cnt, st);
+    }
+    __syncthreads();
+    if (comb.used) {
+        for (uint32_t s = threadIdx.x; s < kCombSlots; s += kBlockThreads) {
+            const unsigned long long tagged = comb.key[s];
+            if (tagged == 0ULL) continue;
+            const uint64_t idx = lo + (tagged & 0xffffULL) - 1;
+            Key<KW> H;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) H.w[j] = __ldcg(src + idx * KW + j);
+            insert_hashed<KW, W, true>(tv, H, (uint64_t)comb.cnt[s], st);
+            comb.key[s] = 0ULL; comb.cnt[s] = 0u;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) comb.used = 0u;
+    }
+    flush_stats(tv, st);
+}
+
 template <int KW, int W, bool WARP_AGG>
 __global__ void __launch_bounds__(kBlockThreads, TSX_INSERT_MINB)
 k_insert_keys(const __grid_constant__ TableView tv, RadixCtl* __restrict__ ctl, const uint64_t* __restrict__ src) {
@@ -704,107 +817,82 @@ k_insert_keys(const __grid_constant__ TableView tv, RadixCtl* __restrict__ ctl, 
     constexpr uint32_t SLICE = kBlockThreads * R;
     const unsigned full = 0xffffffffu;
     __shared__ unsigned long long item_s;
-    __shared__ unsigned long long comb_key[kCombSlots];
-    __shared__ unsigned int comb_cnt[kCombSlots];
-    __shared__ unsigned int comb_used;
+    __shared__ CombSmem comb;
     const unsigned long long n = ctl->n_insert;
     if (n == 0) return;
     LocalStats st;
     const unsigned lane = threadIdx.x & 31u;
-    for (uint32_t i = threadIdx.x; i < kCombSlots; i += kBlockThreads) { comb_key[i] = 0ULL; comb_cnt[i] = 0u; }
-    if (threadIdx.x == 0) comb_used = 0u;
+    for (uint32_t i = threadIdx.x; i < kCombSlots; i += kBlockThreads) { comb.key[i] = 0ULL; comb.cnt[i] = 0u; }
+    if (threadIdx.x == 0) comb.used = 0u;
     const unsigned long long n_items = (n + SLICE - 1) / SLICE;
-    // thread 0 keeps the ticket of the next slice in flight while the block works on the current one
-    unsigned long long ahead = threadIdx.x == 0 ? atomicAdd(&ctl->ticket[2], 1ULL) : 0ULL;
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            item_s = ahead;
-            if (ahead < n_items) ahead = atomicAdd(&ctl->ticket[2], 1ULL);
-        }
-        __syncthreads();
-        const unsigned long long item = item_s;
-        if (item >= n_items) break;
-        const uint64_t lo = item * SLICE;
+    // Optional software pipeline over slices (TSX_INS_PREFETCH): while the block inserts the keys of slice j, the home
+    // buckets of slice j+1 are requested into L2.  Thread 0 always keeps one more ticket in flight.
+    auto prefetch_slice = [&](unsigned long long it) {
+#if TSX_INS_PREFETCH
+        if (it >= n_items) return;
+        const uint64_t lo = it * SLICE;
         const uint64_t hi = lo + SLICE < n ? lo + SLICE : n;
-        Key<KW> Hs[R];
-        bool dup = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const uint64_t i = lo + (uint64_t)r * kBlockThreads + threadIdx.x;
-#pragma unroll
-            for (int j = 0; j < KW; ++j) Hs[r].w[j] = i < hi ? __ldcs(src + i * KW + j) : 0ULL;
+            if (i < hi) prefetch_bucket_l2(tv.words + ((((__ldcg(src + i * KW) & tv.lbl_mask) + 1) & tv.lbl_mask) << 2));
         }
+#else
+        (void)it;
+#endif
+    };
+    unsigned long long ahead = 0ULL;
+    if (threadIdx.x == 0) {
+        item_s = atomicAdd(&ctl->ticket[2], 1ULL); ahead = atomicAdd(&ctl->ticket[2], 1ULL);
+        if (blockIdx.x == 0) atomicAdd(tv.ctr + CTR_ADDED, n);      // all keys of the launch; insert_hashed<LEAN> takes back what it skips
+    }
+    __syncthreads();
+    unsigned long long item = item_s;
+    prefetch_slice(item);
+    while (item < n_items) {
+        __syncthreads();                                  // everyone has read item_s
+        if (threadIdx.x == 0) {
+            // once the reprobe limit was reached anywhere the run is lost (the reference exits with 42): stop early
+            const bool full_table = (__ldcg(tv.ctr + CTR_ERRORS) & (unsigned long long)ERR_TABLE_FULL) != 0ULL;
+            item_s = full_table ? n_items : ahead;
+            if (ahead < n_items) ahead = atomicAdd(&ctl->ticket[2], 1ULL);
+        }
+        __syncthreads();
+        const unsigned long long item_next = item_s;
+        const uint64_t lo = item * SLICE;
+        const uint64_t hi = lo + SLICE < n ? lo + SLICE : n;
+        item = item_next;
+        prefetch_slice(item_next);
+        // Pass 1 reads word 0 of the thread's keys only to see whether neighbours are equal; pass 2 reads the keys
+        // again (L1 / L2 hits) one at a time with the next one in flight.  Holding all R keys across the inserts
+        // instead costs 6-14 registers, which at 6 resident blocks per SM means spills.
+        bool dup = false;
         if (WARP_AGG) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const uint64_t i = lo + (uint64_t)r * kBlockThreads + threadIdx.x;
-                const uint64_t nb = __shfl_down_sync(full, Hs[r].w[0], 1);
-                dup |= (lane < 31u) && (i + 1 < hi) && (nb == Hs[r].w[0]);
+                const uint64_t k0 = i < hi ? __ldg(src + i * KW) : 0ULL;
+                const uint64_t nb = __shfl_down_sync(full, k0, 1);
+                dup |= (lane < 31u) && (i + 1 < hi) && (nb == k0);
             }
         }
-        const bool skew = WARP_AGG && __syncthreads_or(dup ? 1 : 0);
-        if (!skew) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint64_t i = lo + (uint64_t)r * kBlockThreads + threadIdx.x;
-                if (i < hi) insert_hashed<KW, W>(tv, Hs[r], 1, st);
-            }
+        if (WARP_AGG && __syncthreads_or(dup ? 1 : 0)) {
+            insert_slice_skewed<KW, W>(tv, src, lo, hi, comb);
             continue;
         }
-        // ---- skewed slice ----
+        uint64_t i = lo + threadIdx.x;
+        Key<KW> H;
 #pragma unroll
+        for (int j = 0; j < KW; ++j) H.w[j] = i < hi ? __ldcs(src + i * KW + j) : 0ULL;
+#pragma unroll 1
         for (int r = 0; r < R; ++r) {
-            const uint64_t i = lo + (uint64_t)r * kBlockThreads + threadIdx.x;
-            const bool valid = i < hi;
-            const Key<KW> H = Hs[r];
-            uint64_t cnt = 1;
-            bool lead = valid;
-            unsigned dups = 0;
-            const unsigned vm = __ballot_sync(full, valid);
-            if (valid) {
-                unsigned peers = __match_any_sync(vm, H.w[0]);
+            const uint64_t i_next = i + kBlockThreads;
+            Key<KW> Hn;
 #pragma unroll
-                for (int j = 1; j < KW; ++j) peers &= __match_any_sync(vm, H.w[j]);
-                cnt = (uint64_t)__popc(peers);
-                lead = (unsigned)(__ffs(peers) - 1) == lane;
-            }
-            dups = __popc(vm) - __popc(__ballot_sync(full, lead));
-            if (!lead) continue;
-            if (dups >= 4) {
-                // combine across the block before touching the table
-                const uint32_t slot = (uint32_t)(H.w[0] ^ (H.w[0] >> 40)) & (kCombSlots - 1);
-                const unsigned long long tagged = (H.w[0] & ~0xffffULL) | (unsigned long long)((i - lo) + 1);
-                const unsigned long long oldk = atomicCAS(&comb_key[slot], 0ULL, tagged);
-                bool absorbed = (oldk == 0ULL);
-                if (!absorbed && ((oldk ^ tagged) & ~0xffffULL) == 0ULL) {
-                    const uint64_t other = lo + (oldk & 0xffffULL) - 1;
-                    absorbed = true;
-#pragma unroll
-                    for (int j = 0; j < KW; ++j) absorbed &= (__ldcg(src + other * KW + j) == H.w[j]);
-                }
-                if (absorbed) {
-                    atomicAdd(&comb_cnt[slot], (unsigned int)cnt);
-                    comb_used = 1u;
-                    continue;
-                }
-            }
-            insert_hashed<KW, W>(tv, H, cnt, st);
-        }
-        __syncthreads();
-        if (comb_used) {
-            for (uint32_t s = threadIdx.x; s < kCombSlots; s += kBlockThreads) {
-                const unsigned long long tagged = comb_key[s];
-                if (tagged == 0ULL) continue;
-                const uint64_t idx = lo + (tagged & 0xffffULL) - 1;
-                Key<KW> H;
-#pragma unroll
-                for (int j = 0; j < KW; ++j) H.w[j] = __ldcg(src + idx * KW + j);
-                insert_hashed<KW, W>(tv, H, (uint64_t)comb_cnt[s], st);
-                comb_key[s] = 0ULL; comb_cnt[s] = 0u;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) comb_used = 0u;
+            for (int j = 0; j < KW; ++j) Hn.w[j] = (r + 1 < R && i_next < hi) ? __ldcs(src + i_next * KW + j) : 0ULL;
+            if (i < hi) insert_hashed<KW, W, true>(tv, H, 1, st);
+            H = Hn;
+            i = i_next;
         }
     }
     flush_stats(tv, st);

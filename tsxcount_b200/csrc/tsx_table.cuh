@@ -190,7 +190,7 @@ __device__ __forceinline__ void flush_stats(const TableView& tv, const LocalStat
     const unsigned full = 0xffffffffu;
     uint32_t d = __reduce_add_sync(full, st.distinct);
     uint32_t o = __reduce_add_sync(full, st.overflow);
-    uint32_t m = __reduce_max_sync(full, st.maxprobe);
+    uint32_t m = __reduce_max_sync(full, st.maxprobe > 1u ? st.maxprobe : (st.distinct ? 1u : 0u));
     uint32_t e = __reduce_or_sync(full, st.errors);
     uint64_t a = st.added;
 #pragma unroll
@@ -230,13 +230,16 @@ __device__ __forceinline__ Stored<KW, W> make_stored(const TableView& tv, const 
 
 // Add `amount` to the overflow entry of the primary found at probe i / slot pslot.
 // Reference: handleOverflow, TSXHashMapPerf.h:699-881 (probe on at reprobes i+j, tag = (i, j)).
+// Out of line (rare) and WITHOUT a LocalStats reference: a reference handed to a non-inlined function forces the
+// caller's statistics into local memory for the whole kernel (ncu showed 2 LDL + 3 STL per inserted k-mer, and spill
+// stores go through to L2: 1.3 sectors per k-mer).  Returns error flags | 0x100 if a new overflow entry was created.
+constexpr uint32_t kOvfCreated = 0x100u;
 template <int KW, int W>
-__device__ __noinline__ void overflow_add(const TableView& tv, uint64_t home, uint32_t i, uint32_t pslot, uint64_t amount,
-                                          LocalStats& st) {
+__device__ __noinline__ uint32_t overflow_add_raw(const TableView& tv, uint64_t home, uint32_t i, uint32_t pslot, uint64_t amount) {
     constexpr int SPB = 4 / W;
     const uint64_t tag0 = (uint64_t)i | tv.f_ovf | ((uint64_t)pslot << (tv.L.R + 3));
     const uint32_t cbits = 64 - tv.L.cshift;
-    if (amount >> cbits) { st.errors |= ERR_SATURATED; return; }
+    if (amount >> cbits) return ERR_SATURATED;
     for (uint32_t j = 1; j <= tv.L.max_probe; ++j) {
         const uint64_t tag = tag0 | ((uint64_t)j << (tv.L.R + 5));
         uint64_t* bp = tv.words + (((home + tri(i + j)) & tv.lbl_mask) << 2);
@@ -252,22 +255,29 @@ __device__ __noinline__ void overflow_add(const TableView& tv, uint64_t home, ui
                 if (W == 2) {
                     uint64_t o0, o1;
                     cas128(bp + sl * W, 0, 0, 0, nh, o0, o1);
-                    if (o0 == 0 && o1 == 0) { st.overflow++; return; }
+                    if (o0 == 0 && o1 == 0) return kOvfCreated;
                     h = o1;
                 } else {
                     const uint64_t old = atomicCAS((unsigned long long*)hp, 0ULL, (unsigned long long)nh);
-                    if (old == 0) { st.overflow++; return; }
+                    if (old == 0) return kOvfCreated;
                     h = old;
                 }
             }
             if ((h & tv.tag_mask) == tag) {
                 const uint64_t old = atomicAdd((unsigned long long*)hp, (unsigned long long)(amount << tv.L.cshift));
-                if (((old >> tv.L.cshift) + amount) >> cbits) st.errors |= ERR_SATURATED;
-                return;
+                return (((old >> tv.L.cshift) + amount) >> cbits) ? (uint32_t)ERR_SATURATED : 0u;
             }
         }
     }
-    st.errors |= ERR_TABLE_FULL;
+    return ERR_TABLE_FULL;
+}
+
+template <int KW, int W>
+__device__ __forceinline__ void overflow_add(const TableView& tv, uint64_t home, uint32_t i, uint32_t pslot, uint64_t amount,
+                                             LocalStats& st) {
+    const uint32_t r = overflow_add_raw<KW, W>(tv, home, i, pslot, amount);
+    st.errors |= r & 0xffu;
+    st.overflow += r >> 8;
 }
 
 // value += count on a matched primary; propagates the carry.  Reference: incrementElement_key_value,
@@ -296,13 +306,20 @@ __device__ __forceinline__ void add_to_primary(const TableView& tv, uint64_t* hp
 // TSXHashMapCAS.h:268-508.  Lock-free: an entry's key bits are immutable once written, a thread moves
 // past a slot only after it has seen it occupied by a different key, and every thread claims the
 // lowest free slot of a bucket, so a k-mer can never be stored twice.
-template <int KW, int W>
+//
+// LEAN (k_insert_keys): the statistics that change with every k-mer are reduced to `distinct`, so that the kernel fits
+// 40 registers without spilling in its inner loop.  The caller credits all its keys to CTR_ADDED up front and this
+// function takes back the ones it does not insert; the reprobe limit is published at once (the kernel polls the flag
+// per slice) instead of being remembered per thread.
+template <int KW, int W, bool LEAN = false>
 __device__ __forceinline__ void insert_hashed(const TableView& tv, const Key<KW>& H, uint64_t count, LocalStats& st) {
     constexpr int SPB = 4 / W;
     const Stored<KW, W> s = make_stored<KW, W>(tv, H);
-    if (!s.owned) { st.errors |= ERR_WRONG_SHARD; return; }
-    if (st.errors & ERR_TABLE_FULL) return;        // this thread already hit the reprobe limit: the run is lost (exit 42)
-    st.added += count;
+    if (!s.owned) { st.errors |= ERR_WRONG_SHARD; if (LEAN) st.added -= count; return; }
+    if (!LEAN) {
+        if (st.errors & ERR_TABLE_FULL) return;    // this thread already hit the reprobe limit: the run is lost (exit 42)
+        st.added += count;
+    }
     const uint64_t vmask = low_mask(tv.L.V);
     for (uint32_t i = 1; i <= tv.L.max_probe; ++i) {
         uint64_t* bp = tv.words + (((s.bucket + tri(i)) & tv.lbl_mask) << 2);
@@ -341,7 +358,7 @@ __device__ __forceinline__ void insert_hashed(const TableView& tv, const Key<KW>
                 }
                 if (won) {
                     st.distinct++;
-                    if (i > st.maxprobe) st.maxprobe = i;
+                    if (i > 1 && i > st.maxprobe) st.maxprobe = i;     // probe 1 is implied by distinct > 0 (flush_stats)
                     const uint64_t ov = tv.L.V >= 64 ? 0 : (count >> tv.L.V);
                     if (ov) {
                         overflow_add<KW, W>(tv, s.bucket, i, sl, ov, st);
@@ -377,6 +394,7 @@ __device__ __forceinline__ void insert_hashed(const TableView& tv, const Key<KW>
         if (retry_bucket) { --i; continue; }
     }
     st.errors |= ERR_TABLE_FULL;
+    if (LEAN) atomicOr(tv.ctr + CTR_ERRORS, (unsigned long long)ERR_TABLE_FULL);
 }
 
 // Out-of-line copy for kernels where inserting is the rare path (phase A of the two-phase insert): keeps the
