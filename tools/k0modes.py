@@ -12,13 +12,18 @@ import tsxcount_b200 as tsx  # noqa: E402
 lib = tsx._lib.load()
 hm = tsx.TSXHashMapCUDA(34, 0, 31)
 tb = hm.stats()["table_bytes"]
-NAMES = {1: "load", 2: "load+red", 3: "load+cas(late use)", 5: "load+cas+wait", 4: "atomic(returning)", 0: "red"}
+NAMES = {1: "load", 2: "load+red", 3: "load+cas(late use)", 5: "load+cas+wait", 4: "atomic(returning)", 0: "red",
+         6: "load+cas32+wait", 7: "load+add64(returning)+wait", 8: "load+add32(returning)+wait", 9: "load+exch64+wait",
+         10: "load+or64(returning)+wait"}
 density = 0.93
-for region_kb in (128, 1024, 8192, 16384):
+REGIONS = [int(x) for x in os.environ.get('K0_REGIONS_KIB', '128,1024,8192,16384').split(',')]
+MODES = [int(x) for x in os.environ.get('K0_MODES', '1,2,3,5').split(',')]
+BPS = [int(x) for x in os.environ.get('K0_BPS', '8,6,5').split(',')]
+for region_kb in REGIONS:
     rb = region_kb << 10
     sectors = rb // 32
-    for mode in (1, 2, 3, 5):
-        for bps in (8, 6, 5):
+    for mode in MODES:
+        for bps in BPS:
             if mode in (1,) and bps != 8:
                 continue
             ops_per_region = int(sectors * density)

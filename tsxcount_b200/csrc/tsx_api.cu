@@ -67,7 +67,7 @@ struct tsxc_table {
     // region-sorted insert pipeline (tsx_radix.cuh): S0 histogram, S1/S2 radix partition, phase B insert
     RadixGeom rg{};
     bool radix_on = false;                                     // tables this large take the pipeline by default
-    uint32_t region_log2 = 23;                                 // target size of a fine table region (bytes, log2)
+    uint32_t region_log2 = 25;                                 // target size of a fine table region (bytes, log2)
     RadixCtl* d_ctl = nullptr;
     uint32_t* d_seghist = nullptr; size_t cap_seghist = 0;     // S0: counts per (segment, digit 1)
     uint32_t* d_segtotal = nullptr; size_t cap_segtotal = 0;

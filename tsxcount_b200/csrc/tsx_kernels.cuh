@@ -420,6 +420,18 @@ __global__ void __launch_bounds__(kBlockThreads) k_k0_region_sweep(uint64_t* __r
                 unsigned long long* p = (unsigned long long*)(words + ((a & ~3ULL) | ((a + pick) & 3ULL)));
                 const unsigned long long old = atomicCAS(p, w[(a + pick) & 3ULL], w[(a + pick) & 3ULL] + (1ULL << 40));
                 if (old == 0x5a5a5a5a5a5a5a5aULL) break;
+            } else if (mode >= 6 && mode <= 10) {             // sector load -> some other returning atomic -> wait
+                uint64_t w[4];
+                load_bucket(words + (a & ~3ULL), w);
+                const uint64_t pick = (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x5a5a5a5a5a5a5a5aULL ? 1 : 0;
+                unsigned long long* p = (unsigned long long*)(words + ((a & ~3ULL) | ((a + pick) & 3ULL)));
+                unsigned long long old;
+                if (mode == 6) old = atomicCAS((unsigned int*)p, (unsigned int)w[(a + pick) & 3ULL], (unsigned int)w[(a + pick) & 3ULL] + 1u);
+                else if (mode == 7) old = atomicAdd(p, 1ULL << 40);
+                else if (mode == 8) old = atomicAdd((unsigned int*)p, 1u);
+                else if (mode == 9) old = atomicExch(p, w[(a + pick) & 3ULL] + 1ULL);
+                else old = atomicOr(p, 1ULL << (i & 31u));
+                if (old == 0x5a5a5a5a5a5a5a5aULL) break;
             } else if (mode == 4) {                           // returning atomic only
                 sink += atomicAdd((unsigned long long*)(words + a), 1ULL << 40);
             } else {                                          // sector load only
