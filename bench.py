@@ -408,7 +408,7 @@ def main():
             launches += st["kernel_launches"]
             clear_ms.append(1e3 * clear_s)
             step_ms.append(st["step_ms"])
-            phases.append({"hist": st["hist_ms"], "part1": st["part1_ms"], "part2": st["part2_ms"], "insert": st["insert_ms"]})
+            phases.append({"hist": st["hist_ms"], "part1": st["part1_ms"], "insert": st["insert_ms"]})
         clocks = sampler.stop()
         log(f"{w['name']} timed steps: {[round(x, 1) for x in step_ms]} ms; phases {phases[-1]}")
         res = {"w": w, "n_kmers": n_kmers, "n_reads": n_reads, "n_words": n_words, "read_len": read_len, "k": k, "l": l,
@@ -459,13 +459,18 @@ def main():
             region = layout["table_bytes"] >> fine_bits
             passes = max(1, -(-n_kmers // max(1, st["chunk_cap_keys"])))
             touches = (n_kmers / passes) / (layout["table_bytes"] / 32)
-            ms = C.c_float(0)
-            for _ in range(2):
-                tsx._lib.check(lib.tsxc_k0_region_sweep(hm.handle, layout["table_bytes"], region, int(touches * region / 32), 2048, 2,
-                                                        C.byref(ms)), hm.handle)
             total_ops = int(touches * region / 32) * (layout["table_bytes"] // region)
-            k0r = {"g_ops_per_s": total_ops / ms.value / 1e6, "region_bytes": region, "touches_per_sector": touches,
-                   "ops_per_item": 2048, "passes_per_step": passes}
+            rates = {}
+            # mode 2: sector load + fire-and-forget RED; mode 5: sector load + CAS whose result the thread needs (what an
+            # insert does: profiles/r02_k0r_modes.md); 6 resident blocks per SM like k_insert_keys
+            for mode, name in ((2, "load_red"), (5, "load_cas")):
+                ms = C.c_float(0)
+                for _ in range(2):
+                    tsx._lib.check(lib.tsxc_k0_region_sweep(hm.handle, layout["table_bytes"], region, int(touches * region / 32), 1024,
+                                                            mode | (6 << 8), C.byref(ms)), hm.handle)
+                rates[name] = total_ops / ms.value / 1e6
+            k0r = {"g_ops_per_s": rates["load_cas"], "load_red_g_ops_per_s": rates["load_red"], "region_bytes": region,
+                   "touches_per_sector": touches, "ops_per_item": 1024, "passes_per_step": passes}
         hm.clear(); hm.sync()
         log(f"K0: {k0}  K0r: {k0r}")
         return {"k0": k0, "k0r": k0r}
@@ -548,15 +553,15 @@ def main():
                        "and traffic are per step",
                 "algorithmic_bytes_per_kmer": dom_bytes, "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / ms_per_step,
                 "whole_step": {"algorithmic_bytes_per_kmer": algo_b, "achieved": step_gbs, "frac": step_gbs / peak},
-                "phase_ms": ph, "chunk_cap_keys": st["chunk_cap_keys"], "group_cap_keys": st["group_cap_keys"]}
+                "phase_ms": ph, "chunk_cap_keys": st["chunk_cap_keys"], "page_keys": st["group_cap_keys"]}
     if pipeline:
         # what every kernel of the pipeline streams per k-mer BY DESIGN (not credited as algorithmic work)
-        design = {"hist": ("k_hist_reads (S0)", in_b), "part1": ("k_part_reads (S1)", in_b + E),
-                  "part2": ("k_hist_keys + k_part_keys (S2)", 3 * E), "insert": ("k_insert_keys (B)", 3 * E)}
+        design = {"hist": ("k_count_segs + k_plan_chunks (plan; k_hist_reads in exact mode)", in_b / 2),
+                  "part1": ("k_part_reads (S1)", in_b + E), "insert": ("k_build_slices + k_insert_keys (B)", 3 * E)}
         roofline["kernels"] = [{"kernel": design[p][0], "ms_per_step": ph[p], "share_of_step": ph[p] / ms_per_step,
                                 "design_bytes_per_kmer": design[p][1],
                                 "design_GB_s": n_kmers * design[p][1] / (ph[p] * 1e-3) / 1e9 if ph[p] else None}
-                               for p in ("hist", "part1", "part2", "insert")]
+                               for p in ("hist", "part1", "insert")]
     k0 = r.get("k0") or {}
     roofline_rand8 = None
     if k0:
@@ -564,8 +569,9 @@ def main():
         denom = k0r["g_ops_per_s"] if k0r else k0["k0"]["sector_load_plus_atomic"]
         roofline_rand8 = {"achieved": value, "unit": "G RMW/s", "peak": denom, "frac": value / denom,
                           "insert_kernel_alone": {"achieved": n_kmers / (dom_ms * 1e-3) / 1e9, "frac": n_kmers / (dom_ms * 1e-3) / 1e9 / denom},
-                          "peak_is": "K0r: dependent sector load + atomicAdd, all blocks sweeping the table region by region, measured "
-                                     "live at this run's region size and touches per sector" if k0r else "K0 uniform sector load + atomic",
+                          "peak_is": "K0r: dependent sector load + CAS whose result the thread needs, all blocks sweeping the table region by "
+                                     "region, measured live at this run's region size and touches per sector (load + fire-and-forget "
+                                     "RED, which no insert can use, is reported beside it)" if k0r else "K0 uniform sector load + atomic",
                           "k0r": k0r, "k0_uniform": k0["k0"],
                           "note": "achieved = whole-step k-mers/s (one RMW per k-mer by SURVEY.md §8d) over the measured RMW rate"}
 

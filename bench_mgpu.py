@@ -37,7 +37,7 @@ def parity_check(wl, rank, world, local_rank, n_reads=20_000, l_small=22, region
     _lib.check(lib.tsxc_gen_reads_device(C.byref(gp), rank * n_reads, n_reads, local_rank, None, d_packed.data_ptr(), d_off.data_ptr()))
     torch.cuda.synchronize()
     old = {v: os.environ.get(v) for v in ("TSXC_REGION_LOG2", "TSXC_SEG_LOG2", "TSXC_CHUNK_KEYS")}
-    os.environ["TSXC_REGION_LOG2"] = region_log2      # small regions: both radix digits are exercised
+    os.environ["TSXC_REGION_LOG2"] = region_log2      # small regions: the small shards take the routed pipeline
     os.environ["TSXC_SEG_LOG2"] = "11"                # several segments, several rounds
     try:
         be = CudaRouteBackend(k, l_small + shard_bits, 0, rank, world, local_rank)
@@ -176,7 +176,7 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None, extra_work
                "device_ms_per_step": 1e3 * T_dev / args.steps, "kmers_per_step": n_kmers * world, "distinct": total_distinct,
                "launches": launches, "clocks": clocks, "layout": layout, "rounds_per_step": sc.rounds // max(1, sc.batches),
                # of the LAST timed step (tsxc_clear resets the accounting): CUDA events around each phase's launches
-               "phase_ms_rank0": {"hist": st["hist_ms"], "route": st["part1_ms"], "sort": st["part2_ms"], "insert": st["insert_ms"]},
+               "phase_ms_rank0": {"hist": st["hist_ms"], "route": st["part1_ms"], "insert": st["insert_ms"]},
                "n_kmers_rank": n_kmers, "read_len": read_len, "k": k, "l_global": l_global,
                "recv_cap_keys": sc.recv_cap}
         # e2e: the rank's reads start in pinned host memory; H2D copy + routed counting + global distinct read-back
@@ -246,7 +246,7 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None, extra_work
             "device_ms_per_step": main["device_ms_per_step"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_part_reads (routing, peer stores) + k_part_keys + k_insert_keys (per GPU)",
+                         "kernel": "k_hist_reads + k_part_reads (routing, peer stores) + k_insert_keys (per GPU)",
                          "algorithmic_bytes_per_kmer": 2 * E + in_b, "phase_ms_rank0": main["phase_ms_rank0"]},
             "nvlink": {"sent_bytes_per_gpu_per_step": sent,
                        "GB_s_per_gpu_per_direction_during_routing": (sent / (route_ms * 1e-3) / 1e9) if route_ms else None,

@@ -93,7 +93,7 @@ typedef struct tsxc_stats_t {
     double   part1_ms;            /*                     S1 (extract+hash+tile sort by digit 1) */
     double   part2_ms;            /*                     S2 (digit-2 histogram, scan, tile sort by digit 2) */
     uint64_t chunk_cap_keys;      /* capacity of key buffer A: k-mers per insert pass (0 until the pipeline ran) */
-    uint64_t group_cap_keys;      /* capacity of key buffer B */
+    uint64_t group_cap_keys;      /* keys per page of the paged key buffer (0: bins have exact offsets) */
     uint32_t radix_digit1_bits, radix_digit2_bits;
 } tsxc_stats_t;
 

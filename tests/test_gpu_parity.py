@@ -365,11 +365,17 @@ def test_route_receive_overflow_is_reported_not_dropped(tsx, monkeypatch):
 
 
 # ---- the region-sorted insert pipeline (tsx_radix.cuh) on small tables ----------------------------------------
-@pytest.fixture(params=["12", "16"], ids=["two_digits", "one_digit"])
+@pytest.fixture(params=["12", "16", "18"], ids=["exact_1024_bins", "exact_128_bins", "paged_32_bins"])
 def small_regions(monkeypatch, request):
-    """Tables of 512 MiB and more take the pipeline; shrink the fine regions so that small tables do too
-    (4 KiB regions: both radix digits; 64 KiB regions: digit 1 only)."""
+    """Tables of 512 MiB and more take the pipeline; shrink the table regions so that small tables do too.  8 MiB
+    tables: 4 KiB regions = the full 10-bit digit, 64 KiB regions = 7 bits (both with exact bin offsets from the
+    histogram pass: with pages of one slice the key buffer is too small for a page pool), 256 KiB regions = 32 bins of
+    a paged pool with 32-key pages.  The key buffer holds 200 000 k-mers, so most tests need two or three chunks."""
     monkeypatch.setenv("TSXC_REGION_LOG2", request.param)
+    monkeypatch.setenv("TSXC_SEG_LOG2", "9")
+    monkeypatch.setenv("TSXC_CHUNK_KEYS", "200000")
+    if request.param == "18":
+        monkeypatch.setenv("TSXC_PAGE_LOG2", "5")
     monkeypatch.setenv("TSXC_LOOKUP_SORT_MIN", "1000")      # batched lookups of these tests are sorted by region too
 
 
@@ -387,18 +393,34 @@ def test_pipeline_parity(tsx, small_regions, case):
 
 
 @pytest.mark.parametrize("case", [PART_CASES[0], PART_CASES[4], PART_CASES[7]], ids=lambda c: c[0])
-def test_pipeline_many_chunks_and_groups(tsx, monkeypatch, case):
-    """Key buffers far smaller than the batch: the planner cuts it into several chunks (insert passes), every chunk
-    into several groups of buffer B; segments of one block round make chunk boundaries fall inside reads."""
+def test_pipeline_many_chunks_exact_offsets(tsx, monkeypatch, case):
+    """A key buffer far smaller than the batch: the planner cuts it into several chunks (insert passes); segments of
+    one block round make chunk boundaries fall inside reads.  Bins get exact offsets from the histogram pass."""
     monkeypatch.setenv("TSXC_REGION_LOG2", "12")
     monkeypatch.setenv("TSXC_SEG_LOG2", "9")
     monkeypatch.setenv("TSXC_CHUNK_KEYS", "70000")
-    monkeypatch.setenv("TSXC_GROUP_KEYS", "9000")
     name, gen, n_reads, read_len, k, l, s, flags = case
     seqs = orc.gen_reads(n_reads=n_reads, read_len=read_len, **gen)
     st, oc = run_case(tsx, seqs, k, l, s, flags)
-    assert st["chunk_cap_keys"] == 70000 and st["group_cap_keys"] == 9000
-    assert st["main_kernel_launches"] >= 3 * (2 + 5 * 7)
+    assert st["chunk_cap_keys"] == 70000 and st["group_cap_keys"] == 0          # no page pool
+    if oc.n_total > 140000:
+        assert st["main_kernel_launches"] >= 2 + 3 * 4
+
+
+@pytest.mark.parametrize("k,l,chunk,page_log2", [(31, 20, 1_000_000, 4), (63, 19, 600_000, 4), (127, 18, 300_000, 3)])
+def test_pipeline_paged_bins_many_pages_many_chunks(tsx, monkeypatch, k, l, chunk, page_log2):
+    """The page pool under load: 32 bins, pages of 16 / 8 keys (every tile run crosses pages, most runs take several
+    fresh pages at once), a pool that the batch fills several times over (several chunks); reads sampled from a
+    small genome so that the table holds them."""
+    monkeypatch.setenv("TSXC_REGION_LOG2", "18")
+    monkeypatch.setenv("TSXC_SEG_LOG2", "9")
+    monkeypatch.setenv("TSXC_PAGE_LOG2", str(page_log2))
+    monkeypatch.setenv("TSXC_CHUNK_KEYS", str(chunk))
+    seqs = orc.gen_reads(seed=0xBEEF + k, n_reads=30000, read_len=150, mode=3, genome_len=40_000, sub_rate_q16=40)
+    st, oc = run_case(tsx, seqs, k, l, 0)
+    assert st["group_cap_keys"] == 1 << page_log2                               # the page size: the pool is in use
+    assert oc.n_total > 2 * chunk
+    assert st["main_kernel_launches"] >= 2 + 2 * 5
 
 
 def test_pipeline_ragged_reads_and_repeats(tsx, small_regions):
@@ -507,7 +529,8 @@ def test_reference_pinned_fixtures(tsx, tmp_path):
 
 # ---- the default two-phase configuration at a size the oracle cannot count: size-independent properties ----
 def test_large_default_path_properties(tsx):
-    """2.4e8 uniform 31-mers into a 4 GiB table (512 regions of 8 MiB: the default geometry).  Properties: every k-mer is added exactly once (sum of counts), all are distinct (a duplicate
+    """2.4e8 uniform 31-mers into a 4 GiB table (32 regions of 128 MiB, pages of 1024 k-mers: the default geometry).
+    Properties: every k-mer is added exactly once (sum of counts), all are distinct (a duplicate
     has probability ~1e-2 at this size), sampled k-mers regenerated by the oracle are present with count 1 and
     absent ones with 0; a second pass doubles every sampled count and leaves the distinct count unchanged."""
     lib = tsx._lib.load()
@@ -532,7 +555,7 @@ def test_large_default_path_properties(tsx):
                 assert st["error_flags"] == 0 and st["kmers_added"] == rep * n_kmers
                 assert st["distinct"] == n_kmers
                 assert st["main_kernel_launches"] >= 4 * rep          # the pipeline ran
-                assert st["radix_digit1_bits"] == 8 and st["radix_digit2_bits"] == 1
+                assert st["radix_digit1_bits"] == 5 and st["radix_digit2_bits"] == 0 and st["group_cap_keys"] == 1024
                 assert np.array_equal(hm.getKmerCounts(oc.keys_kw(1)), rep * oc.counts)
                 assert hm.getKmerCounts(other.keys_kw(1)).sum() == 0
     finally:

@@ -65,15 +65,20 @@ struct tsxc_table {
     char* d_text = nullptr; size_t cap_text = 0;            // dump lines formatted on the device
     uint64_t* d_pairs[2] = {nullptr, nullptr}; size_t cap_pairs[2] = {0, 0};   // region-sorted lookups: (hash, index) records
     // region-sorted insert pipeline (tsx_radix.cuh): S0 histogram, S1/S2 radix partition, phase B insert
-    RadixGeom rg{};
+    RadixGeom rg{};                                            // the insert pipeline: one digit of up to 10 bits
+    RadixGeom rg_lookup{};                                     // region-sorted lookups: two digits of up to 8 bits
+    PageGeom pg{};                                             // how buffer A is addressed (paged pool / exact offsets)
+    int part_grid = 0;                                         // thread blocks of S1 the page pool was planned for
     bool radix_on = false;                                     // tables this large take the pipeline by default
-    uint32_t region_log2 = 25;                                 // target size of a fine table region (bytes, log2)
+    uint32_t region_log2 = 27;                                 // target size of a table region (bytes, log2)
+    uint16_t* d_page_bin = nullptr; size_t cap_page_bin = 0;   // paged mode: bin of every pool page
+    uint16_t* d_page_len = nullptr; size_t cap_page_len = 0;   //             keys in it
+    ulonglong2* d_slices = nullptr; size_t cap_slices = 0;     // phase B work items: (first key, keys)
     RadixCtl* d_ctl = nullptr;
     uint32_t* d_seghist = nullptr; size_t cap_seghist = 0;     // S0: counts per (segment, digit 1)
     uint32_t* d_segtotal = nullptr; size_t cap_segtotal = 0;
     uint64_t* d_segprefix = nullptr; size_t cap_segprefix = 0;
     uint64_t* d_A = nullptr; uint64_t cap_A = 0;               // keys, sorted by digit 1 (multi-GPU: the receive buffer)
-    uint64_t* d_B = nullptr; uint64_t cap_B = 0;               // keys, one group of A sorted by fine region
     bool cap_A_limited = false;                                // cap_A was set by free memory, not by a batch size
     uint32_t* d_fhist = nullptr;                               // kMaxFine
     unsigned long long* d_fcur = nullptr;                      // kMaxFine
@@ -150,12 +155,14 @@ void collect_main_ms(tsxc_table* t) {  // caller has synchronized the stream
 // The pipeline's key buffers take whatever HBM the table leaves free; anything else that needs memory later
 // (staging slots, lookup buffers) may claim it back: the buffers are re-sized at the next batch.
 int release_radix_buffers(tsxc_table* t) {
-    if (!t->d_A && !t->d_B) return TSXC_OK;
+    if (!t->d_A) return TSXC_OK;
     if (t->peers_set) return TSXC_OK;          // exported to peers: must stay where it is
     CU(cudaStreamSynchronize(t->stream));
-    if (t->d_A) { CU(cudaFree(t->d_A)); t->d_A = nullptr; }
-    if (t->d_B) { CU(cudaFree(t->d_B)); t->d_B = nullptr; }
-    t->cap_A = t->cap_B = 0; t->cap_A_limited = false;
+    CU(cudaFree(t->d_A)); t->d_A = nullptr;
+    if (t->d_page_bin) { CU(cudaFree(t->d_page_bin)); t->d_page_bin = nullptr; t->cap_page_bin = 0; }
+    if (t->d_page_len) { CU(cudaFree(t->d_page_len)); t->d_page_len = nullptr; t->cap_page_len = 0; }
+    if (t->d_slices) { CU(cudaFree(t->d_slices)); t->d_slices = nullptr; t->cap_slices = 0; }
+    t->cap_A = 0; t->cap_A_limited = false;
     return TSXC_OK;
 }
 
@@ -214,11 +221,27 @@ int status_from_flags(tsxc_table* t, uint64_t flags) {
 
 // ---- region-sorted pipeline: geometry, buffers, launch sequence -------------------------------------------------
 
-// Digits for a shard of 2^LBl buckets (32 bytes each) and fine regions of 2^region_log2 bytes.
+// One digit for the insert pipeline: regions of 2^region_log2 bytes of a shard of 2^LBl buckets (32 bytes each), at most
+// kNB1 bins including the owner bits.
 RadixGeom make_radix_geom(const Layout& L, uint32_t region_log2, uint32_t seg_log2) {
     RadixGeom g{};
     const uint32_t table_log2 = L.LBl + 5;
-    uint32_t fb = table_log2 > region_log2 ? table_log2 - region_log2 : 0;   // fine-bin bits inside the shard
+    uint32_t fb = table_log2 > region_log2 ? table_log2 - region_log2 : 0;   // region bits inside the shard
+    fb = std::min<uint32_t>(fb, L.LBl);
+    g.d1 = std::min<uint32_t>(10, L.shard_bits + fb);
+    g.d2 = 0;
+    g.nb1 = 1u << g.d1; g.nb2 = 1u; g.nbl = 1u << (g.d1 - L.shard_bits);
+    g.shift1 = L.LBg - g.d1; g.shift2 = g.shift1;
+    g.owner_shift = g.d1 - L.shard_bits;
+    g.seg_log2 = seg_log2;
+    return g;
+}
+
+// Two digits of at most 8 bits for the region-sorted lookups (fine regions of 2^region_log2 bytes).
+RadixGeom make_lookup_geom(const Layout& L, uint32_t region_log2, uint32_t seg_log2) {
+    RadixGeom g{};
+    const uint32_t table_log2 = L.LBl + 5;
+    uint32_t fb = table_log2 > region_log2 ? table_log2 - region_log2 : 0;
     fb = std::min<uint32_t>(fb, std::min<uint32_t>(L.LBl, 16));
     g.d1 = std::min<uint32_t>(8, L.shard_bits + fb);
     g.d2 = std::min<uint32_t>(8, fb - (g.d1 - L.shard_bits));
@@ -235,9 +258,13 @@ uint64_t env_u64(const char* name, uint64_t dflt) {
     return std::strtoull(e, nullptr, 10);
 }
 
-// Sizes buffers A and B for a batch with at most `positions` k-mers.  A holds one chunk; as much as the batch
-// needs, at most what HBM leaves free (a denser chunk is a faster insert pass: more touches per table region).
-int radix_reserve(tsxc_table* t, uint64_t positions) {
+uint32_t slice_keys_of(const Layout& L) { return kBlockThreads * (L.KW == 1 ? 4u : (L.KW == 2 ? 2u : 1u)); }
+
+// Sizes buffer A for a batch with at most `positions` k-mers: as much as the batch needs, at most what HBM leaves
+// free (a denser chunk is a faster insert pass: more touches per table region).  A single shard addresses A as a
+// pool of pages when the pool holds enough of them; otherwise (small buffers, multi-GPU receive buffers) bins get
+// exact offsets from a histogram pass.
+int radix_reserve(tsxc_table* t, uint64_t positions, bool for_peers = false) {
     const RadixGeom& g = t->rg;
     const uint64_t seg_keys = 32ULL << g.seg_log2;
     uint64_t want = std::max<uint64_t>(((positions + seg_keys - 1) / seg_keys) * seg_keys, 2 * seg_keys);
@@ -255,79 +282,110 @@ int radix_reserve(tsxc_table* t, uint64_t positions) {
     CU(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t reserve = env_u64("TSXC_RESERVE_MB", 4096) << 20;     // staging slots, lookups, the caller
     const uint64_t budget = free_b > reserve ? free_b - reserve : free_b / 2;
-    const uint32_t groups = g.d2 ? 8 : 0;                                // B holds 1/8 of A
-    const double bytes_per_key = 8.0 * t->L.KW * (1.0 + (groups ? 1.0 / groups : 0.0));
+    const uint32_t slice = slice_keys_of(t->L);
+    // per key: the key itself, its share of a slice descriptor and of the page records
+    const double bytes_per_key = 8.0 * t->L.KW + 20.0 / slice;
     const uint64_t cap_max = (uint64_t)((double)budget / bytes_per_key);
     uint64_t cap = std::min(want, cap_max);
-    if (cap < 2 * seg_keys) return fail(t, TSXC_E_NOMEM, "not enough free device memory for the key buffers of the insert pipeline");
-    uint64_t cap_b = 0;
-    if (groups) cap_b = std::min(cap, std::max<uint64_t>((cap + groups - 1) / groups, 4 * seg_keys));
-    if (const uint64_t e = env_u64("TSXC_GROUP_KEYS", 0)) cap_b = std::min(cap, std::max<uint64_t>(e, 4096));
-    CU(cudaMalloc(&t->d_A, cap * t->L.KW * sizeof(uint64_t)));
-    if (cap_b) {
-        cudaError_t e = cudaMalloc(&t->d_B, cap_b * t->L.KW * sizeof(uint64_t));
-        if (e != cudaSuccess) { cudaGetLastError(); cudaFree(t->d_A); t->d_A = nullptr; return fail(t, TSXC_E_NOMEM, "key buffer B allocation failed"); }
+    if (cap < 2 * seg_keys) return fail(t, TSXC_E_NOMEM, "not enough free device memory for the key buffer of the insert pipeline");
+    // paged addressing: pages of one slice (fewer keys only for tests); every (thread block of S1, bin) may leave a page
+    // partly empty, so the pool has to be much larger than that
+    PageGeom pg{};
+    // thread blocks of S1: two per SM (98 KB of shared memory each), never more than the batch has segments
+    const uint64_t grid_max = std::min<uint64_t>((uint64_t)t->sms * 2, std::max<uint64_t>(1, (positions + seg_keys - 1) / seg_keys));
+    uint32_t slice_log2 = 0;
+    while ((1u << (slice_log2 + 1)) <= slice) ++slice_log2;
+    if (t->L.shard_bits == 0 && !for_peers && !env_u64("TSXC_NO_PAGING", 0)) {
+        uint32_t pl = slice_log2;
+        if (const uint64_t e = env_u64("TSXC_PAGE_LOG2", 0)) pl = (uint32_t)std::min<uint64_t>(slice_log2, std::max<uint64_t>(e, 2));
+        const uint64_t n_pages = std::min<uint64_t>(cap >> pl, 0x7fffffffULL);
+        if (n_pages >= 4ULL * grid_max * g.nbl) {
+            pg.paged = 1; pg.page_log2 = pl; pg.n_pages = (uint32_t)n_pages;
+            cap = n_pages << pl;
+        }
     }
-    t->cap_A = cap; t->cap_B = cap_b; t->cap_A_limited = cap < want;
+    CU(cudaMalloc(&t->d_A, cap * t->L.KW * sizeof(uint64_t)));
+    const size_t n_slices_max = pg.paged ? (size_t)pg.n_pages : (size_t)(cap / slice) + g.nbl + 1;
+    if ((rc = ensure(t, &t->d_slices, &t->cap_slices, n_slices_max))) return rc;
+    if (pg.paged && (rc = ensure(t, &t->d_page_bin, &t->cap_page_bin, (size_t)pg.n_pages))) return rc;
+    if (pg.paged && (rc = ensure(t, &t->d_page_len, &t->cap_page_len, (size_t)pg.n_pages))) return rc;
+    if (!t->d_A) return fail(t, TSXC_E_NOMEM, "not enough free device memory for the tables of the insert pipeline");
+    t->pg = pg;
+    t->part_grid = (int)grid_max;
+    t->cap_A = cap; t->cap_A_limited = cap < want;
     return TSXC_OK;
 }
 
-// S2 (when the geometry has a second digit) + phase B over the keys currently described by ctl->cur_coff.
+// Phase B over the keys currently described by ctl (cur_coff / slicestart): slice descriptors, then the insert.
 int launch_sort_insert(tsxc_table* t, cudaStream_t s) {
     const RadixGeom& g = t->rg;
     const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
     static const int insert_blocks_per_sm = [] { const int v = (int)env_u64("TSXC_INSERT_GRID", 0); return (v >= 1 && v <= 16) ? v : 6; }();
     const int grid_b = t->sms * insert_blocks_per_sm;
-    const int grid_p = t->sms * 2;
-#define INS_(KW_, W_, SRC_)                                                                         \
-    if (agg) k_insert_keys<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, t->d_ctl, SRC_);   \
-    else k_insert_keys<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, t->d_ctl, SRC_)
-    if (g.d2 == 0) {
-        PhaseTimer pt(t, s, PH_INSERT);
-#define M(KW_, W_) INS_(KW_, W_, t->d_A)
-        TSX_DISPATCH(t->L, M);
+    PhaseTimer pt(t, s, PH_INSERT);
+    k_build_slices<<<t->sms * 4, kBlockThreads, 0, s>>>(t->d_ctl, t->pg, t->d_page_bin, t->d_page_len, g.nbl, slice_keys_of(t->L), t->d_slices);
+#define M(KW_, W_)                                                                                             \
+    if (agg) k_insert_keys<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, t->d_ctl, t->d_A, t->d_slices);   \
+    else k_insert_keys<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, t->d_ctl, t->d_A, t->d_slices)
+    TSX_DISPATCH(t->L, M);
 #undef M
-        pt.end(1);
-        return TSXC_OK;
-    }
-    const uint32_t n_groups = (uint32_t)((t->cap_A + t->cap_B - 1) / t->cap_B);
-    const uint32_t n_fine = g.nbl * g.nb2;
-    for (uint32_t gi = 0; gi < n_groups; ++gi) {
-        {
-            PhaseTimer pt(t, s, PH_PART2);
-#define M(KW_)                                                                                                    \
-            k_plan_group<KW_><<<1, kNB, 0, s>>>(t->d_ctl, gi, t->cap_B, g.nbl, t->d_fhist, n_fine);               \
-            k_hist_keys<KW_><<<grid_p, kRadixThreads, 0, s>>>(t->tv, g, t->d_ctl, t->d_A, t->d_fhist);            \
-            k_scan_fine<<<1, 1024, 0, s>>>(t->d_ctl, t->d_fhist, t->d_fcur, n_fine);                              \
-            k_part_keys<KW_><<<grid_p, kRadixThreads, 0, s>>>(t->tv, g, t->d_ctl, t->d_A, t->d_fcur, t->d_B)
-            TSX_DISPATCH_KW(t->L, M);
-#undef M
-            pt.end(4);
-        }
-        PhaseTimer pt(t, s, PH_INSERT);
-#define M(KW_, W_) INS_(KW_, W_, t->d_B)
-        TSX_DISPATCH(t->L, M);
-#undef M
-        pt.end(1);
-    }
-#undef INS_
+    pt.end(2);
     return TSXC_OK;
 }
 
-// S0 + planner over segments [seg0, seg0 + n_segs) of the batch.
+template <int KW> constexpr size_t part_smem_bytes(bool paged) {
+    return ((paged ? sizeof(TileSmem<KW, kNB1, true>) : sizeof(TileSmem<KW, kNB1, false>)) + 15) / 16 * 16 + 256 * sizeof(uint64_t*);
+}
+
+// The partition kernels use more than the 48 KB of shared memory a kernel gets by default.
+int opt_in_shared_memory(tsxc_table* t) {
+#define M(KW_)                                                                                                                     \
+    CU(cudaFuncSetAttribute(k_hist_reads<KW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes));                    \
+    CU(cudaFuncSetAttribute(k_part_reads<KW_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(false))); \
+    CU(cudaFuncSetAttribute(k_part_reads<KW_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(true)))
+    TSX_DISPATCH_KW(t->L, M);
+#undef M
+    return TSXC_OK;
+}
+
+// S1 of chunk c (exact mode: into A or the owners' buffers; paged mode: into the pool)
+int launch_part_reads(tsxc_table* t, uint32_t c, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words, uint64_t n_bases,
+                      uint64_t seg0, uint64_t* const* d_peers, cudaStream_t s) {
+    const RadixGeom& g = t->rg;
+    const int grid_p = t->part_grid > 0 ? t->part_grid : t->sms * 2;
+    unsigned long long* err = t->d_ctr + CTR_ERRORS;
+#define M(KW_)                                                                                                                          \
+    if (t->pg.paged && !d_peers)                                                                                                         \
+        k_part_reads<KW_, true><<<grid_p, kRadixThreads, part_smem_bytes<KW_>(true), s>>>(t->tv, g, t->pg, t->d_ctl, c, d_packed, d_ends, n_words, n_bases, seg0, t->d_A, nullptr, t->d_page_bin, t->d_page_len, err); \
+    else                                                                                                                                 \
+        k_part_reads<KW_, false><<<grid_p, kRadixThreads, part_smem_bytes<KW_>(false), s>>>(t->tv, g, t->pg, t->d_ctl, c, d_packed, d_ends, n_words, n_bases, seg0, t->d_A, d_peers, nullptr, nullptr, err)
+    TSX_DISPATCH_KW(t->L, M);
+#undef M
+    return TSXC_OK;
+}
+
+// Planner over segments [seg0, seg0 + n_segs) of the batch.  exact: S0 histogram (bins get exact offsets);
+// otherwise only the k-mers per segment are counted (paged mode).
 int launch_hist_plan(tsxc_table* t, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words, uint64_t n_bases,
-                     uint64_t seg0, uint32_t n_segs, uint64_t cap, cudaStream_t s) {
+                     uint64_t seg0, uint32_t n_segs, uint64_t cap, bool exact, cudaStream_t s) {
     const RadixGeom& g = t->rg;
     int rc;
-    if ((rc = ensure(t, &t->d_seghist, &t->cap_seghist, (size_t)n_segs * g.nb1))) return rc;
+    if (exact && (rc = ensure(t, &t->d_seghist, &t->cap_seghist, (size_t)n_segs * g.nb1))) return rc;
     if ((rc = ensure(t, &t->d_segtotal, &t->cap_segtotal, (size_t)n_segs))) return rc;
     if ((rc = ensure(t, &t->d_segprefix, &t->cap_segprefix, (size_t)n_segs + 1))) return rc;
     PhaseTimer pt(t, s, PH_HIST);
     const int grid = (int)std::min<uint64_t>(n_segs, (uint64_t)t->sms * 2);
-#define M(KW_) k_hist_reads<KW_><<<grid, kRadixThreads, 0, s>>>(t->tv, g, d_packed, d_ends, n_words, n_bases, seg0, n_segs, t->d_seghist, t->d_segtotal)
-    TSX_DISPATCH_KW(t->L, M);
+    if (exact) {
+#define M(KW_) k_hist_reads<KW_><<<grid, kRadixThreads, kHistSmemBytes, s>>>(t->tv, g, d_packed, d_ends, n_words, n_bases, seg0, n_segs, t->d_seghist, t->d_segtotal)
+        TSX_DISPATCH_KW(t->L, M);
 #undef M
-    k_plan_chunks<<<1, kNB, 0, s>>>(t->d_ctl, t->d_seghist, t->d_segtotal, t->d_segprefix, n_segs, g.nb1, cap, 32ULL << g.seg_log2, t->d_ctr + CTR_ERRORS);
+    } else {
+#define M(KW_) k_count_segs<KW_><<<grid, kRadixThreads, 0, s>>>(d_ends, n_words, n_bases, t->L.k, g.seg_log2, seg0, n_segs, t->d_segtotal)
+        TSX_DISPATCH_KW(t->L, M);
+#undef M
+    }
+    k_plan_chunks<<<1, 1024, 0, s>>>(t->d_ctl, exact ? t->d_seghist : nullptr, t->d_segtotal, t->d_segprefix, n_segs, g.nb1, cap,
+                                     32ULL << g.seg_log2, t->d_ctr + CTR_ERRORS);
     pt.end(2);
     return TSXC_OK;
 }
@@ -347,24 +405,30 @@ int launch_count_reads_radix(tsxc_table* t, const uint64_t* d_packed, const uint
     const RadixGeom& g = t->rg;
     int rc = radix_reserve(t, n_words * 32);
     if (rc) return rc;
+    const bool paged = t->pg.paged != 0;
+    // paged: every (thread block of S1, bin) may leave its last page partly empty
+    const uint64_t cap = paged ? (uint64_t)(t->pg.n_pages - (uint64_t)t->part_grid * g.nbl) << t->pg.page_log2 : t->cap_A;
+    const uint32_t slice = slice_keys_of(t->L);
     const uint64_t seg_words = 1ULL << g.seg_log2;
     const uint64_t n_segs_total = (n_words + seg_words - 1) / seg_words;
     uint64_t segs_per_run = 0;
-    plan_bounds(g, t->cap_A, &segs_per_run, 0, nullptr);
-    const int grid_p = t->sms * 2;
+    plan_bounds(g, cap, &segs_per_run, 0, nullptr);
     for (uint64_t seg0 = 0; seg0 < n_segs_total; seg0 += segs_per_run) {
         const uint32_t n_segs = (uint32_t)std::min<uint64_t>(segs_per_run, n_segs_total - seg0);
-        if ((rc = launch_hist_plan(t, d_packed, d_ends, n_words, n_bases, seg0, n_segs, t->cap_A, s))) return rc;
+        if ((rc = launch_hist_plan(t, d_packed, d_ends, n_words, n_bases, seg0, n_segs, cap, !paged, s))) return rc;
         uint32_t max_chunks = 0;
-        plan_bounds(g, t->cap_A, nullptr, n_segs, &max_chunks);
+        plan_bounds(g, cap, nullptr, n_segs, &max_chunks);
         for (uint32_t c = 0; c < max_chunks; ++c) {
             {
                 PhaseTimer pt(t, s, PH_PART1);
-                k_chunk_begin<<<1, kNB, 0, s>>>(t->d_ctl, c);
-#define M(KW_) k_part_reads<KW_><<<grid_p, kRadixThreads, 0, s>>>(t->tv, g, t->d_ctl, c, d_packed, d_ends, n_words, n_bases, seg0, t->d_A, nullptr)
-                TSX_DISPATCH_KW(t->L, M);
-#undef M
-                pt.end(2);
+                if (paged) {
+                    k_chunk_begin_paged<<<1, 1024, 0, s>>>(t->d_ctl, c);
+                } else {
+                    k_chunk_begin<<<1, 1024, 0, s>>>(t->d_ctl, c, slice);
+                }
+                if ((rc = launch_part_reads(t, c, d_packed, d_ends, n_words, n_bases, seg0, nullptr, s))) return rc;
+                if (paged) k_chunk_end_paged<<<1, 1024, 0, s>>>(t->d_ctl);
+                pt.end(paged ? 3 : 2);
             }
             if ((rc = launch_sort_insert(t, s))) return rc;
         }
@@ -377,7 +441,7 @@ int launch_count_reads_radix(tsxc_table* t, const uint64_t* d_packed, const uint
 int launch_count_marked(tsxc_table* t, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words, uint64_t n_bases,
                         cudaStream_t s) {
     // the pipeline pays off once every table region receives a few thousand k-mers per pass
-    if (t->radix_on && !(t->L.flags & TSXC_FLAG_DIRECT) && n_words >= (uint64_t)t->rg.nbl * t->rg.nb2 * 4)
+    if (t->radix_on && !(t->L.flags & TSXC_FLAG_DIRECT) && n_words >= (uint64_t)t->rg.nbl * 4)
         return launch_count_reads_radix(t, d_packed, d_ends, n_words, n_bases, s);
     const int grid = grid_for(t, n_words);
     const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
@@ -413,8 +477,8 @@ int ensure_acc(tsxc_table* t) {
     CU(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t reserve = env_u64("TSXC_RESERVE_MB", 4096) << 20;
     const uint64_t budget = free_b > reserve ? free_b - reserve : free_b / 2;
-    // per base position: a key in A (+1/8 in B) if it starts a k-mer, 2 bits + 1 end bit in each of the two buffers
-    const double per_pos = 9.0 * t->L.KW + 0.75;
+    // per base position: a key in A if it starts a k-mer, 2 bits + 1 end bit in each of the two buffers
+    const double per_pos = 8.0 * t->L.KW + 0.1 + 0.75;
     uint64_t pos = (uint64_t)((double)budget / per_pos);
     pos = std::min<uint64_t>(pos, std::max<uint64_t>(1ULL << 22, 4 * t->L.n_slots));   // more than ~4 k-mers per slot per pass is pointless
     uint64_t words = std::min<uint64_t>(pos / 32, 1ULL << 28);
@@ -502,7 +566,7 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
             return bail(TSXC_E_CUDA);
         }
     }
-    // Fine table regions of 2^region_log2 bytes (default 8 MiB: profiles/r02_k0r_fetch.md); tables of 512 MiB and
+    // Table regions of 2^region_log2 bytes (default 128 MiB: profiles/r02_pipeline_history.md); tables of 512 MiB and
     // more take the region-sorted pipeline.  TSXC_REGION_LOG2 overrides both (tests force tiny tables through it).
     uint32_t min_table_log2 = 29;
     if (const char* env = std::getenv("TSXC_REGION_LOG2")) {
@@ -512,7 +576,9 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
     uint32_t seg_log2 = (uint32_t)env_u64("TSXC_SEG_LOG2", kSegWordsLog2Default);
     seg_log2 = std::max<uint32_t>(kSegWordsLog2Min, std::min<uint32_t>(seg_log2, 20));
     h->rg = make_radix_geom(L, h->region_log2, seg_log2);
+    h->rg_lookup = make_lookup_geom(L, std::min<uint32_t>(h->region_log2, 24), seg_log2);
     h->radix_on = (L.LBl + 5 >= min_table_log2) && (h->rg.d1 > L.shard_bits);
+    { const int arc = opt_in_shared_memory(h); if (arc != TSXC_OK) return bail(arc); }
     h->tv = make_view(L, h->d_words, h->d_ctr);
     CU(cudaMemsetAsync(h->d_ctl, 0, sizeof(RadixCtl), h->stream));
     int rc = tsxc_clear(h);
@@ -636,7 +702,7 @@ int tsxc_destroy(tsxc_table* t) {
     for (auto& m : t->marks) if (m) cudaEventDestroy(m);
     for (auto& a : t->acc) { cudaFree(a.d_packed); cudaFree(a.d_ends); if (a.consumed) cudaEventDestroy(a.consumed); }
     if (t->acc_copied) cudaEventDestroy(t->acc_copied);
-    cudaFree(t->d_A); cudaFree(t->d_B); cudaFree(t->d_ctl); cudaFree(t->d_seghist); cudaFree(t->d_segtotal); cudaFree(t->d_segprefix);
+    cudaFree(t->d_A); cudaFree(t->d_page_bin); cudaFree(t->d_page_len); cudaFree(t->d_slices); cudaFree(t->d_ctl); cudaFree(t->d_seghist); cudaFree(t->d_segtotal); cudaFree(t->d_segprefix);
     cudaFree(t->d_fhist); cudaFree(t->d_fcur); cudaFree(t->d_peers); cudaFree(t->d_ticket_k0);
     cudaFree(t->d_ends); cudaFree(t->d_keys); cudaFree(t->d_counts); cudaFree(t->d_nout); cudaFree(t->d_text); cudaFree(t->d_pairs[0]); cudaFree(t->d_pairs[1]);
     cudaFree(t->d_ctr); cudaFree(t->d_words);
@@ -804,7 +870,7 @@ int tsxc_sync(tsxc_table* t) {
 }
 
 static int lookup_device_locked(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, uint64_t* d_counts_out) {
-    const RadixGeom& rg = t->rg;
+    const RadixGeom& rg = t->rg_lookup;
     cudaStream_t s = t->stream;
     const uint64_t sorted_min = env_u64("TSXC_LOOKUP_SORT_MIN", 1ULL << 18);
     if (t->radix_on && rg.d1 > 0 && t->L.shard_bits == 0 && !(t->L.flags & TSXC_FLAG_DIRECT) && n >= sorted_min && t->d_fhist) {
@@ -899,7 +965,7 @@ int tsxc_stats(tsxc_table* t, tsxc_stats_t* out) {
     out->kernel_launches = t->n_launches; out->main_kernel_launches = t->n_main_launches; out->main_kernel_ms = t->main_ms;
     out->partition_ms = t->phase_ms[PH_HIST] + t->phase_ms[PH_PART1] + t->phase_ms[PH_PART2]; out->insert_ms = t->phase_ms[PH_INSERT];
     out->hist_ms = t->phase_ms[PH_HIST]; out->part1_ms = t->phase_ms[PH_PART1]; out->part2_ms = t->phase_ms[PH_PART2];
-    out->chunk_cap_keys = t->cap_A; out->group_cap_keys = t->cap_B;
+    out->chunk_cap_keys = t->cap_A; out->group_cap_keys = t->pg.paged ? (1ULL << t->pg.page_log2) : 0;
     out->radix_digit1_bits = t->rg.d1; out->radix_digit2_bits = t->rg.d2;
     return TSXC_OK;
 }
@@ -995,7 +1061,7 @@ int tsxc_route_recv_buffer(tsxc_table* t, uint64_t cap_keys, void** d_ptr_out, u
     CU(cudaSetDevice(t->device));
     if (t->peers_set) return fail(t, TSXC_E_INVALID, "receive buffer already exported");
     // cap_keys == 0: as much as free memory allows (radix_reserve's policy), else exactly what the caller asks for
-    int rc = radix_reserve(t, cap_keys ? cap_keys : ~0ULL >> 8);
+    int rc = radix_reserve(t, cap_keys ? cap_keys : ~0ULL >> 8, true);
     if (rc) return rc;
     *d_ptr_out = t->d_A;
     if (cap_keys_out) *cap_keys_out = t->cap_A;
@@ -1012,7 +1078,6 @@ int tsxc_route_set_peers(tsxc_table* t, void* const* peer_buffers, uint64_t recv
     CU(cudaMemcpyAsync(t->d_peers, peer_buffers, n * sizeof(void*), cudaMemcpyHostToDevice, t->stream));
     CU(cudaStreamSynchronize(t->stream));
     t->cap_A = recv_cap_keys;        // every rank plans against the smallest buffer of the group
-    if (t->cap_B > t->cap_A) t->cap_B = t->cap_A;
     t->peers_set = true;
     return TSXC_OK;
 }
@@ -1043,7 +1108,7 @@ int tsxc_route_begin(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_
     if (n_segs > segs_per_run) return fail(t, TSXC_E_INVALID, "batch too large for one routing plan: split it");
     uint32_t max_chunks = 0;
     if (n_segs) {
-        if ((rc = launch_hist_plan(t, d_packed, t->d_ends, n_words, n_bases, 0, (uint32_t)n_segs, cap_send, s))) return rc;
+        if ((rc = launch_hist_plan(t, d_packed, t->d_ends, n_words, n_bases, 0, (uint32_t)n_segs, cap_send, true, s))) return rc;
         plan_bounds(rg, cap_send, nullptr, (uint32_t)n_segs, &max_chunks);
     } else {
         CU(cudaMemsetAsync(t->d_ctl, 0, 16, s));     // n_chunks = 0
@@ -1058,7 +1123,7 @@ int tsxc_route_hist(tsxc_table* t, uint32_t round, uint32_t* d_hist_out) {
     if (!t || !d_hist_out) return fail(t, TSXC_E_INVALID, "null argument");
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
-    k_round_hist<<<1, kNB, 0, t->stream>>>(t->d_ctl, round, t->rg.nb1, d_hist_out);
+    k_round_hist<<<1, 1024, 0, t->stream>>>(t->d_ctl, round, t->rg.nb1, d_hist_out);
     t->n_launches++;
     CU(cudaGetLastError());
     return TSXC_OK;
@@ -1072,12 +1137,9 @@ int tsxc_route_send(tsxc_table* t, uint32_t round, const uint32_t* d_hist_all) {
     const RadixGeom& rg = t->rg;
     cudaStream_t s = t->stream;
     PhaseTimer pt(t, s, PH_PART1);
-    k_route_offsets<<<1, kNB, 0, s>>>(t->d_ctl, round, d_hist_all, 1u << t->L.shard_bits, t->L.shard_rank, rg.nb1, rg.nbl, t->cap_A,
-                                      t->d_ctr + CTR_ERRORS);
-    const int grid_p = t->sms * 2;
-#define M(KW_) k_part_reads<KW_><<<grid_p, kRadixThreads, 0, s>>>(t->tv, rg, t->d_ctl, round, t->route_packed, t->d_ends, t->route_n_words, t->route_n_bases, 0, t->d_A, t->d_peers)
-    TSX_DISPATCH_KW(t->L, M);
-#undef M
+    k_route_offsets<<<1, 1024, 0, s>>>(t->d_ctl, round, d_hist_all, 1u << t->L.shard_bits, t->L.shard_rank, rg.nb1, rg.nbl, t->cap_A,
+                                       slice_keys_of(t->L), t->d_ctr + CTR_ERRORS);
+    { const int prc = launch_part_reads(t, round, t->route_packed, t->d_ends, t->route_n_words, t->route_n_bases, 0, t->d_peers, s); if (prc) return prc; }
     pt.end(2);
     CU(cudaGetLastError());
     return TSXC_OK;

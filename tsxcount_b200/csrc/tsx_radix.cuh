@@ -1,27 +1,28 @@
 // tsx_radix.cuh — the region-sorted insert pipeline for tables far larger than L2 / TLB reach.
 //
-// Measured on B200 (profiles/r01_k0_random_access.md, profiles/r02_k0r_fetch.md): a dependent sector load +
-// atomic runs at 4 G/s when spread uniformly over 128 GiB, at 45 G/s when all SMs work inside one 128 MiB
-// region at a time and at 65-69 G/s for 8-16 MiB regions.  So k-mer hashes are sorted by table region first,
-// with a two-digit most-significant-digit radix partition whose every store is a coalesced run, and inserted in
-// region order afterwards:
+// Measured on B200 (profiles/r01_k0_random_access.md, profiles/r02_k0r_modes.md): a dependent sector load + CAS
+// runs at 4 G/s when spread uniformly over 128 GiB, at 37 G/s when all SMs work inside one 128 MiB region at a
+// time and at 45 G/s (the ceiling of the atomic-return path) for regions of 32 MiB and less.  So k-mer hashes are
+// sorted by table region first and inserted in region order afterwards.  One partition pass with up to 1024 bins
+// (128 MiB regions of a 128 GiB table) beats two passes with 2^13 bins: the second pass costs 73 ms per 8e9 k-mers,
+// the coarser regions cost the insert 30 ms (profiles/r02_pipeline_history.md).
 //
-//   S0  k_hist_reads   extract + hash every k-mer, count per (segment of the read stream, digit 1)
-//       k_plan_chunks  device-side planner: cuts the batch into chunks of at most `cap` k-mers and turns the
-//                      counts into exact bin offsets  ->  nothing is sized by guesswork, no bin can overflow,
-//                      whatever the skew of the input
-//   S1  k_part_reads   extract + hash again, block-local counting sort of a tile by digit 1 in shared memory,
-//                      coalesced runs into buffer A (exact positions reserved with one atomicAdd per (tile, bin));
-//                      in the multi-GPU path the runs go straight into the owning rank's peer-mapped buffer
-//   S2a k_hist_keys    digit-2 histogram of a group of A           (exact sizes of the fine bins)
-//       k_scan_fine    exclusive scan -> fine-bin offsets
-//   S2b k_part_keys    the same tile sort on digit 2: A -> B, B is ordered by fine table region
-//   B   k_insert_keys  blocks take consecutive slices of B through a ticket, so the whole chip probes one or two
-//                      8-16 MiB table regions at a time; duplicates inside a slice are combined in shared memory
-//                      before they reach the table (heavy hitters cost one atomic per slice, not one per k-mer)
+//   plan  k_count_segs   k-mers per segment of the read stream (read-end bitmap only, no hashing)
+//         k_plan_chunks  device-side planner: cuts the batch into chunks of at most `cap` k-mers
+//   S1    k_part_reads   extract + hash every k-mer, block-local counting sort of a tile by digit 1 in shared memory,
+//                        coalesced runs into buffer A.  Single GPU: A is a pool of pages; a bin's run takes the
+//                        next positions of the bin's virtual address space (one atomicAdd per (tile, bin)) and the
+//                        reservation that crosses into a new page allocates it, so bins grow as the data demands:
+//                        no histogram pass, no bin can overflow whatever the skew.  Multi-GPU: exact offsets from
+//                        an all-gathered histogram (S0 = k_hist_reads), and the runs go straight into the owning
+//                        rank's peer-mapped receive buffer
+//   B     k_insert_keys  blocks take consecutive slices of the bins through a ticket, so the whole chip probes one or
+//                        two table regions at a time; duplicates inside a slice are combined in shared memory
+//                        before they reach the table (heavy hitters cost one atomic per slice, not one per k-mer)
 //
-// Ranking inside a tile uses warp-private counters and a per-digit-bit ballot match (no shared-memory atomics:
-// at 2 cycles per lane they would cost more than everything else in these kernels together).
+// Ranking inside a tile uses warp-private counters and optimistic conflict detection (rank_in_warp); no
+// shared-memory atomics: at 2 cycles per lane they would cost more than everything else in these kernels together.
+// The two-digit machinery (k_hist_keys / k_part_keys) is what region-sorted lookups still use.
 //
 // Reference semantics: extraction src/mains/testExecution.h:15-36, encoding src/utils/SequenceUtils.h:86-123,
 // insert src/tsxcount/TSXHashMapPerf.h:56-205 (paths relative to mjoppich/tsxCount).  Nothing here has a
@@ -37,18 +38,21 @@ namespace tsx {
 
 constexpr int kRadixThreads = 512;
 constexpr int kRadixWarps = kRadixThreads / 32;
-constexpr int kNB = 256;                    // bins per digit (digits are at most 8 bits wide)
+constexpr int kNB = 256;                    // bins per digit of the two-digit passes (lookups)
+constexpr int kNB1 = 1024;                  // bins of S1 (digit 1 is at most 10 bits wide)
+constexpr int kCursorStride = 16;           // S1 cursors sit in their own 128-byte lines (unsigned long long units)
 constexpr int kSegWordsLog2Default = 15;    // planner granularity: 2^15 packed words = 2^20 base positions
 constexpr int kSegWordsLog2Min = 9;         // one block round (16 warps x 32 words)
 constexpr int kMaxChunks = 64;
 constexpr int kMaxFine = kNB * kNB;
 constexpr int kCombSlots = 1024;            // shared-memory combiner of phase B
+constexpr int kPageLog2Max = 16;            // keys per page of the paged buffer A, log2 (>= log2 of a tile)
 
 // Digit geometry, derived once per handle on the host.
 //   global bucket index bg = H.w[0] & lbg_mask  (LBg bits; its top shard_bits select the owning shard)
 //   digit 1 = top d1 bits of bg                 (includes the owner bits: bins of S1 are owner-major)
 //   local coarse bin = digit 1 without the owner bits (nbl = 2^(d1 - shard_bits) per shard)
-//   digit 2 = the next d2 bits; fine bin (local) = local coarse bin * nb2 + digit 2
+//   digit 2 = the next d2 bits; fine bin (local) = local coarse bin * nb2 + digit 2      (lookups only)
 struct RadixGeom {
     uint32_t d1, d2;
     uint32_t nb1, nb2, nbl;
@@ -60,7 +64,7 @@ struct RadixGeom {
 struct ChunkDesc {
     uint64_t seg_begin, seg_end;           // segments [seg_begin, seg_end) of the batch
     uint64_t n_keys;
-    uint64_t coff[kNB + 1];                // exclusive prefix of the digit-1 counts
+    uint64_t coff[kNB1 + 1];               // exclusive prefix of the digit-1 counts (exact mode only)
 };
 
 struct GroupDesc {
@@ -69,13 +73,31 @@ struct GroupDesc {
     uint32_t itemstart[kNB + 1];           // tiles of local coarse bin b are items [itemstart[b], itemstart[b+1])
 };
 
+// Buffer A of a single shard is a pool of small pages (as many keys as a slice of phase B, 1024 at k <= 32).  In S1
+// every (thread block, bin) fills a page of its own and takes the next one from the pool when it is full (one
+// atomicAdd per page; the pages a tile run needs beyond the current one are taken together and are contiguous).
+// Bins therefore grow as the data demands: no histogram pass, no bin can overflow whatever the skew, and the
+// reservation traffic is one returning atomic per 1024 k-mers instead of one per (tile, bin) = per 4 k-mers, which
+// at 1024 bins costs 20 ms per 8e9 k-mers (the atomic-return path again, profiles/r02_pipeline_history.md).
+// page_bin[p] = bin of page p (0xffff: unused), page_len[p] = keys in it.
+struct PageGeom {
+    uint32_t paged;              // 0: bins have exact offsets in A, 1: paged pool
+    uint32_t page_log2;          // keys per page, log2 (at most a slice of phase B)
+    uint32_t n_pages;            // pages in the pool
+    uint32_t pad;
+};
+
 struct RadixCtl {
     uint32_t n_chunks, chunk_active;
     uint32_t plan_error, recv_overflow;
     unsigned long long ticket[4];          // 0: S2a, 1: S2b, 2: phase B
-    unsigned long long cursor1[kNB];       // S1 reservation cursors: position inside the destination buffer
-    unsigned long long n_insert;           // keys phase B has to insert (group size, or everything when d2 == 0)
-    uint64_t cur_coff[kNB + 1];            // local coarse-bin offsets of the buffer A that S2 / phase B read
+    unsigned long long n_insert;           // keys phase B has to insert
+    unsigned long long page_next;          // paged mode: pages handed out in this chunk
+    uint32_t n_slices, pad0;               // work items of phase B
+    uint32_t slicestart[kNB1 + 1];         // slices of local bin b are items [slicestart[b], slicestart[b+1])
+    uint32_t bin_pages[kNB1];              // paged mode: pages of bin b (S1), then the fill cursor of k_build_slices
+    uint64_t cur_coff[kNB1 + 1];           // exclusive prefix of the local bin counts (= offsets inside A in exact mode)
+    unsigned long long cursor1[kNB1 * kCursorStride];   // S1 reservation cursors
     GroupDesc group;
     ChunkDesc chunk[kMaxChunks];
 };
@@ -140,7 +162,7 @@ __device__ __forceinline__ unsigned match_digit(bool valid, uint32_t digit, uint
     // instructions (test -> predicate, vote, two predicated ANDs): these kernels are bound by the integer ALU pipe.
     unsigned peers = __ballot_sync(full, valid);
 #pragma unroll
-    for (uint32_t b = 0; b < 8; ++b) {
+    for (uint32_t b = 0; b < 10; ++b) {
         if (b >= bits) break;
         asm volatile("{\n\t"
                      ".reg .pred p;\n\t"
@@ -203,6 +225,40 @@ __device__ __forceinline__ uint32_t rank_in_warp(CT* wcnt, uint8_t* wtag_, bool 
     return pend ? old + __popc(peers & ((1u << lane) - 1u)) : rank;
 }
 
+// Exclusive scan of v over all threads of the block (any block size that is a multiple of 32, up to 1024).
+// scratch: 32 words of shared memory.  Contains two __syncthreads; every thread of the block must call it.
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* scratch, uint32_t* total) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(full, inc, d);
+        if (lane >= (unsigned)d) inc += y;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+    for (unsigned w = 0; w < nw; ++w) {
+        const uint32_t x = scratch[w];
+        if (w < warp) pre += x;
+        tot += x;
+    }
+    __syncthreads();
+    if (total) *total = tot;
+    return pre + inc - v;
+}
+
+// 64-bit variant for values below 2^40 each and at most 1024 threads: the low 20 bits and the rest are scanned
+// separately (their prefix sums fit 32 bits) and recombined, which is exact.
+__device__ __forceinline__ uint64_t block_exscan_u64(uint64_t v, uint32_t* scratch, uint64_t* total) {
+    uint32_t tlo = 0, thi = 0;
+    const uint32_t plo = block_exscan((uint32_t)(v & 0xfffffULL), scratch, &tlo);
+    const uint32_t phi = block_exscan((uint32_t)(v >> 20), scratch, &thi);
+    if (total) *total = ((uint64_t)thi << 20) + tlo;
+    return ((uint64_t)phi << 20) + plo;
+}
+
 // Exclusive scan of v over the first 256 threads of the block (the others pass 0).  scratch: 8 words of shared
 // memory.  Contains two __syncthreads; every thread of the block must call it.
 __device__ __forceinline__ uint32_t block_exscan_256(uint32_t v, uint32_t* scratch, uint32_t* total) {
@@ -238,33 +294,44 @@ __device__ __forceinline__ uint64_t block_exscan_256_u64(uint64_t v, uint32_t* s
     return ((uint64_t)phi << 23) + plo;
 }
 
-template <int KW>
+template <int KW, int NB, bool PAGED = false>
 struct TileSmem {
-    uint64_t sorted[RadixCfg<KW>::TILE * KW];
-    long long gdelta[kNB];            // position of a bin's run in its destination minus its start inside the tile
-    uint32_t binstart[kNB];
-    uint32_t scratch[8];
-    uint16_t cnt[kRadixWarps][kNB];
+    alignas(16) uint64_t sorted[RadixCfg<KW>::TILE * KW];
+    alignas(16) uint16_t cnt[kRadixWarps][NB];   // zeroed with 128-bit stores
+    long long gdelta[NB];             // position of a bin's run in its destination minus its start inside the tile
+    long long gdelta2[PAGED ? NB : 2];   // paged: the same for the part of the run that lies in freshly taken pages
+    uint32_t binstart[NB];
+    uint32_t split[PAGED ? NB : 4];      // paged: tile index at which the run continues in the fresh pages
+    uint32_t page_cur[PAGED ? NB : 4];   // paged: the block's current page of the bin (0xffffffff: none yet)
+    uint32_t page_fill[PAGED ? NB : 4];  // paged: keys already in it
+    uint32_t page_cnt[PAGED ? NB : 4];   // paged: pages this block has taken for the bin
+    uint32_t scratch[32];
 };
 
-template <int KW>
-__device__ __forceinline__ void tile_smem_init(TileSmem<KW>& sm) {
-    for (uint32_t i = threadIdx.x; i < kRadixWarps * kNB / 2; i += kRadixThreads) reinterpret_cast<uint32_t*>(&sm.cnt[0][0])[i] = 0u;
+template <int KW, int NB, bool PAGED>
+__device__ __forceinline__ void tile_smem_init(TileSmem<KW, NB, PAGED>& sm) {
+    uint4* c = reinterpret_cast<uint4*>(&sm.cnt[0][0]);
+    for (uint32_t i = threadIdx.x; i < kRadixWarps * NB / 8; i += kRadixThreads) c[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// Block-local counting sort of one tile by an 8-bit digit and coalesced write of every bin's run.
+// Block-local counting sort of one tile by a digit of at most log2(NB) bits and coalesced write of every bin's run.
 //   Hs / vmask : the thread's OPT keys and which of them exist
 //   digit      : key word 0 -> digit
-//   reserve    : (bin, n) -> first position of a run of n keys of `bin` in its destination   (thread `bin`, n > 0)
+//   reserve    : (bin, n) -> position of a run of n > 0 keys of `bin` in the bin's address space (one atomicAdd; the
+//                owning thread issues both of its bins' reservations before it looks at either result)
+//   place      : (bin, n, start, position) -> fills sm.gdelta[bin] (and gdelta2 / split when PAGED) for the run that
+//                starts at tile index `start`
 //   dst        : bin -> base pointer of its destination buffer
 // On entry sm.cnt is all zero (and visible to the block); on exit it is zero again.
-template <int KW, typename DigitFn, typename ReserveFn, typename DstFn>
-__device__ __forceinline__ void tile_partition(TileSmem<KW>& sm, const Key<KW> (&Hs)[RadixCfg<KW>::OPT], uint32_t vmask,
-                                               uint32_t bits, DigitFn digit, ReserveFn reserve, DstFn dst) {
+template <int KW, int NB, bool PAGED, typename DigitFn, typename ReserveFn, typename PlaceFn, typename DstFn>
+__device__ __forceinline__ void tile_partition(TileSmem<KW, NB, PAGED>& sm, const Key<KW> (&Hs)[RadixCfg<KW>::OPT], uint32_t vmask,
+                                               uint32_t bits, DigitFn digit, ReserveFn reserve, PlaceFn place, DstFn dst) {
     constexpr int OPT = RadixCfg<KW>::OPT;
+    static_assert(NB % 2 == 0 && NB / 2 <= kRadixThreads, "two bins per thread");
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     // the ranking's tag rows live in `sorted`, which is idle until the scatter below (a barrier lies in between)
-    uint8_t* tag = reinterpret_cast<uint8_t*>(sm.sorted) + warp * kNB;
+    uint8_t* tag = reinterpret_cast<uint8_t*>(sm.sorted) + warp * NB;
+    static_assert(kRadixWarps * NB <= RadixCfg<KW>::TILE * KW * 8, "tag rows fit the tile buffer");
     uint32_t rk[OPT];
 #pragma unroll
     for (int j = 0; j < OPT; ++j) {
@@ -273,21 +340,29 @@ __device__ __forceinline__ void tile_partition(TileSmem<KW>& sm, const Key<KW> (
         rk[j] = rank_in_warp<uint16_t>(sm.cnt[warp], tag, v, d, lane, bits) | (d << 16);
     }
     __syncthreads();
-    // per bin: totals over the warps; the counters become each warp's offset inside the bin
-    uint32_t total = 0;
-    if (threadIdx.x < kNB) {
+    // thread t owns bins 2t and 2t+1 (one 32-bit word of every warp's counter row): totals over the warps; the
+    // counters become each warp's offset inside the bin
+    uint32_t c0 = 0, c1 = 0;
+    if (threadIdx.x < NB / 2) {
 #pragma unroll
         for (int w = 0; w < kRadixWarps; ++w) {
-            const uint32_t c = sm.cnt[w][threadIdx.x];
-            sm.cnt[w][threadIdx.x] = (uint16_t)total;
-            total += c;
+            uint32_t* cell = reinterpret_cast<uint32_t*>(&sm.cnt[w][0]) + threadIdx.x;
+            const uint32_t c = *cell;
+            *cell = (c0 & 0xffffu) | (c1 << 16);
+            c0 += c & 0xffffu;
+            c1 += c >> 16;
         }
     }
     uint32_t n_tile = 0;
-    const uint32_t start = block_exscan_256(total, sm.scratch, &n_tile);
-    if (threadIdx.x < kNB) {
-        sm.binstart[threadIdx.x] = start;
-        if (total) sm.gdelta[threadIdx.x] = (long long)reserve(threadIdx.x, total) - (long long)start;
+    const uint32_t start0 = block_exscan(c0 + c1, sm.scratch, &n_tile);
+    if (threadIdx.x < NB / 2) {
+        const uint32_t b0 = 2 * threadIdx.x, start1 = start0 + c0;
+        sm.binstart[b0] = start0;
+        sm.binstart[b0 + 1] = start1;
+        const unsigned long long p0 = c0 ? reserve(b0, c0) : 0ULL;
+        const unsigned long long p1 = c1 ? reserve(b0 + 1, c1) : 0ULL;
+        if (c0) place(b0, c0, start0, p0);
+        if (c1) place(b0 + 1, c1, start1, p1);
     }
     __syncthreads();
 #pragma unroll
@@ -305,7 +380,9 @@ __device__ __forceinline__ void tile_partition(TileSmem<KW>& sm, const Key<KW> (
 #pragma unroll
         for (int w = 0; w < KW; ++w) h[w] = sm.sorted[i * KW + w];
         const uint32_t d = digit(h[0]);
-        uint64_t* out = dst(d) + (uint64_t)(sm.gdelta[d] + (long long)i) * KW;
+        long long g = sm.gdelta[d];
+        if constexpr (PAGED) { if (i >= sm.split[d]) g = sm.gdelta2[d]; }
+        uint64_t* out = dst(d) + (uint64_t)(g + (long long)i) * KW;
         if constexpr (KW == 1) {
             __stcg(out, h[0]);
         } else {
@@ -313,24 +390,27 @@ __device__ __forceinline__ void tile_partition(TileSmem<KW>& sm, const Key<KW> (
             for (int w = 0; w < KW; w += 2) __stcg(reinterpret_cast<ulonglong2*>(out + w), make_ulonglong2(h[w], h[w + 1]));
         }
     }
-    tile_smem_init<KW>(sm);
+    tile_smem_init<KW, NB, PAGED>(sm);
     __syncthreads();
 }
 
-// ---- S0: digit-1 histogram per segment of the read stream ------------------------------------------------------
+// ---- S0 (exact mode): digit-1 histogram per segment of the read stream ---------------------------------------------
 // Segments [seg0, seg0 + n_segs) of the batch; seghist / segtotal are indexed relative to seg0.
+// Dynamic shared memory: kRadixWarps * kNB1 counters (uint32) + kRadixWarps * kNB1 tag bytes.
+constexpr size_t kHistSmemBytes = (size_t)kRadixWarps * kNB1 * 5 + 32 * 4;
 template <int KW>
 __global__ void __launch_bounds__(kRadixThreads, RadixCfg<KW>::MINB)
 k_hist_reads(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, const uint64_t* __restrict__ packed,
              const uint32_t* __restrict__ ends, uint64_t n_words, uint64_t n_bases, uint64_t seg0, uint32_t n_segs,
              uint32_t* __restrict__ seghist, uint32_t* __restrict__ segtotal) {
-    __shared__ uint32_t cnt[kRadixWarps][kNB];
-    __shared__ uint8_t tag[kRadixWarps][kNB];
-    __shared__ uint32_t scratch[8];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw);                       // [kRadixWarps][kNB1]
+    uint32_t* scratch = cnt + kRadixWarps * kNB1;                                // [32]
+    uint8_t* tag = reinterpret_cast<uint8_t*>(scratch + 32);                     // [kRadixWarps][kNB1]
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t seg_words = 1ULL << rg.seg_log2;
     for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < kRadixWarps * kNB; i += kRadixThreads) (&cnt[0][0])[i] = 0u;
+        for (uint32_t i = threadIdx.x; i < kRadixWarps * kNB1; i += kRadixThreads) cnt[i] = 0u;
         __syncthreads();
         const uint64_t w0 = (seg0 + seg) << rg.seg_log2;
         const uint64_t w1 = w0 + seg_words < n_words ? w0 + seg_words : n_words;
@@ -342,36 +422,73 @@ k_hist_reads(const __grid_constant__ TableView tv, const __grid_constant__ Radix
                 Key<KW> key;
                 const bool valid = kl.kmer_at(o, tv.L.k, tv.hp, key);
                 const Key<KW> H = hash_key<KW>(key, tv.hp);
-                (void)rank_in_warp<uint32_t>(cnt[warp], tag[warp], valid, digit1_of(rg, tv.lbg_mask, H.w[0]), lane, rg.d1);
+                (void)rank_in_warp<uint32_t>(cnt + warp * kNB1, tag + warp * kNB1, valid, digit1_of(rg, tv.lbg_mask, H.w[0]), lane, rg.d1);
             }
         }
         __syncthreads();
-        uint32_t total = 0;
-        if (threadIdx.x < kNB) {
+        uint32_t mine = 0;
+        for (uint32_t b = threadIdx.x; b < rg.nb1; b += kRadixThreads) {
+            uint32_t total = 0;
 #pragma unroll
-            for (int w = 0; w < kRadixWarps; ++w) total += cnt[w][threadIdx.x];
-            if (threadIdx.x < rg.nb1) seghist[(uint64_t)seg * rg.nb1 + threadIdx.x] = total;
+            for (int w = 0; w < kRadixWarps; ++w) total += cnt[w * kNB1 + b];
+            seghist[(uint64_t)seg * rg.nb1 + b] = total;
+            mine += total;
         }
         uint32_t seg_sum = 0;
-        (void)block_exscan_256(total, scratch, &seg_sum);
+        (void)block_exscan(mine, scratch, &seg_sum);
         if (threadIdx.x == 0) segtotal[seg] = seg_sum;
     }
 }
 
-// ---- planner: chunks of at most cap keys, exact digit-1 offsets per chunk ----------------------------------------
+// ---- paged mode: k-mers per segment from the read-end bitmap alone --------------------------------------------------
+// A k-mer starts at base g iff no read ends inside [g, g+k-2] and g+k <= n_bases: the same rule KmerLane applies,
+// without touching the bases.
+template <int KW>
+__global__ void __launch_bounds__(kRadixThreads) k_count_segs(const uint32_t* __restrict__ ends, uint64_t n_words, uint64_t n_bases,
+                                                              uint32_t k, uint32_t seg_log2, uint64_t seg0, uint32_t n_segs,
+                                                              uint32_t* __restrict__ segtotal) {
+    constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
+    __shared__ uint32_t scratch[32];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t seg_words = 1ULL << seg_log2;
+    for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+        const uint64_t w0 = (seg0 + seg) << seg_log2;
+        const uint64_t w1 = w0 + seg_words < n_words ? w0 + seg_words : n_words;
+        uint32_t mine = 0;
+        for (uint64_t base = w0 + warp * 32; base < w1; base += kRadixWarps * 32) {
+            uint32_t ewin[NE + 1];
+            load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
+            uint32_t dist = first_end_after<NE>(ewin);
+            const uint64_t g0 = (base + lane) << 5;
+            const uint64_t limit = (base + lane < w1) ? n_bases : 0;
+            const uint32_t ends_cur = ewin[0];
+#pragma unroll 8
+            for (int o = 31; o >= 0; --o) {
+                dist = ((ends_cur >> o) & 1u) ? 0u : (dist == 0xffffffffu ? dist : dist + 1u);
+                mine += ((dist >= k - 1) && (g0 + (uint64_t)o + k <= limit)) ? 1u : 0u;
+            }
+        }
+        uint32_t seg_sum = 0;
+        (void)block_exscan(mine, scratch, &seg_sum);
+        if (threadIdx.x == 0) segtotal[seg] = seg_sum;
+    }
+}
+
+// ---- planner: chunks of at most cap keys (+ exact digit-1 offsets per chunk when seghist is given) ------------------
 // segprefix: n_segs + 1 words of scratch.  Chunk c = the longest run of segments after chunk c-1 whose k-mers fit cap.
-__global__ void __launch_bounds__(kNB) k_plan_chunks(RadixCtl* __restrict__ ctl, const uint32_t* __restrict__ seghist,
-                                                     const uint32_t* __restrict__ segtotal, uint64_t* __restrict__ segprefix,
-                                                     uint32_t n_segs, uint32_t nb1, uint64_t cap, uint64_t seg_keys,
-                                                     unsigned long long* __restrict__ err_ctr) {
-    __shared__ uint32_t scratch[8];
+// One block of 1024 threads.
+__global__ void __launch_bounds__(1024) k_plan_chunks(RadixCtl* __restrict__ ctl, const uint32_t* __restrict__ seghist,
+                                                      const uint32_t* __restrict__ segtotal, uint64_t* __restrict__ segprefix,
+                                                      uint32_t n_segs, uint32_t nb1, uint64_t cap, uint64_t seg_keys,
+                                                      unsigned long long* __restrict__ err_ctr) {
+    __shared__ uint32_t scratch[32];
     __shared__ uint32_t n_chunks_s;
     // inclusive prefix of the segment totals: segprefix[s] = keys of segments [0, s)
-    const uint32_t per = (n_segs + kNB - 1) / kNB;
-    const uint32_t i0 = threadIdx.x * per, i1 = i0 + per < n_segs ? i0 + per : n_segs;
+    const uint32_t per = (n_segs + blockDim.x - 1) / blockDim.x;
+    const uint32_t i0 = threadIdx.x * per < n_segs ? threadIdx.x * per : n_segs, i1 = i0 + per < n_segs ? i0 + per : n_segs;
     uint64_t mine = 0;
     for (uint32_t i = i0; i < i1; ++i) mine += segtotal[i];
-    uint64_t run = block_exscan_256_u64(mine, scratch, nullptr);
+    uint64_t run = block_exscan_u64(mine, scratch, nullptr);
     for (uint32_t i = i0; i < i1; ++i) { segprefix[i] = run; run += segtotal[i]; }
     if (i1 == n_segs && i0 < n_segs) segprefix[n_segs] = run;
     if (n_segs == 0 && threadIdx.x == 0) segprefix[0] = 0;
@@ -404,6 +521,7 @@ __global__ void __launch_bounds__(kNB) k_plan_chunks(RadixCtl* __restrict__ ctl,
         n_chunks_s = c;
     }
     __syncthreads();
+    if (!seghist) return;
     const uint32_t nc = n_chunks_s;
     for (uint32_t c = 0; c < nc; ++c) {
         const uint64_t s0 = ctl->chunk[c].seg_begin, s1 = ctl->chunk[c].seg_end;
@@ -413,29 +531,71 @@ __global__ void __launch_bounds__(kNB) k_plan_chunks(RadixCtl* __restrict__ ctl,
             for (uint64_t s = s0; s < s1; ++s) sum += seghist[s * nb1 + threadIdx.x];
         }
         uint64_t tot = 0;
-        const uint64_t pre = block_exscan_256_u64(sum, scratch, &tot);
-        ctl->chunk[c].coff[threadIdx.x] = pre;
-        if (threadIdx.x == kNB - 1) ctl->chunk[c].coff[kNB] = tot;
+        const uint64_t pre = block_exscan_u64(sum, scratch, &tot);
+        if (threadIdx.x < kNB1) ctl->chunk[c].coff[threadIdx.x] = pre;
+        if (threadIdx.x == 0) ctl->chunk[c].coff[kNB1] = tot;
     }
 }
 
-// per chunk, single GPU: arm the S1 cursors; A's coarse offsets are the chunk's own
-__global__ void __launch_bounds__(kNB) k_chunk_begin(RadixCtl* __restrict__ ctl, uint32_t c) {
+// Slices of phase B from the local bin counts n_b (every thread of a 1024-thread block passes the count of bin
+// threadIdx.x, 0 beyond nbl): cur_coff = exclusive prefix of the counts, slicestart = exclusive prefix of the slices.
+__device__ __forceinline__ void publish_bins(RadixCtl* __restrict__ ctl, uint64_t n_b, uint32_t slice_keys, uint32_t* scratch) {
+    uint64_t tot = 0;
+    const uint64_t pre = block_exscan_u64(n_b, scratch, &tot);
+    uint32_t n_slices = 0;
+    const uint32_t spre = block_exscan((uint32_t)((n_b + slice_keys - 1) / slice_keys), scratch, &n_slices);
+    ctl->cur_coff[threadIdx.x] = pre;
+    ctl->slicestart[threadIdx.x] = spre;
+    if (threadIdx.x == 0) {
+        ctl->cur_coff[kNB1] = tot;
+        ctl->slicestart[kNB1] = n_slices;
+        ctl->n_slices = n_slices;
+        ctl->n_insert = tot;
+        ctl->ticket[0] = ctl->ticket[1] = ctl->ticket[2] = 0ULL;
+    }
+}
+
+// per chunk, single GPU, exact mode: arm the S1 cursors; A's bin offsets are the chunk's own
+__global__ void __launch_bounds__(1024) k_chunk_begin(RadixCtl* __restrict__ ctl, uint32_t c, uint32_t slice_keys) {
+    __shared__ uint32_t scratch[32];
     const bool active = c < ctl->n_chunks;
     const uint64_t off = active ? ctl->chunk[c].coff[threadIdx.x] : 0ULL;
-    ctl->cursor1[threadIdx.x] = off;
-    ctl->cur_coff[threadIdx.x] = off;
+    const uint64_t nxt = active ? ctl->chunk[c].coff[threadIdx.x + 1] : 0ULL;
+    ctl->cursor1[threadIdx.x * kCursorStride] = off;
+    if (threadIdx.x == 0) ctl->chunk_active = active ? 1u : 0u;
+    publish_bins(ctl, nxt - off, slice_keys, scratch);
+}
+
+// per chunk, single GPU, paged mode: bins start empty, no page is taken
+__global__ void __launch_bounds__(1024) k_chunk_begin_paged(RadixCtl* __restrict__ ctl, uint32_t c) {
+    ctl->bin_pages[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
-        ctl->cur_coff[kNB] = active ? ctl->chunk[c].coff[kNB] : 0ULL;
-        ctl->chunk_active = active ? 1u : 0u;
-        ctl->n_insert = active ? ctl->chunk[c].n_keys : 0ULL;
+        ctl->chunk_active = c < ctl->n_chunks ? 1u : 0u;
+        ctl->page_next = 0ULL;
+        ctl->n_insert = 0ULL;
+        ctl->n_slices = 0u;
+    }
+}
+
+// ... and after S1: one slice of phase B per page, grouped by bin (bin_pages becomes the fill cursor of k_build_slices)
+__global__ void __launch_bounds__(1024) k_chunk_end_paged(RadixCtl* __restrict__ ctl) {
+    __shared__ uint32_t scratch[32];
+    const uint32_t n_p = ctl->chunk_active ? ctl->bin_pages[threadIdx.x] : 0u;
+    uint32_t n_slices = 0;
+    const uint32_t spre = block_exscan(n_p, scratch, &n_slices);
+    ctl->slicestart[threadIdx.x] = spre;
+    ctl->bin_pages[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) {
+        ctl->slicestart[kNB1] = n_slices;
+        ctl->n_slices = n_slices;
+        if (!ctl->chunk_active) ctl->n_insert = 0ULL;
         ctl->ticket[0] = ctl->ticket[1] = ctl->ticket[2] = 0ULL;
     }
 }
 
 // per round, multi-GPU: this rank's digit-1 counts of round c (zeros once its own chunks are used up), the payload of
 // the all-gather that precedes k_route_offsets
-__global__ void __launch_bounds__(kNB) k_round_hist(const RadixCtl* __restrict__ ctl, uint32_t c, uint32_t nb1, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(1024) k_round_hist(const RadixCtl* __restrict__ ctl, uint32_t c, uint32_t nb1, uint32_t* __restrict__ out) {
     if (threadIdx.x >= nb1) return;
     uint32_t v = 0;
     if (c < ctl->n_chunks) v = (uint32_t)(ctl->chunk[c].coff[threadIdx.x + 1] - ctl->chunk[c].coff[threadIdx.x]);
@@ -443,15 +603,15 @@ __global__ void __launch_bounds__(kNB) k_round_hist(const RadixCtl* __restrict__
 }
 
 // per chunk, multi-GPU: hist_all[s * nb1 + d] = k-mers rank s has for digit-1 bin d in this round (all-gathered).
-// Bin d = (owner o, local coarse bin lc).  Owner o's receive buffer is laid out bin-major, source-minor, so every
-// local coarse bin is one contiguous range there, exactly like buffer A of the single-GPU path:
+// Bin d = (owner o, local bin lc).  Owner o's receive buffer is laid out bin-major, source-minor, so every local
+// bin is one contiguous range there, exactly like buffer A of the single-GPU exact mode:
 //   position of (source s, bin d) in o's buffer = sum_{lc' < lc} sum_s' hist[s'][o, lc'] + sum_{s' < s} hist[s'][d]
 // Every rank evaluates the capacity check for every owner on the same data, so all ranks skip the round together.
-__global__ void __launch_bounds__(kNB) k_route_offsets(RadixCtl* __restrict__ ctl, uint32_t c, const uint32_t* __restrict__ hist_all,
-                                                       uint32_t n_ranks, uint32_t my_rank, uint32_t nb1, uint32_t nbl, uint64_t cap_recv,
-                                                       unsigned long long* __restrict__ err_ctr) {
-    __shared__ uint32_t scratch[8];
-    __shared__ uint64_t ex_s[kNB + 1];
+__global__ void __launch_bounds__(1024) k_route_offsets(RadixCtl* __restrict__ ctl, uint32_t c, const uint32_t* __restrict__ hist_all,
+                                                        uint32_t n_ranks, uint32_t my_rank, uint32_t nb1, uint32_t nbl, uint64_t cap_recv,
+                                                        uint32_t slice_keys, unsigned long long* __restrict__ err_ctr) {
+    __shared__ uint32_t scratch[32];
+    __shared__ uint64_t ex_s[kNB1 + 1];
     __shared__ uint32_t over_s;
     if (threadIdx.x == 0) over_s = 0u;
     uint64_t col = 0, before = 0;
@@ -462,9 +622,9 @@ __global__ void __launch_bounds__(kNB) k_route_offsets(RadixCtl* __restrict__ ct
             col += h;
         }
     uint64_t tot = 0;
-    const uint64_t ex = block_exscan_256_u64(col, scratch, &tot);
+    const uint64_t ex = block_exscan_u64(col, scratch, &tot);
     ex_s[threadIdx.x] = ex;
-    if (threadIdx.x == kNB - 1) ex_s[kNB] = tot;
+    if (threadIdx.x == 0) ex_s[kNB1] = tot;
     __syncthreads();
     if (threadIdx.x < nb1 && (threadIdx.x % nbl) == 0) {       // first bin of an owner: what that owner receives
         const uint32_t last = threadIdx.x + nbl;
@@ -475,44 +635,84 @@ __global__ void __launch_bounds__(kNB) k_route_offsets(RadixCtl* __restrict__ ct
     const bool mine_active = c < ctl->n_chunks;
     if (threadIdx.x < nb1) {
         const uint32_t owner_first = threadIdx.x - (threadIdx.x % nbl);
-        ctl->cursor1[threadIdx.x] = ex - ex_s[owner_first] + before;
+        ctl->cursor1[threadIdx.x * kCursorStride] = ex - ex_s[owner_first] + before;
     }
-    if (threadIdx.x <= nbl) {                                   // my own receive layout
-        const uint32_t first = my_rank * nbl;
-        ctl->cur_coff[threadIdx.x] = over ? 0ULL : ex_s[first + threadIdx.x] - ex_s[first];
-    }
+    // my own receive layout: local bin lc = global bin my_rank * nbl + lc
+    uint64_t n_b = 0;
+    if (threadIdx.x < nbl && !over) n_b = ex_s[my_rank * nbl + threadIdx.x + 1] - ex_s[my_rank * nbl + threadIdx.x];
     if (threadIdx.x == 0) {
-        const uint32_t first = my_rank * nbl;
         ctl->chunk_active = (!over && mine_active) ? 1u : 0u;   // gates S1 (sending)
-        ctl->n_insert = over ? 0ULL : ex_s[first + nbl] - ex_s[first];
         if (over) { ctl->recv_overflow = 1u; atomicOr(err_ctr, (unsigned long long)ERR_SEND_OVERFLOW); }
-        ctl->ticket[0] = ctl->ticket[1] = ctl->ticket[2] = 0ULL;
     }
+    publish_bins(ctl, n_b, slice_keys, scratch);
 }
 
 // ---- S1: extract + hash + tile sort by digit 1 -> buffer A --------------------------------------------------------
-// dst_of_owner == nullptr: everything goes to A.  Otherwise (multi-GPU) the run of bin d goes to
-// dst_of_owner[owner of d], the owner's receive buffer (peer-mapped over NVLink for the other ranks): the routing
-// kernel IS the exchange.
-template <int KW>
+// Exact mode (PAGED = false): run of bin d goes to position cursor1[d]++ of dst_of_owner[owner of d] (multi-GPU: the
+// owner's receive buffer, peer-mapped over NVLink for the other ranks: the routing kernel IS the exchange) or of A.
+// Paged mode: see PageGeom.
+// Dynamic shared memory: TileSmem<KW, kNB1, PAGED> + 256 owner pointers.
+template <int KW, bool PAGED>
 __global__ void __launch_bounds__(kRadixThreads, RadixCfg<KW>::MINB)
-k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, RadixCtl* __restrict__ ctl, uint32_t c,
-             const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ends, uint64_t n_words, uint64_t n_bases,
-             uint64_t seg0, uint64_t* __restrict__ A, uint64_t* const* __restrict__ dst_of_owner) {
+k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, const __grid_constant__ PageGeom pg,
+             RadixCtl* __restrict__ ctl, uint32_t c, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ends,
+             uint64_t n_words, uint64_t n_bases, uint64_t seg0, uint64_t* __restrict__ A, uint64_t* const* __restrict__ dst_of_owner,
+             uint16_t* __restrict__ page_bin, uint16_t* __restrict__ page_len, unsigned long long* __restrict__ err_ctr) {
     constexpr int OPT = RadixCfg<KW>::OPT;
-    __shared__ TileSmem<KW> sm;
-    __shared__ uint64_t* owner_base[kNB];
+    using Smem = TileSmem<KW, kNB1, PAGED>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    uint64_t** owner_base = reinterpret_cast<uint64_t**>(smem_raw + ((sizeof(Smem) + 15) & ~(size_t)15));
     if (!ctl->chunk_active) return;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    tile_smem_init<KW>(sm);
-    if (threadIdx.x < kNB) owner_base[threadIdx.x] = dst_of_owner ? dst_of_owner[threadIdx.x >> rg.owner_shift] : A;
+    tile_smem_init<KW, kNB1, PAGED>(sm);
+    if (threadIdx.x < 256) owner_base[threadIdx.x] = (dst_of_owner && threadIdx.x < (rg.nb1 >> rg.owner_shift)) ? dst_of_owner[threadIdx.x] : A;
+    const uint32_t page_keys = 1u << pg.page_log2;
+    if constexpr (PAGED) {
+        for (uint32_t b = threadIdx.x; b < kNB1; b += kRadixThreads) { sm.page_cur[b] = 0xffffffffu; sm.page_fill[b] = page_keys; sm.page_cnt[b] = 0u; }
+    }
     __syncthreads();
     const uint64_t seg_begin = ctl->chunk[c].seg_begin, seg_end = ctl->chunk[c].seg_end;
     const uint64_t seg_words = 1ULL << rg.seg_log2;
     const uint64_t lbg_mask = tv.lbg_mask;
+    unsigned long long my_keys = 0;                     // paged: keys this thread has placed (as the owner of its two bins)
     auto digit = [&](uint64_t h0) { return digit1_of(rg, lbg_mask, h0); };
-    auto reserve = [&](uint32_t bin, uint32_t n) { return (uint64_t)atomicAdd(&ctl->cursor1[bin], (unsigned long long)n); };
-    auto dst = [&](uint32_t d) { return owner_base[d]; };
+    auto reserve = [&](uint32_t bin, uint32_t n) -> unsigned long long {
+        if constexpr (!PAGED) {
+            return atomicAdd(&ctl->cursor1[bin * kCursorStride], (unsigned long long)n);
+        } else {
+            // only the part of the run that does not fit the block's current page of this bin needs fresh pages
+            const uint32_t room = page_keys - sm.page_fill[bin];
+            if (n <= room) return 0ULL;
+            const uint32_t m = (n - room + page_keys - 1) >> pg.page_log2;
+            return atomicAdd(&ctl->page_next, (unsigned long long)m);
+        }
+    };
+    auto place = [&](uint32_t bin, uint32_t n, uint32_t start, unsigned long long p) {
+        if constexpr (!PAGED) {
+            sm.gdelta[bin] = (long long)p - (long long)start;
+        } else {
+            const uint32_t cur = sm.page_cur[bin], fill = sm.page_fill[bin];
+            const uint32_t room = page_keys - fill;
+            my_keys += n;
+            sm.gdelta[bin] = (long long)(((uint64_t)cur << pg.page_log2) + fill) - (long long)start;   // unused when room == 0
+            if (n <= room) {
+                sm.split[bin] = 0xffffffffu;
+                sm.page_fill[bin] = fill + n;
+                return;
+            }
+            const uint32_t rest = n - room, m = (rest + page_keys - 1) >> pg.page_log2;
+            if (p + m > pg.n_pages) { atomicOr(err_ctr, (unsigned long long)ERR_PLAN); p = 0; }   // cannot happen: the planner leaves room
+            if (cur != 0xffffffffu) page_len[cur] = (uint16_t)page_keys;        // the old page is completed by this run
+            for (uint32_t q = 0; q < m; ++q) { page_bin[p + q] = (uint16_t)bin; if (q + 1 < m) page_len[p + q] = (uint16_t)page_keys; }
+            sm.split[bin] = start + room;
+            sm.gdelta2[bin] = (long long)(p << pg.page_log2) - (long long)(start + room);
+            sm.page_cur[bin] = (uint32_t)p + m - 1;
+            sm.page_fill[bin] = rest - ((m - 1) << pg.page_log2);
+            sm.page_cnt[bin] += m;
+        }
+    };
+    auto dst = [&](uint32_t d) { return owner_base[d >> rg.owner_shift]; };
     for (uint64_t seg = seg_begin + blockIdx.x; seg < seg_end; seg += gridDim.x) {
         const uint64_t w0 = (seg0 + seg) << rg.seg_log2;
         const uint64_t w1 = w0 + seg_words < n_words ? w0 + seg_words : n_words;
@@ -529,9 +729,21 @@ k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ Radix
                     if (kl.kmer_at(o0 - j, tv.L.k, tv.hp, key)) vmask |= 1u << j;
                     Hs[j] = hash_key<KW>(key, tv.hp);
                 }
-                tile_partition<KW>(sm, Hs, vmask, rg.d1, digit, reserve, dst);
+                tile_partition<KW, kNB1, PAGED>(sm, Hs, vmask, rg.d1, digit, reserve, place, dst);
             }
         }
+    }
+    if constexpr (PAGED) {
+        // the block's last page of every bin is partly filled; its page counts and keys go to the chunk's totals
+        for (uint32_t b = threadIdx.x; b < kNB1; b += kRadixThreads) {
+            const uint32_t cur = sm.page_cur[b];
+            if (cur != 0xffffffffu) page_len[cur] = (uint16_t)sm.page_fill[b];
+            if (sm.page_cnt[b]) atomicAdd(&ctl->bin_pages[b], sm.page_cnt[b]);
+        }
+        const unsigned full = 0xffffffffu;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) my_keys += __shfl_xor_sync(full, my_keys, sft);
+        if (lane == 0 && my_keys) atomicAdd(&ctl->n_insert, my_keys);
     }
 }
 
@@ -684,10 +896,10 @@ __global__ void __launch_bounds__(kRadixThreads, RadixCfg<KW>::MINB)
 k_part_keys(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, RadixCtl* __restrict__ ctl,
             const uint64_t* __restrict__ A, unsigned long long* __restrict__ fcur, uint64_t* __restrict__ B) {
     constexpr int OPT = RadixCfg<KW>::OPT;
-    __shared__ TileSmem<KW> sm;
+    __shared__ TileSmem<KW, kNB, false> sm;
     __shared__ ItemFeed<KW> feed;
     if (!ctl->group.active) return;
-    tile_smem_init<KW>(sm);
+    tile_smem_init<KW, kNB, false>(sm);
     item_feed_init<KW>(feed, ctl, rg.nbl);
     const uint64_t lbg_mask = tv.lbg_mask;
     auto digit = [&](uint64_t h0) { return digit2_of(rg, lbg_mask, h0); };
@@ -706,8 +918,9 @@ k_part_keys(const __grid_constant__ TableView tv, const __grid_constant__ RadixG
 #pragma unroll
             for (int w = 0; w < KW; ++w) Hs[j].w[w] = v ? __ldcs(A + i * KW + w) : 0ULL;
         }
-        auto reserve = [&](uint32_t bin, uint32_t n) { return (uint64_t)atomicAdd(cur + bin, (unsigned long long)n); };
-        tile_partition<KW>(sm, Hs, vmask, rg.d2, digit, reserve, dst);
+        auto reserve = [&](uint32_t bin, uint32_t n) { return atomicAdd(cur + bin, (unsigned long long)n); };
+        auto place = [&](uint32_t bin, uint32_t, uint32_t start, unsigned long long p) { sm.gdelta[bin] = (long long)p - (long long)start; };
+        tile_partition<KW, kNB, false>(sm, Hs, vmask, rg.d2, digit, reserve, place, dst);
     }
 }
 
@@ -732,9 +945,8 @@ k_part_keys(const __grid_constant__ TableView tv, const __grid_constant__ RadixG
 #ifndef TSX_INSERT_MINB
 #define TSX_INSERT_MINB 6
 #endif
-#ifndef TSX_INS_PREFETCH
-#define TSX_INS_PREFETCH 0          // measured: prefetching the next slice's buckets into L2 costs 10 % (221 -> 242 ms on config 2)
-#endif
+// (Measured and dropped: prefetching the next slice's home buckets into L2 with prefetch.global.L2 costs 10 %,
+// 221 -> 242 ms on config 2; the kernel is bound by the atomic-return path, not by latency.)
 
 struct CombSmem {
     unsigned long long key[kCombSlots];
@@ -761,7 +973,6 @@ __device__ __noinline__ void insert_slice_skewed(const TableView& tv, const uint
         for (int j = 0; j < KW; ++j) H.w[j] = valid ? __ldcg(src + i * KW + j) : 0ULL;
         uint64_t cnt = 1;
         bool lead = valid;
-        unsigned dups = 0;
         const unsigned vm = __ballot_sync(full, valid);
         if (valid) {
             unsigned peers = __match_any_sync(vm, H.w[0]);
@@ -770,10 +981,12 @@ __device__ __noinline__ void insert_slice_skewed(const TableView& tv, const uint
             cnt = (uint64_t)__popc(peers);
             lead = (unsigned)(__ffs(peers) - 1) == lane;
         }
-        dups = __popc(vm) - __popc(__ballot_sync(full, lead));
         if (!lead) continue;
-        if (dups >= 4) {
-            // combine across the block before touching the table
+        {
+            // combine across the block before touching the table: every key of a skewed slice goes through the
+            // shared-memory combiner, so copies that are far apart in the slice are merged too (a k-mer that makes up
+            // 1 % of a table region reaches the table once per slice instead of ten times; what matters is not the
+            // atomics saved but that all blocks work in the same region, i.e. on the same hot entries, at once)
             const uint32_t slot = (uint32_t)(H.w[0] ^ (H.w[0] >> 40)) & (kCombSlots - 1);
             const unsigned long long tagged = (H.w[0] & ~0xffffULL) | (unsigned long long)((i - lo) + 1);
             const unsigned long long oldk = atomicCAS(&comb.key[slot], 0ULL, tagged);
@@ -810,59 +1023,79 @@ __device__ __noinline__ void insert_slice_skewed(const TableView& tv, const uint
     flush_stats(tv, st);
 }
 
+// Work items of phase B.  desc[item] = (position of the slice's first key in A, number of keys).
+// Exact mode: slice j of local bin b = keys [j * slice_keys, ...) of the bin, which starts at cur_coff[b].
+// Paged mode: one slice per page; the pages of a bin take consecutive items in any order (bin_pages is the cursor).
+__global__ void __launch_bounds__(kBlockThreads) k_build_slices(RadixCtl* __restrict__ ctl, const __grid_constant__ PageGeom pg,
+                                                                const uint16_t* __restrict__ page_bin, const uint16_t* __restrict__ page_len,
+                                                                uint32_t nbl, uint32_t slice_keys, ulonglong2* __restrict__ desc) {
+    if (pg.paged) {
+        const uint64_t n_used = ctl->page_next < pg.n_pages ? ctl->page_next : pg.n_pages;
+        for (uint64_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_used; p += (uint64_t)gridDim.x * blockDim.x) {
+            const uint32_t b = page_bin[p];
+            if (b >= nbl) continue;
+            const uint32_t pos = ctl->slicestart[b] + atomicAdd(&ctl->bin_pages[b], 1u);
+            desc[pos] = make_ulonglong2(p << pg.page_log2, (unsigned long long)page_len[p]);
+        }
+        return;
+    }
+    const uint32_t n_slices = ctl->n_slices;
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_slices; item += gridDim.x * blockDim.x) {
+        uint32_t lo_b = 0, hi_b = nbl;         // largest b with slicestart[b] <= item (empty bins share their successor's start)
+        while (hi_b - lo_b > 1) {
+            const uint32_t mid = (lo_b + hi_b) >> 1;
+            if (ctl->slicestart[mid] <= item) lo_b = mid; else hi_b = mid;
+        }
+        const uint64_t v = (uint64_t)(item - ctl->slicestart[lo_b]) * slice_keys;
+        const uint64_t n_b = ctl->cur_coff[lo_b + 1] - ctl->cur_coff[lo_b];
+        const uint64_t len = n_b - v < slice_keys ? n_b - v : slice_keys;
+        desc[item] = make_ulonglong2(ctl->cur_coff[lo_b] + v, len);
+    }
+}
+
+template <int KW> struct InsertCfg {
+    static constexpr int R = KW == 1 ? 4 : (KW == 2 ? 2 : 1);          // keys per thread per slice
+    static constexpr uint32_t SLICE = kBlockThreads * R;
+};
+
 template <int KW, int W, bool WARP_AGG>
 __global__ void __launch_bounds__(kBlockThreads, TSX_INSERT_MINB)
-k_insert_keys(const __grid_constant__ TableView tv, RadixCtl* __restrict__ ctl, const uint64_t* __restrict__ src) {
-    constexpr int R = KW == 1 ? 4 : (KW == 2 ? 2 : 1);          // keys per thread per slice
-    constexpr uint32_t SLICE = kBlockThreads * R;
+k_insert_keys(const __grid_constant__ TableView tv, RadixCtl* __restrict__ ctl, const uint64_t* __restrict__ src,
+              const ulonglong2* __restrict__ desc) {
+    constexpr int R = InsertCfg<KW>::R;
     const unsigned full = 0xffffffffu;
-    __shared__ unsigned long long item_s;
+    __shared__ unsigned long long item_lo_s;
+    __shared__ uint32_t item_len_s;
     __shared__ CombSmem comb;
-    const unsigned long long n = ctl->n_insert;
-    if (n == 0) return;
+    const unsigned long long n_items = ctl->n_slices;
+    if (n_items == 0) return;
     LocalStats st;
     const unsigned lane = threadIdx.x & 31u;
     for (uint32_t i = threadIdx.x; i < kCombSlots; i += kBlockThreads) { comb.key[i] = 0ULL; comb.cnt[i] = 0u; }
-    if (threadIdx.x == 0) comb.used = 0u;
-    const unsigned long long n_items = (n + SLICE - 1) / SLICE;
-    // Optional software pipeline over slices (TSX_INS_PREFETCH): while the block inserts the keys of slice j, the home
-    // buckets of slice j+1 are requested into L2.  Thread 0 always keeps one more ticket in flight.
-    auto prefetch_slice = [&](unsigned long long it) {
-#if TSX_INS_PREFETCH
-        if (it >= n_items) return;
-        const uint64_t lo = it * SLICE;
-        const uint64_t hi = lo + SLICE < n ? lo + SLICE : n;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const uint64_t i = lo + (uint64_t)r * kBlockThreads + threadIdx.x;
-            if (i < hi) prefetch_bucket_l2(tv.words + ((((__ldcg(src + i * KW) & tv.lbl_mask) + 1) & tv.lbl_mask) << 2));
-        }
-#else
-        (void)it;
-#endif
-    };
+    // thread 0 keeps the ticket of the next slice in flight while the block works on the current one
     unsigned long long ahead = 0ULL;
     if (threadIdx.x == 0) {
-        item_s = atomicAdd(&ctl->ticket[2], 1ULL); ahead = atomicAdd(&ctl->ticket[2], 1ULL);
-        if (blockIdx.x == 0) atomicAdd(tv.ctr + CTR_ADDED, n);      // all keys of the launch; insert_hashed<LEAN> takes back what it skips
+        comb.used = 0u;
+        ahead = atomicAdd(&ctl->ticket[2], 1ULL);
+        if (blockIdx.x == 0) atomicAdd(tv.ctr + CTR_ADDED, ctl->n_insert);   // all keys of the launch; insert_hashed<LEAN> takes back what it skips
     }
-    __syncthreads();
-    unsigned long long item = item_s;
-    prefetch_slice(item);
-    while (item < n_items) {
-        __syncthreads();                                  // everyone has read item_s
+    while (true) {
+        __syncthreads();                                  // everyone has read the previous slice's descriptor
         if (threadIdx.x == 0) {
             // once the reprobe limit was reached anywhere the run is lost (the reference exits with 42): stop early
             const bool full_table = (__ldcg(tv.ctr + CTR_ERRORS) & (unsigned long long)ERR_TABLE_FULL) != 0ULL;
-            item_s = full_table ? n_items : ahead;
-            if (ahead < n_items) ahead = atomicAdd(&ctl->ticket[2], 1ULL);
+            if (ahead < n_items && !full_table) {
+                const ulonglong2 d = __ldg(desc + ahead);
+                item_lo_s = d.x; item_len_s = (uint32_t)d.y;
+                ahead = atomicAdd(&ctl->ticket[2], 1ULL);
+            } else {
+                item_len_s = 0u;
+            }
         }
         __syncthreads();
-        const unsigned long long item_next = item_s;
-        const uint64_t lo = item * SLICE;
-        const uint64_t hi = lo + SLICE < n ? lo + SLICE : n;
-        item = item_next;
-        prefetch_slice(item_next);
+        const uint64_t lo = item_lo_s;
+        const uint64_t hi = lo + item_len_s;
+        if (hi == lo) break;
         // Pass 1 reads word 0 of the thread's keys only to see whether neighbours are equal; pass 2 reads the keys
         // again (L1 / L2 hits) one at a time with the next one in flight.  Holding all R keys across the inserts
         // instead costs 6-14 registers, which at 6 resident blocks per SM means spills.
