@@ -286,11 +286,17 @@ def _route_all(tsx, shards, d_packed, d_off, n_reads, n_bases, recv_cap_keys=0):
     return rounds, cap
 
 
+@pytest.mark.parametrize("pool", [False, True], ids=["from_receive_buffer", "fine_pass_into_page_pool"])
 @pytest.mark.parametrize("k,n_shards,mode,region", [(31, 2, 1, "12"), (31, 8, 0, "12"), (63, 4, 2, "14"), (127, 2, 1, "12"),
                                                     (31, 4, 3, "30")])
-def test_sharded_route_and_insert(tsx, k, n_shards, mode, region, monkeypatch):
+def test_sharded_route_and_insert(tsx, k, n_shards, mode, region, pool, monkeypatch):
     monkeypatch.setenv("TSXC_REGION_LOG2", region)    # "30": no fine regions at all, routing by owner only
     monkeypatch.setenv("TSXC_SEG_LOG2", "9")          # many planner segments, several rounds
+    if pool:
+        # the two-level mode of large shards: groups of the receive buffer take a second, local partition pass into a
+        # pool of 8-key pages that holds a third of a round (default pages of one slice would not fit these tiny buffers)
+        monkeypatch.setenv("TSXC_PAGE_LOG2", "3")
+        monkeypatch.setenv("TSXC_POOL_KEYS", "40000")
     lib = tsx._lib.load()
     seqs = orc.gen_reads(seed=31, n_reads=3000, read_len=150, mode=mode,
                          genome_len=(1 << 8) if mode == 2 else (50_000 if mode == 3 else 0), sub_rate_q16=328 if mode == 3 else 0)
@@ -317,7 +323,11 @@ def test_sharded_route_and_insert(tsx, k, n_shards, mode, region, monkeypatch):
         assert rounds >= 2
         got = {}
         for hm in shards:
-            assert hm.stats()["error_flags"] == 0
+            st = hm.stats()
+            assert st["error_flags"] == 0
+            if region != "30":
+                assert st["radix_digit2_bits"] > 0
+                assert st["group_cap_keys"] == 8 if pool else st["group_cap_keys"] in (0, 1024, 512, 256)
             keys, counts = hm.getAllKmers()
             for key, c in zip(keys.tolist(), counts.tolist()):
                 assert tuple(key) not in got, "k-mer present in two shards"

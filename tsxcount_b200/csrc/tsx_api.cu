@@ -79,6 +79,7 @@ struct tsxc_table {
     uint32_t* d_segtotal = nullptr; size_t cap_segtotal = 0;
     uint64_t* d_segprefix = nullptr; size_t cap_segprefix = 0;
     uint64_t* d_A = nullptr; uint64_t cap_A = 0;               // keys, sorted by digit 1 (multi-GPU: the receive buffer)
+    uint64_t* d_B = nullptr; uint64_t cap_B = 0;               // two-level mode: the page pool a group of A is sorted into
     bool cap_A_limited = false;                                // cap_A was set by free memory, not by a batch size
     uint32_t* d_fhist = nullptr;                               // kMaxFine
     unsigned long long* d_fcur = nullptr;                      // kMaxFine
@@ -159,6 +160,7 @@ int release_radix_buffers(tsxc_table* t) {
     if (t->peers_set) return TSXC_OK;          // exported to peers: must stay where it is
     CU(cudaStreamSynchronize(t->stream));
     CU(cudaFree(t->d_A)); t->d_A = nullptr;
+    if (t->d_B) { CU(cudaFree(t->d_B)); t->d_B = nullptr; t->cap_B = 0; }
     if (t->d_page_bin) { CU(cudaFree(t->d_page_bin)); t->d_page_bin = nullptr; t->cap_page_bin = 0; }
     if (t->d_page_len) { CU(cudaFree(t->d_page_len)); t->d_page_len = nullptr; t->cap_page_len = 0; }
     if (t->d_slices) { CU(cudaFree(t->d_slices)); t->d_slices = nullptr; t->cap_slices = 0; }
@@ -221,17 +223,25 @@ int status_from_flags(tsxc_table* t, uint64_t flags) {
 
 // ---- region-sorted pipeline: geometry, buffers, launch sequence -------------------------------------------------
 
-// One digit for the insert pipeline: regions of 2^region_log2 bytes of a shard of 2^LBl buckets (32 bytes each), at most
-// kNB1 bins including the owner bits.
+// Digits of the insert pipeline: regions of 2^region_log2 bytes of a shard of 2^LBl buckets (32 bytes each), at most
+// kNB1 of them.  One shard: one digit.  Hash-sharded: a routing digit (owner + coarse local bits) and a local fine digit.
 RadixGeom make_radix_geom(const Layout& L, uint32_t region_log2, uint32_t seg_log2) {
     RadixGeom g{};
     const uint32_t table_log2 = L.LBl + 5;
     uint32_t fb = table_log2 > region_log2 ? table_log2 - region_log2 : 0;   // region bits inside the shard
     fb = std::min<uint32_t>(fb, L.LBl);
-    g.d1 = std::min<uint32_t>(10, L.shard_bits + fb);
-    g.d2 = 0;
-    g.nb1 = 1u << g.d1; g.nb2 = 1u; g.nbl = 1u << (g.d1 - L.shard_bits);
-    g.shift1 = L.LBg - g.d1; g.shift2 = g.shift1;
+    if (L.shard_bits == 0) {
+        g.d1 = std::min<uint32_t>(10, fb);
+        g.d2 = 0;
+    } else {
+        // hash-sharded: the routing pass keeps runs of 128 bytes for NVLink (at most 256 bins over all shards), the
+        // receiver adds the remaining bits in a second, local pass (tsx_radix.cuh, two-level mode)
+        g.d1 = std::min<uint32_t>(8, L.shard_bits + fb);
+        const uint32_t c = g.d1 - L.shard_bits;
+        g.d2 = std::min<uint32_t>(10 - c, fb - c);
+    }
+    g.nb1 = 1u << g.d1; g.nb2 = 1u << g.d2; g.nbl = 1u << (g.d1 - L.shard_bits);
+    g.shift1 = L.LBg - g.d1; g.shift2 = L.LBg - g.d1 - g.d2;
     g.owner_shift = g.d1 - L.shard_bits;
     g.seg_log2 = seg_log2;
     return g;
@@ -283,21 +293,36 @@ int radix_reserve(tsxc_table* t, uint64_t positions, bool for_peers = false) {
     const uint64_t reserve = env_u64("TSXC_RESERVE_MB", 4096) << 20;     // staging slots, lookups, the caller
     const uint64_t budget = free_b > reserve ? free_b - reserve : free_b / 2;
     const uint32_t slice = slice_keys_of(t->L);
-    // per key: the key itself, its share of a slice descriptor and of the page records
-    const double bytes_per_key = 8.0 * t->L.KW + 20.0 / slice;
+    // per key: the key itself (+ 1/4 in the page pool of the two-level mode), its share of a slice descriptor and of the
+    // page records
+    const bool two_level = g.d2 > 0;
+    const double bytes_per_key = 8.0 * t->L.KW * (two_level ? 1.25 : 1.0) + 20.0 / slice;
     const uint64_t cap_max = (uint64_t)((double)budget / bytes_per_key);
     uint64_t cap = std::min(want, cap_max);
     if (cap < 2 * seg_keys) return fail(t, TSXC_E_NOMEM, "not enough free device memory for the key buffer of the insert pipeline");
-    // paged addressing: pages of one slice (fewer keys only for tests); every (thread block of S1, bin) may leave a page
-    // partly empty, so the pool has to be much larger than that
-    PageGeom pg{};
-    // thread blocks of S1: two per SM (98 KB of shared memory each), never more than the batch has segments
+    // thread blocks of the partition kernels: two per SM, never more than the batch has segments
     const uint64_t grid_max = std::min<uint64_t>((uint64_t)t->sms * 2, std::max<uint64_t>(1, (positions + seg_keys - 1) / seg_keys));
+    // paged addressing: pages of one slice (fewer keys only for tests); every (thread block, bin) may leave a page partly
+    // empty, so the pool has to be much larger than that
+    PageGeom pg{};
     uint32_t slice_log2 = 0;
     while ((1u << (slice_log2 + 1)) <= slice) ++slice_log2;
-    if (t->L.shard_bits == 0 && !for_peers && !env_u64("TSXC_NO_PAGING", 0)) {
-        uint32_t pl = slice_log2;
-        if (const uint64_t e = env_u64("TSXC_PAGE_LOG2", 0)) pl = (uint32_t)std::min<uint64_t>(slice_log2, std::max<uint64_t>(e, 2));
+    uint32_t pl = slice_log2;
+    if (const uint64_t e = env_u64("TSXC_PAGE_LOG2", 0)) pl = (uint32_t)std::min<uint64_t>(slice_log2, std::max<uint64_t>(e, 2));
+    uint64_t cap_b = 0;
+    if (two_level) {
+        // the pool holds a quarter of the receive buffer; without room for four coarse bins' slack the groups would be
+        // tiny: then phase B reads the receive buffer directly (coarse regions: slower, still exact)
+        cap_b = std::max<uint64_t>(cap / 4, 4 * seg_keys);
+        if (const uint64_t e = env_u64("TSXC_POOL_KEYS", 0)) cap_b = e;
+        const uint64_t n_pages = std::min<uint64_t>(cap_b >> pl, 0x7fffffffULL);
+        if (n_pages >= 4ULL * grid_max * g.nb2 && !env_u64("TSXC_NO_PAGING", 0)) {
+            pg.paged = 1; pg.page_log2 = pl; pg.n_pages = (uint32_t)n_pages;
+            cap_b = n_pages << pl;
+        } else {
+            cap_b = 0;
+        }
+    } else if (t->L.shard_bits == 0 && !for_peers && !env_u64("TSXC_NO_PAGING", 0)) {
         const uint64_t n_pages = std::min<uint64_t>(cap >> pl, 0x7fffffffULL);
         if (n_pages >= 4ULL * grid_max * g.nbl) {
             pg.paged = 1; pg.page_log2 = pl; pg.n_pages = (uint32_t)n_pages;
@@ -305,6 +330,10 @@ int radix_reserve(tsxc_table* t, uint64_t positions, bool for_peers = false) {
         }
     }
     CU(cudaMalloc(&t->d_A, cap * t->L.KW * sizeof(uint64_t)));
+    if (cap_b) {
+        cudaError_t e = cudaMalloc(&t->d_B, cap_b * t->L.KW * sizeof(uint64_t));
+        if (e != cudaSuccess) { cudaGetLastError(); cudaFree(t->d_A); t->d_A = nullptr; return fail(t, TSXC_E_NOMEM, "page pool allocation failed"); }
+    }
     const size_t n_slices_max = pg.paged ? (size_t)pg.n_pages : (size_t)(cap / slice) + g.nbl + 1;
     if ((rc = ensure(t, &t->d_slices, &t->cap_slices, n_slices_max))) return rc;
     if (pg.paged && (rc = ensure(t, &t->d_page_bin, &t->cap_page_bin, (size_t)pg.n_pages))) return rc;
@@ -312,37 +341,79 @@ int radix_reserve(tsxc_table* t, uint64_t positions, bool for_peers = false) {
     if (!t->d_A) return fail(t, TSXC_E_NOMEM, "not enough free device memory for the tables of the insert pipeline");
     t->pg = pg;
     t->part_grid = (int)grid_max;
-    t->cap_A = cap; t->cap_A_limited = cap < want;
+    t->cap_A = cap; t->cap_B = cap_b; t->cap_A_limited = cap < want;
     return TSXC_OK;
 }
 
+template <int KW> constexpr size_t part_smem_bytes(bool paged) {
+    return ((paged ? sizeof(TileSmem<KW, kNB1, true>) : sizeof(TileSmem<KW, kNB1, false>)) + 15) / 16 * 16 + 256 * sizeof(uint64_t*) +
+           (paged ? sizeof(PageState) : 0);
+}
+template <int KW> constexpr size_t fine_smem_bytes() {
+    return ((sizeof(TileSmem<KW, kNB, true>) + 15) / 16 * 16 + sizeof(ItemFeed<KW>) + 15) / 16 * 16 + sizeof(PageState);
+}
+
 // Phase B over the keys currently described by ctl (cur_coff / slicestart): slice descriptors, then the insert.
+// Two-level mode (hash-sharded tables): A is cut into groups, every group goes through the fine partition into the page
+// pool B first.
 int launch_sort_insert(tsxc_table* t, cudaStream_t s) {
     const RadixGeom& g = t->rg;
     const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
     static const int insert_blocks_per_sm = [] { const int v = (int)env_u64("TSXC_INSERT_GRID", 0); return (v >= 1 && v <= 16) ? v : 6; }();
     const int grid_b = t->sms * insert_blocks_per_sm;
-    PhaseTimer pt(t, s, PH_INSERT);
-    k_build_slices<<<t->sms * 4, kBlockThreads, 0, s>>>(t->d_ctl, t->pg, t->d_page_bin, t->d_page_len, g.nbl, slice_keys_of(t->L), t->d_slices);
-#define M(KW_, W_)                                                                                             \
-    if (agg) k_insert_keys<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, t->d_ctl, t->d_A, t->d_slices);   \
-    else k_insert_keys<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, t->d_ctl, t->d_A, t->d_slices)
-    TSX_DISPATCH(t->L, M);
+    const uint32_t slice = slice_keys_of(t->L);
+#define INS_(KW_, W_, SRC_)                                                                                        \
+    if (agg) k_insert_keys<KW_, W_, true><<<grid_b, kBlockThreads, 0, s>>>(t->tv, t->d_ctl, SRC_, t->d_slices);    \
+    else k_insert_keys<KW_, W_, false><<<grid_b, kBlockThreads, 0, s>>>(t->tv, t->d_ctl, SRC_, t->d_slices)
+    if (g.d2 == 0 || !t->d_B) {
+        PhaseTimer pt(t, s, PH_INSERT);
+        PageGeom pg = t->pg;
+        if (g.d2) pg.paged = 0;                     // two-level geometry without a pool: straight from the receive buffer
+        k_build_slices<<<t->sms * 4, kBlockThreads, 0, s>>>(t->d_ctl, pg, t->d_page_bin, t->d_page_len, g.nbl, slice, t->d_slices);
+#define M(KW_, W_) INS_(KW_, W_, t->d_A)
+        TSX_DISPATCH(t->L, M);
 #undef M
-    pt.end(2);
+        pt.end(2);
+        return TSXC_OK;
+    }
+    const int grid2 = t->part_grid > 0 ? t->part_grid : t->sms * 2;
+    // a group ends when the pool could run dry: the slack of one coarse bin is at most a quarter of the pool by construction
+    // and a bin cut by a group boundary pays it twice, so every group but the last gets through at least a quarter of the
+    // pool's worth of (keys + slack) and this many group slots always suffice (the last slot checks it)
+    const uint64_t pages_total = (t->cap_A >> t->pg.page_log2) + (uint64_t)g.nbl * g.nb2 * grid2;
+    const uint32_t n_groups = (uint32_t)(pages_total / (t->pg.n_pages / 4) + 2);
+    unsigned long long* err = t->d_ctr + CTR_ERRORS;
+    for (uint32_t gi = 0; gi < n_groups; ++gi) {
+        {
+            PhaseTimer pt(t, s, PH_PART2);
+#define M(KW_)                                                                                                             \
+            k_plan_group_paged<KW_><<<1, kNB, 0, s>>>(t->d_ctl, gi, n_groups, g.nbl, g.nb2, t->pg, (uint32_t)grid2, err);            \
+            k_part_keys_paged<KW_><<<grid2, kRadixThreads, fine_smem_bytes<KW_>(), s>>>(t->tv, g, t->pg, t->d_ctl, t->d_A, t->d_B, \
+                                                                                        t->d_page_bin, t->d_page_len, err)
+            TSX_DISPATCH_KW(t->L, M);
+#undef M
+            k_chunk_end_paged<<<1, 1024, 0, s>>>(t->d_ctl);
+            pt.end(3);
+        }
+        PhaseTimer pt(t, s, PH_INSERT);
+        k_build_slices<<<t->sms * 4, kBlockThreads, 0, s>>>(t->d_ctl, t->pg, t->d_page_bin, t->d_page_len, g.nbl * g.nb2, slice, t->d_slices);
+#define M(KW_, W_) INS_(KW_, W_, t->d_B)
+        TSX_DISPATCH(t->L, M);
+#undef M
+        pt.end(2);
+    }
+#undef INS_
     return TSXC_OK;
 }
 
-template <int KW> constexpr size_t part_smem_bytes(bool paged) {
-    return ((paged ? sizeof(TileSmem<KW, kNB1, true>) : sizeof(TileSmem<KW, kNB1, false>)) + 15) / 16 * 16 + 256 * sizeof(uint64_t*);
-}
 
 // The partition kernels use more than the 48 KB of shared memory a kernel gets by default.
 int opt_in_shared_memory(tsxc_table* t) {
 #define M(KW_)                                                                                                                     \
     CU(cudaFuncSetAttribute(k_hist_reads<KW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes));                    \
     CU(cudaFuncSetAttribute(k_part_reads<KW_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(false))); \
-    CU(cudaFuncSetAttribute(k_part_reads<KW_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(true)))
+    CU(cudaFuncSetAttribute(k_part_reads<KW_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(true)));   \
+    CU(cudaFuncSetAttribute(k_part_keys_paged<KW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fine_smem_bytes<KW_>()))
     TSX_DISPATCH_KW(t->L, M);
 #undef M
     return TSXC_OK;
@@ -441,7 +512,8 @@ int launch_count_reads_radix(tsxc_table* t, const uint64_t* d_packed, const uint
 int launch_count_marked(tsxc_table* t, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words, uint64_t n_bases,
                         cudaStream_t s) {
     // the pipeline pays off once every table region receives a few thousand k-mers per pass
-    if (t->radix_on && !(t->L.flags & TSXC_FLAG_DIRECT) && n_words >= (uint64_t)t->rg.nbl * 4)
+    // (a shard of a hash-sharded table is fed through tsxc_route_*; reads handed to it directly take the fused kernel)
+    if (t->radix_on && t->L.shard_bits == 0 && !t->peers_set && !(t->L.flags & TSXC_FLAG_DIRECT) && n_words >= (uint64_t)t->rg.nbl * 4)
         return launch_count_reads_radix(t, d_packed, d_ends, n_words, n_bases, s);
     const int grid = grid_for(t, n_words);
     const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
@@ -702,7 +774,7 @@ int tsxc_destroy(tsxc_table* t) {
     for (auto& m : t->marks) if (m) cudaEventDestroy(m);
     for (auto& a : t->acc) { cudaFree(a.d_packed); cudaFree(a.d_ends); if (a.consumed) cudaEventDestroy(a.consumed); }
     if (t->acc_copied) cudaEventDestroy(t->acc_copied);
-    cudaFree(t->d_A); cudaFree(t->d_page_bin); cudaFree(t->d_page_len); cudaFree(t->d_slices); cudaFree(t->d_ctl); cudaFree(t->d_seghist); cudaFree(t->d_segtotal); cudaFree(t->d_segprefix);
+    cudaFree(t->d_A); cudaFree(t->d_B); cudaFree(t->d_page_bin); cudaFree(t->d_page_len); cudaFree(t->d_slices); cudaFree(t->d_ctl); cudaFree(t->d_seghist); cudaFree(t->d_segtotal); cudaFree(t->d_segprefix);
     cudaFree(t->d_fhist); cudaFree(t->d_fcur); cudaFree(t->d_peers); cudaFree(t->d_ticket_k0);
     cudaFree(t->d_ends); cudaFree(t->d_keys); cudaFree(t->d_counts); cudaFree(t->d_nout); cudaFree(t->d_text); cudaFree(t->d_pairs[0]); cudaFree(t->d_pairs[1]);
     cudaFree(t->d_ctr); cudaFree(t->d_words);

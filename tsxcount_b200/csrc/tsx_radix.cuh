@@ -302,10 +302,76 @@ struct TileSmem {
     long long gdelta2[PAGED ? NB : 2];   // paged: the same for the part of the run that lies in freshly taken pages
     uint32_t binstart[NB];
     uint32_t split[PAGED ? NB : 4];      // paged: tile index at which the run continues in the fresh pages
-    uint32_t page_cur[PAGED ? NB : 4];   // paged: the block's current page of the bin (0xffffffff: none yet)
-    uint32_t page_fill[PAGED ? NB : 4];  // paged: keys already in it
-    uint32_t page_cnt[PAGED ? NB : 4];   // paged: pages this block has taken for the bin
     uint32_t scratch[32];
+};
+
+// A thread block's view of the page pool: its current page of every bin.  Lives in shared memory; bin b is only ever
+// touched by the thread that owns b in tile_partition (or, for the fine pass, by the owner of the tile-local bin that
+// maps to it), and phases are separated by the barriers of tile_partition.
+struct PageState {
+    uint32_t cur[kNB1];               // the block's current page of the bin (0xffffffff: none yet)
+    uint32_t fill[kNB1];              // keys already in it
+    uint32_t cnt[kNB1];               // pages this block has taken for the bin
+};
+
+struct PagePool {
+    PageState* ps;
+    RadixCtl* ctl;
+    uint16_t* page_bin;
+    uint16_t* page_len;
+    unsigned long long* err_ctr;
+    uint32_t page_log2, n_pages;
+    unsigned long long my_keys;       // keys this thread has placed
+
+    __device__ __forceinline__ void init() {
+        for (uint32_t b = threadIdx.x; b < kNB1; b += blockDim.x) { ps->cur[b] = 0xffffffffu; ps->fill[b] = 1u << page_log2; ps->cnt[b] = 0u; }
+        my_keys = 0;
+    }
+    // only the part of a run that does not fit the block's current page of the bin needs fresh pages
+    __device__ __forceinline__ unsigned long long reserve(uint32_t bin, uint32_t n) {
+        const uint32_t room = (1u << page_log2) - ps->fill[bin];
+        if (n <= room) return 0ULL;
+        const uint32_t m = (n - room + (1u << page_log2) - 1) >> page_log2;
+        return atomicAdd(&ctl->page_next, (unsigned long long)m);
+    }
+    // run of n keys of `bin` whose first key has tile index `start`; p = what reserve() returned.
+    // g1: position minus tile index for keys before `split`, g2: the same for the keys in the fresh pages
+    __device__ __forceinline__ void place(uint32_t bin, uint32_t n, uint32_t start, unsigned long long p, long long& g1, long long& g2,
+                                          uint32_t& split) {
+        const uint32_t page_keys = 1u << page_log2;
+        const uint32_t c = ps->cur[bin], fill = ps->fill[bin];
+        const uint32_t room = page_keys - fill;
+        my_keys += n;
+        g1 = (long long)(((uint64_t)c << page_log2) + fill) - (long long)start;      // unused when room == 0
+        g2 = 0;
+        if (n <= room) {
+            split = 0xffffffffu;
+            ps->fill[bin] = fill + n;
+            return;
+        }
+        const uint32_t rest = n - room, m = (rest + page_keys - 1) >> page_log2;
+        if (p + m > n_pages) { atomicOr(err_ctr, (unsigned long long)ERR_PLAN); p = 0; }   // cannot happen: the planner leaves room
+        if (c != 0xffffffffu) page_len[c] = (uint16_t)page_keys;                            // the old page is completed by this run
+        for (uint32_t q = 0; q < m; ++q) { page_bin[p + q] = (uint16_t)bin; if (q + 1 < m) page_len[p + q] = (uint16_t)page_keys; }
+        split = start + room;
+        g2 = (long long)(p << page_log2) - (long long)(start + room);
+        ps->cur[bin] = (uint32_t)p + m - 1;
+        ps->fill[bin] = rest - ((m - 1) << page_log2);
+        ps->cnt[bin] += m;
+    }
+    // the block's last page of every bin is partly filled; its page counts and keys go to the totals
+    __device__ __forceinline__ void finish() {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < kNB1; b += blockDim.x) {
+            const uint32_t c = ps->cur[b];
+            if (c != 0xffffffffu) page_len[c] = (uint16_t)ps->fill[b];
+            if (ps->cnt[b]) atomicAdd(&ctl->bin_pages[b], ps->cnt[b]);
+        }
+        const unsigned full = 0xffffffffu;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) my_keys += __shfl_xor_sync(full, my_keys, sft);
+        if ((threadIdx.x & 31u) == 0 && my_keys) atomicAdd(&ctl->n_insert, my_keys);
+    }
 };
 
 template <int KW, int NB, bool PAGED>
@@ -662,55 +728,26 @@ k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ Radix
     using Smem = TileSmem<KW, kNB1, PAGED>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-    uint64_t** owner_base = reinterpret_cast<uint64_t**>(smem_raw + ((sizeof(Smem) + 15) & ~(size_t)15));
+    constexpr size_t kSmemA = (sizeof(Smem) + 15) & ~(size_t)15;
+    uint64_t** owner_base = reinterpret_cast<uint64_t**>(smem_raw + kSmemA);
+    PagePool pool{reinterpret_cast<PageState*>(smem_raw + kSmemA + 256 * sizeof(uint64_t*)), ctl, page_bin, page_len, err_ctr, pg.page_log2, pg.n_pages, 0ULL};
     if (!ctl->chunk_active) return;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     tile_smem_init<KW, kNB1, PAGED>(sm);
     if (threadIdx.x < 256) owner_base[threadIdx.x] = (dst_of_owner && threadIdx.x < (rg.nb1 >> rg.owner_shift)) ? dst_of_owner[threadIdx.x] : A;
-    const uint32_t page_keys = 1u << pg.page_log2;
-    if constexpr (PAGED) {
-        for (uint32_t b = threadIdx.x; b < kNB1; b += kRadixThreads) { sm.page_cur[b] = 0xffffffffu; sm.page_fill[b] = page_keys; sm.page_cnt[b] = 0u; }
-    }
+    if constexpr (PAGED) pool.init();
     __syncthreads();
     const uint64_t seg_begin = ctl->chunk[c].seg_begin, seg_end = ctl->chunk[c].seg_end;
     const uint64_t seg_words = 1ULL << rg.seg_log2;
     const uint64_t lbg_mask = tv.lbg_mask;
-    unsigned long long my_keys = 0;                     // paged: keys this thread has placed (as the owner of its two bins)
     auto digit = [&](uint64_t h0) { return digit1_of(rg, lbg_mask, h0); };
     auto reserve = [&](uint32_t bin, uint32_t n) -> unsigned long long {
-        if constexpr (!PAGED) {
-            return atomicAdd(&ctl->cursor1[bin * kCursorStride], (unsigned long long)n);
-        } else {
-            // only the part of the run that does not fit the block's current page of this bin needs fresh pages
-            const uint32_t room = page_keys - sm.page_fill[bin];
-            if (n <= room) return 0ULL;
-            const uint32_t m = (n - room + page_keys - 1) >> pg.page_log2;
-            return atomicAdd(&ctl->page_next, (unsigned long long)m);
-        }
+        if constexpr (!PAGED) return atomicAdd(&ctl->cursor1[bin * kCursorStride], (unsigned long long)n);
+        else return pool.reserve(bin, n);
     };
     auto place = [&](uint32_t bin, uint32_t n, uint32_t start, unsigned long long p) {
-        if constexpr (!PAGED) {
-            sm.gdelta[bin] = (long long)p - (long long)start;
-        } else {
-            const uint32_t cur = sm.page_cur[bin], fill = sm.page_fill[bin];
-            const uint32_t room = page_keys - fill;
-            my_keys += n;
-            sm.gdelta[bin] = (long long)(((uint64_t)cur << pg.page_log2) + fill) - (long long)start;   // unused when room == 0
-            if (n <= room) {
-                sm.split[bin] = 0xffffffffu;
-                sm.page_fill[bin] = fill + n;
-                return;
-            }
-            const uint32_t rest = n - room, m = (rest + page_keys - 1) >> pg.page_log2;
-            if (p + m > pg.n_pages) { atomicOr(err_ctr, (unsigned long long)ERR_PLAN); p = 0; }   // cannot happen: the planner leaves room
-            if (cur != 0xffffffffu) page_len[cur] = (uint16_t)page_keys;        // the old page is completed by this run
-            for (uint32_t q = 0; q < m; ++q) { page_bin[p + q] = (uint16_t)bin; if (q + 1 < m) page_len[p + q] = (uint16_t)page_keys; }
-            sm.split[bin] = start + room;
-            sm.gdelta2[bin] = (long long)(p << pg.page_log2) - (long long)(start + room);
-            sm.page_cur[bin] = (uint32_t)p + m - 1;
-            sm.page_fill[bin] = rest - ((m - 1) << pg.page_log2);
-            sm.page_cnt[bin] += m;
-        }
+        if constexpr (!PAGED) sm.gdelta[bin] = (long long)p - (long long)start;
+        else pool.place(bin, n, start, p, sm.gdelta[bin], sm.gdelta2[bin], sm.split[bin]);
     };
     auto dst = [&](uint32_t d) { return owner_base[d >> rg.owner_shift]; };
     for (uint64_t seg = seg_begin + blockIdx.x; seg < seg_end; seg += gridDim.x) {
@@ -733,18 +770,7 @@ k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ Radix
             }
         }
     }
-    if constexpr (PAGED) {
-        // the block's last page of every bin is partly filled; its page counts and keys go to the chunk's totals
-        for (uint32_t b = threadIdx.x; b < kNB1; b += kRadixThreads) {
-            const uint32_t cur = sm.page_cur[b];
-            if (cur != 0xffffffffu) page_len[cur] = (uint16_t)sm.page_fill[b];
-            if (sm.page_cnt[b]) atomicAdd(&ctl->bin_pages[b], sm.page_cnt[b]);
-        }
-        const unsigned full = 0xffffffffu;
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) my_keys += __shfl_xor_sync(full, my_keys, sft);
-        if (lane == 0 && my_keys) atomicAdd(&ctl->n_insert, my_keys);
-    }
+    if constexpr (PAGED) pool.finish();
 }
 
 // ---- per group of A: work items, histogram reset -------------------------------------------------------------------
@@ -922,6 +948,112 @@ k_part_keys(const __grid_constant__ TableView tv, const __grid_constant__ RadixG
         auto place = [&](uint32_t bin, uint32_t, uint32_t start, unsigned long long p) { sm.gdelta[bin] = (long long)p - (long long)start; };
         tile_partition<KW, kNB, false>(sm, Hs, vmask, rg.d2, digit, reserve, place, dst);
     }
+}
+
+// ---- two-level mode (hash-sharded tables): the received keys, sorted by a coarse local digit, get their fine digit ----
+// With G shards the routing pass has 256 / G bins per shard (runs of 16 k-mers = 128 bytes cross NVLink; at 4 k-mers
+// per run the peer stores ran at half the speed), which leaves regions of 0.5-1 GiB per bin.  So the receive buffer R
+// is cut into groups, every group is partitioned once more by the next d2 bits into the page pool (fine bin = coarse
+// bin * nb2 + digit 2, at most kNB1 of them per shard) and inserted from there.  The planner walks the coarse bins
+// and ends a group where the pool could run out of pages: a (block, fine bin) pair may leave one page partly empty.
+template <int KW>
+__global__ void __launch_bounds__(kNB) k_plan_group_paged(RadixCtl* __restrict__ ctl, uint32_t g, uint32_t n_groups, uint32_t nbl, uint32_t nb2,
+                                                          const __grid_constant__ PageGeom pg, uint32_t grid2,
+                                                          unsigned long long* __restrict__ err_ctr) {
+    constexpr uint32_t TILE = RadixCfg<KW>::TILE;
+    __shared__ uint32_t scratch[8];
+    __shared__ uint64_t a0_s, a1_s;
+    GroupDesc& G = ctl->group;
+    const uint64_t n_keys = ctl->cur_coff[nbl];
+    if (threadIdx.x == 0) {
+        const uint64_t a0 = g == 0 ? 0ULL : G.a1;
+        uint64_t a1 = a0;
+        if (a0 < n_keys) {
+            uint32_t b = 0;
+            while (b + 1 < nbl && ctl->cur_coff[b + 1] <= a0) ++b;
+            const uint64_t fixed = (uint64_t)grid2 * nb2;                  // pages the fine bins of one coarse bin may waste
+            uint64_t pages_left = pg.n_pages;
+            for (; b < nbl; ++b) {
+                const uint64_t lo = ctl->cur_coff[b] > a0 ? ctl->cur_coff[b] : a0, hi = ctl->cur_coff[b + 1];
+                if (hi <= lo) continue;
+                if (pages_left <= fixed) break;
+                const uint64_t can = (pages_left - fixed) << pg.page_log2;
+                const uint64_t take = hi - lo < can ? hi - lo : can;
+                a1 = lo + take;
+                pages_left -= fixed + ((take + (1ULL << pg.page_log2) - 1) >> pg.page_log2);
+                if (take < hi - lo) break;
+            }
+            if (a1 == a0) { atomicOr(err_ctr, (unsigned long long)ERR_PLAN); a1 = n_keys; }   // pool smaller than one bin's slack: refused at creation
+            if (g + 1 == n_groups && a1 < n_keys) atomicOr(err_ctr, (unsigned long long)ERR_PLAN);   // out of group slots: cannot happen (see the host side)
+        }
+        a0_s = a0; a1_s = a1;
+    }
+    __syncthreads();
+    const uint64_t a0 = a0_s, a1 = a1_s;
+    const bool active = a1 > a0;
+    uint32_t tiles = 0;
+    if (active && threadIdx.x < nbl) {
+        const uint64_t lo0 = ctl->cur_coff[threadIdx.x], hi0 = ctl->cur_coff[threadIdx.x + 1];
+        const uint64_t lo = lo0 > a0 ? lo0 : a0, hi = hi0 < a1 ? hi0 : a1;
+        if (hi > lo) tiles = (uint32_t)((hi - lo + TILE - 1) / TILE);
+    }
+    uint32_t n_items = 0;
+    const uint32_t pre = block_exscan_256(tiles, scratch, &n_items);
+    G.itemstart[threadIdx.x] = pre;
+    if (threadIdx.x == kNB - 1) G.itemstart[kNB] = pre + tiles;
+    for (uint32_t i = threadIdx.x; i < kNB1; i += kNB) ctl->bin_pages[i] = 0u;
+    if (threadIdx.x == 0) {
+        G.a0 = a0; G.a1 = a1; G.n_items = active ? n_items : 0u; G.active = active ? 1u : 0u;
+        ctl->chunk_active = active ? 1u : 0u;          // k_chunk_end_paged looks at this
+        ctl->page_next = 0ULL;
+        ctl->n_insert = 0ULL;
+        ctl->n_slices = 0u;
+        ctl->ticket[0] = ctl->ticket[1] = ctl->ticket[2] = 0ULL;
+    }
+}
+
+// Dynamic shared memory: TileSmem<KW, kNB, true> + ItemFeed<KW> + PageState.
+template <int KW>
+__global__ void __launch_bounds__(kRadixThreads, RadixCfg<KW>::MINB)
+k_part_keys_paged(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, const __grid_constant__ PageGeom pg,
+                  RadixCtl* __restrict__ ctl, const uint64_t* __restrict__ R, uint64_t* __restrict__ pool_keys,
+                  uint16_t* __restrict__ page_bin, uint16_t* __restrict__ page_len, unsigned long long* __restrict__ err_ctr) {
+    constexpr int OPT = RadixCfg<KW>::OPT;
+    using Smem = TileSmem<KW, kNB, true>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    constexpr size_t kSmemA = (sizeof(Smem) + 15) & ~(size_t)15;
+    constexpr size_t kSmemB = (kSmemA + sizeof(ItemFeed<KW>) + 15) & ~(size_t)15;
+    ItemFeed<KW>& feed = *reinterpret_cast<ItemFeed<KW>*>(smem_raw + kSmemA);
+    PagePool pool{reinterpret_cast<PageState*>(smem_raw + kSmemB), ctl, page_bin, page_len, err_ctr, pg.page_log2, pg.n_pages, 0ULL};
+    if (!ctl->group.active) return;
+    tile_smem_init<KW, kNB, true>(sm);
+    pool.init();
+    item_feed_init<KW>(feed, ctl, rg.nbl);
+    const uint64_t lbg_mask = tv.lbg_mask;
+    auto digit = [&](uint64_t h0) { return digit2_of(rg, lbg_mask, h0); };
+    auto dst = [&](uint32_t) { return pool_keys; };
+    unsigned long long ahead = threadIdx.x == 0 ? atomicAdd(&ctl->ticket[1], 1ULL) : 0ULL;
+    while (next_item<KW>(feed, ctl, 1, rg.nbl, ahead)) {
+        const uint64_t lo = feed.cur.lo, hi = feed.cur.hi;
+        const uint32_t fine0 = feed.cur.bin * rg.nb2;            // all keys of an item share the coarse bin
+        Key<KW> Hs[OPT];
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int j = 0; j < OPT; ++j) {
+            const uint64_t i = lo + (uint64_t)j * kRadixThreads + threadIdx.x;
+            const bool v = i < hi;
+            if (v) vmask |= 1u << j;
+#pragma unroll
+            for (int w = 0; w < KW; ++w) Hs[j].w[w] = v ? __ldcs(R + i * KW + w) : 0ULL;
+        }
+        auto reserve = [&](uint32_t bin, uint32_t n) { return pool.reserve(fine0 + bin, n); };
+        auto place = [&](uint32_t bin, uint32_t n, uint32_t start, unsigned long long p) {
+            pool.place(fine0 + bin, n, start, p, sm.gdelta[bin], sm.gdelta2[bin], sm.split[bin]);
+        };
+        tile_partition<KW, kNB, true>(sm, Hs, vmask, rg.d2, digit, reserve, place, dst);
+    }
+    pool.finish();
 }
 
 // ---- phase B: insert keys in region order ---------------------------------------------------------------------------
