@@ -60,9 +60,9 @@ enum {
 /* Always use the single fused extract+insert kernel, never the region-sorted pipeline that large tables take by
  * default (DESIGN.md "Why a sort by table region") — for A/B measurements. */
 #define TSXC_FLAG_DIRECT 4u
-/* (Round 1 had TSXC_FLAG_SKEWED = 8, a caller hint for inputs dominated by a few k-mers.  The pipeline now sizes
- * every bin from exact histograms and combines duplicates in shared memory before they reach the table, so there is
- * nothing left to hint; the bit is ignored.) */
+/* (Round 1 had TSXC_FLAG_SKEWED = 8, a caller hint for inputs dominated by a few k-mers.  The pipeline's bins now grow
+ * page by page as the data demands and duplicates are combined in shared memory before they reach the table, so there
+ * is nothing left to hint; the bit is ignored.) */
 
 typedef struct tsxc_table tsxc_table; /* opaque */
 

@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 {
   nvidia-smi --query-gpu=index,name --format=csv,noheader
-  ( time timeout 900 python -m pytest tests/test_multigpu_nccl.py tests/test_cli.py -x -q -m gpu ) 2>&1 | tail -15
+  ( time timeout 900 python -m pytest tests/test_multigpu_nccl.py tests/test_cli.py -x -q -m gpu -k "nccl or multi_gpu" ) 2>&1 | tail -15
   echo "== bench --gpus 2"
   ( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 2 --warmup 1 ) > gpurun_out/mg2.json 2> gpurun_out/mg2.log
   echo "rc=$?"; grep -E "bench|Error|error|Traceback" gpurun_out/mg2.log | tail -25
