@@ -110,11 +110,13 @@ template <int KW> struct RadixCfg {
     static constexpr int MINB = KW == 4 ? 1 : 2;
 };
 
-__device__ __forceinline__ uint32_t digit1_of(const RadixGeom& rg, uint64_t lbg_mask, uint64_t h0) {
-    return (uint32_t)((h0 & lbg_mask) >> rg.shift1);
+// digit 1 = bits [shift1, shift1 + d1) of hash word 0 (the top of the bucket index), digit 2 = the d2 bits below it:
+// one funnel shift and one AND each
+__device__ __forceinline__ uint32_t digit1_of(const RadixGeom& rg, uint64_t, uint64_t h0) {
+    return (uint32_t)(h0 >> rg.shift1) & (rg.nb1 - 1);
 }
-__device__ __forceinline__ uint32_t digit2_of(const RadixGeom& rg, uint64_t lbg_mask, uint64_t h0) {
-    return (uint32_t)((h0 & lbg_mask) >> rg.shift2) & (rg.nb2 - 1);
+__device__ __forceinline__ uint32_t digit2_of(const RadixGeom& rg, uint64_t, uint64_t h0) {
+    return (uint32_t)(h0 >> rg.shift2) & (rg.nb2 - 1);
 }
 
 // ---- one lane's view of the packed read stream ---------------------------------------------------------------
@@ -123,26 +125,37 @@ __device__ __forceinline__ uint32_t digit2_of(const RadixGeom& rg, uint64_t lbg_
 template <int KW>
 struct KmerLane {
     static constexpr int NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
-    uint64_t win[KW + 1];
-    uint64_t g0, limit;
+    uint32_t a[2 * KW + 2];      // the lane's window of the stream as 32-bit words
     uint32_t ends_cur, dist;
+    int omax;                    // k-mers may start at offsets <= omax of this word (-1: none: end of stream, or lane out of range)
     __device__ __forceinline__ void load(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ends,
-                                         uint64_t base, uint64_t n_words, uint64_t w_end, uint64_t n_bases, unsigned lane) {
+                                         uint64_t base, uint64_t n_words, uint64_t w_end, uint64_t n_bases, unsigned lane, uint32_t k) {
+        uint64_t win[KW + 1];
         uint32_t ewin[NE + 1];
         load_window<KW, uint64_t>(packed, base, n_words, lane, win);
         load_window<NE, uint32_t>(ends, base, n_words, lane, ewin);
+#pragma unroll
+        for (int j = 0; j <= KW; ++j) { a[2 * j] = (uint32_t)win[j]; a[2 * j + 1] = (uint32_t)(win[j] >> 32); }
         ends_cur = ewin[0];
         dist = first_end_after<NE>(ewin);
-        g0 = (base + lane) << 5;
-        limit = (base + lane < w_end) ? n_bases : 0;     // lanes past the range emit nothing
+        const uint64_t g0 = (base + lane) << 5;
+        omax = -1;
+        if (base + lane < w_end && g0 + k <= n_bases) omax = n_bases - g0 - k < 31 ? (int)(n_bases - g0 - k) : 31;
     }
+    // HI: o >= 16, i.e. the k-mer starts in the upper half of the 64-bit word (callers walk o downwards in groups that
+    // never straddle 16, so the word selection is a compile-time matter and a k-mer costs two funnel shifts per word)
+    template <bool HI>
     __device__ __forceinline__ bool kmer_at(int o, uint32_t k, const HashParams& hp, Key<KW>& key) {
         dist = ((ends_cur >> o) & 1u) ? 0u : (dist == 0xffffffffu ? dist : dist + 1u);
-        const bool valid = (dist >= k - 1) && (g0 + (uint64_t)o + k <= limit);
-        const unsigned sh = 2u * (unsigned)o;
+        const bool valid = (dist >= k - 1) && (o <= omax);
+        const unsigned sb = (2u * (unsigned)o) & 31u;
+        constexpr int H = HI ? 1 : 0;
 #pragma unroll
-        for (int j = 0; j < KW; ++j)
-            key.w[j] = (sh ? ((win[j] >> sh) | (win[j + 1] << (64 - sh))) : win[j]) & word_mask<KW>(j, hp);
+        for (int j = 0; j < KW; ++j) {
+            const uint32_t lo = __funnelshift_r(a[2 * j + H], a[2 * j + 1 + H], sb);
+            const uint32_t hi = __funnelshift_r(a[2 * j + 1 + H], a[2 * j + 2 + H], sb);
+            key.w[j] = (((uint64_t)hi << 32) | lo) & word_mask<KW>(j, hp);
+        }
         return valid;
     }
 };
@@ -238,15 +251,18 @@ __device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* scratch, 
     }
     if (lane == 31) scratch[warp] = inc;
     __syncthreads();
-    uint32_t pre = 0, tot = 0;
-    for (unsigned w = 0; w < nw; ++w) {
-        const uint32_t x = scratch[w];
-        if (w < warp) pre += x;
-        tot += x;
+    // every warp scans the (at most 32) warp totals again with shuffles instead of walking them
+    uint32_t part = lane < nw ? scratch[lane] : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(full, part, d);
+        if (lane >= (unsigned)d) part += y;
     }
+    const uint32_t upto = __shfl_sync(full, part, warp ? warp - 1 : 0);
+    const uint32_t tot = __shfl_sync(full, part, nw - 1);
     __syncthreads();
     if (total) *total = tot;
-    return pre + inc - v;
+    return (warp ? upto : 0u) + inc - v;
 }
 
 // 64-bit variant for values below 2^40 each and at most 1024 threads: the low 20 bits and the rest are scanned
@@ -482,11 +498,18 @@ k_hist_reads(const __grid_constant__ TableView tv, const __grid_constant__ Radix
         const uint64_t w1 = w0 + seg_words < n_words ? w0 + seg_words : n_words;
         for (uint64_t base = w0 + warp * 32; base < w1; base += kRadixWarps * 32) {
             KmerLane<KW> kl;
-            kl.load(packed, ends, base, n_words, w1, n_bases, lane);
+            kl.load(packed, ends, base, n_words, w1, n_bases, lane, tv.L.k);
 #pragma unroll 4
-            for (int o = 31; o >= 0; --o) {
+            for (int o = 31; o >= 16; --o) {
                 Key<KW> key;
-                const bool valid = kl.kmer_at(o, tv.L.k, tv.hp, key);
+                const bool valid = kl.template kmer_at<true>(o, tv.L.k, tv.hp, key);
+                const Key<KW> H = hash_key<KW>(key, tv.hp);
+                (void)rank_in_warp<uint32_t>(cnt + warp * kNB1, tag + warp * kNB1, valid, digit1_of(rg, tv.lbg_mask, H.w[0]), lane, rg.d1);
+            }
+#pragma unroll 4
+            for (int o = 15; o >= 0; --o) {
+                Key<KW> key;
+                const bool valid = kl.template kmer_at<false>(o, tv.L.k, tv.hp, key);
                 const Key<KW> H = hash_key<KW>(key, tv.hp);
                 (void)rank_in_warp<uint32_t>(cnt + warp * kNB1, tag + warp * kNB1, valid, digit1_of(rg, tv.lbg_mask, H.w[0]), lane, rg.d1);
             }
@@ -755,16 +778,25 @@ k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ Radix
         const uint64_t w1 = w0 + seg_words < n_words ? w0 + seg_words : n_words;
         for (uint64_t round = w0; round < w1; round += kRadixWarps * 32) {
             KmerLane<KW> kl;
-            kl.load(packed, ends, round + warp * 32, n_words, w1, n_bases, lane);
+            kl.load(packed, ends, round + warp * 32, n_words, w1, n_bases, lane, tv.L.k);
 #pragma unroll 1
             for (int o0 = 31; o0 >= 0; o0 -= OPT) {
                 Key<KW> Hs[OPT];
                 uint32_t vmask = 0;
+                if (o0 >= 16) {
 #pragma unroll
-                for (int j = 0; j < OPT; ++j) {
-                    Key<KW> key;
-                    if (kl.kmer_at(o0 - j, tv.L.k, tv.hp, key)) vmask |= 1u << j;
-                    Hs[j] = hash_key<KW>(key, tv.hp);
+                    for (int j = 0; j < OPT; ++j) {
+                        Key<KW> key;
+                        if (kl.template kmer_at<true>(o0 - j, tv.L.k, tv.hp, key)) vmask |= 1u << j;
+                        Hs[j] = hash_key<KW>(key, tv.hp);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < OPT; ++j) {
+                        Key<KW> key;
+                        if (kl.template kmer_at<false>(o0 - j, tv.L.k, tv.hp, key)) vmask |= 1u << j;
+                        Hs[j] = hash_key<KW>(key, tv.hp);
+                    }
                 }
                 tile_partition<KW, kNB1, PAGED>(sm, Hs, vmask, rg.d1, digit, reserve, place, dst);
             }

@@ -106,17 +106,6 @@ struct PinnedBatch {
     ~PinnedBatch() { if (packed) tsxc_host_free(packed); if (offsets) tsxc_host_free(offsets); }
 };
 
-// k-mer text -> KW words (SequenceUtils.h:86-123); false for non-ACGT
-bool encode_kmer(const std::string& s, uint32_t kw, uint64_t* out) {
-    for (uint32_t j = 0; j < kw; ++j) out[j] = 0;
-    for (size_t i = 0; i < s.size(); ++i) {
-        uint64_t c;
-        switch (s[i]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; default: return false; }
-        out[(2 * i) >> 6] |= c << ((2 * i) & 63);
-    }
-    return true;
-}
-
 // Count phase.  The reference has one OpenMP producer that reads 40 records at a time and one task per batch that
 // packs and inserts k-mer by k-mer (main.cpp:132-206).  Here: reader threads (FastxReader, ~0.9 Gbases/s each; one
 // by default, --readers=N splits a plain file into N byte ranges), `threads`-1 packer threads (tsxc_pack_reads into
@@ -330,53 +319,112 @@ void countKMersMulti(MultiGpuCounter& mg, const arguments& args) {
     std::cout << "Added a total of " << mg.getKmerCount() << " different kmers" << std::endl;   // main.cpp:222
 }
 
+// KW words -> k-mer text (inverse of encode_kmer; only needed for the error messages of --check)
+std::string decode_kmer(const uint64_t* w, uint32_t k) {
+    std::string s(k, 'A');
+    for (uint32_t i = 0; i < k; ++i) s[i] = "ACGT"[(w[(2 * i) >> 6] >> ((2 * i) & 63)) & 3];
+    return s;
+}
+
+// --check (main.cpp:224-396): every line KMER<TAB>COUNT of <input>.<k>.count must be in the table with that count, and the
+// table must hold nothing else.  The reference parses 100 000 lines at a time into a std::map and probes k-mer by k-mer;
+// here the file is read in 64 MiB blocks, the lines of a block are parsed by `threads` workers (no per-line allocation)
+// and looked up in one batch, which the library sorts by table region (tsxc_lookup, >= 2^18 queries).
 template <typename Map>
 int checkCounts(Map& map, const arguments& args) {
     const std::string ref = args.input_path + "." + std::to_string(args.k) + ".count";         // main.cpp:226
     std::cout << "Checking kmer counts against manual hashmap ..." << std::endl;
     std::cerr << "Loading reference file: " << ref << std::endl;
-    std::ifstream file(ref);
     uint64_t total_errors = 0, ref_count = 0, found = 0;
     const uint32_t kw = map.keyWords();
-    if (file.is_open()) {
-        const size_t kChunk = 100000;                                                           // main.cpp:262
+    const uint32_t k = args.k;
+    FILE* file = std::fopen(ref.c_str(), "rb");
+    if (file) {
+        const size_t kBlock = 64u << 20;
+        const int n_workers = std::max(1, std::min(args.threads, 32));
+        std::vector<char> buf(kBlock + 4096);
+        size_t carry = 0;                                   // bytes of an unfinished line at the start of buf
+        struct Part { std::vector<uint64_t> keys, want; uint64_t bad = 0; std::vector<std::string> bad_names; };
+        std::vector<Part> parts(n_workers);
         std::vector<uint64_t> keys, want, got;
-        std::vector<std::string> names;
-        std::string line;
-        auto flush = [&]() {
-            if (want.empty()) return;
-            std::cout << "Going to check " << want.size() << " kmers" << std::endl;
-            got.resize(want.size());
-            map.getKmerCounts(keys.data(), want.size(), got.data());
-            for (size_t i = 0; i < want.size(); ++i) {
-                if (got[i] != 0) ++found;
-                if (got[i] != want[i]) {                                                        // testExecution.h:50-92
-                    std::cout << "kmer: ( " << names[i] << " ): " << got[i] << " Should be " << want[i] << std::endl;
-                    ++total_errors;
-                    if (args.checkabort) exit(200);                                             // main.cpp:285-291
+        auto parse = [&](const char* p, const char* end, Part& out) {
+            out.keys.clear(); out.want.clear(); out.bad = 0; out.bad_names.clear();
+            while (p < end) {
+                const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+                const char* le = nl ? nl : end;
+                const char* tab = (const char*)memchr(p, '\t', (size_t)(le - p));
+                if (tab) {
+                    const size_t base = out.keys.size();
+                    out.keys.resize(base + kw, 0);
+                    bool ok = (size_t)(tab - p) == k;
+                    for (uint32_t i = 0; ok && i < k; ++i) {
+                        uint64_t c;
+                        switch (p[i]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; default: c = 0; ok = false; }
+                        out.keys[base + ((2 * i) >> 6)] |= c << ((2 * i) & 63);
+                    }
+                    if (ok) {
+                        uint64_t cnt = 0;
+                        for (const char* q = tab + 1; q < le && *q >= '0' && *q <= '9'; ++q) cnt = cnt * 10 + (uint64_t)(*q - '0');
+                        out.want.push_back(cnt);
+                    } else {
+                        out.keys.resize(base);
+                        ++out.bad;
+                        if (out.bad_names.size() < 16) out.bad_names.emplace_back(p, (size_t)(tab - p));
+                    }
                 }
+                p = le + 1;
             }
-            std::cout << "Checked " << want.size() << " kmers" << std::endl;
-            ref_count += want.size();
-            keys.clear(); want.clear(); names.clear();
         };
-        while (std::getline(file, line)) {
-            const size_t tab = line.find('\t');
-            if (tab == std::string::npos) continue;
-            const std::string kmer = line.substr(0, tab);
-            const uint64_t cnt = (uint64_t)std::atoll(line.c_str() + tab + 1);
-            keys.resize(keys.size() + kw);
-            if (kmer.size() != args.k || !encode_kmer(kmer, kw, keys.data() + keys.size() - kw)) {
-                keys.resize(keys.size() - kw);
-                std::cout << "kmer: ( " << kmer << " ) cannot be encoded" << std::endl;
-                ++total_errors; ++ref_count;
-                continue;
+        bool eof = false;
+        while (!eof) {
+            const size_t got_bytes = std::fread(buf.data() + carry, 1, kBlock - carry, file);
+            size_t n = carry + got_bytes;
+            eof = got_bytes == 0;
+            if (n == 0) break;
+            size_t usable = n;
+            if (!eof) {                                     // keep the unfinished last line for the next block
+                while (usable > 0 && buf[usable - 1] != '\n') --usable;
+                if (usable == 0) { if (n >= kBlock) break; carry = n; continue; }   // a line longer than a block: not a count file
             }
-            want.push_back(cnt);
-            names.push_back(kmer);
-            if (want.size() >= kChunk) flush();
+            // cut [0, usable) at line boundaries into one piece per worker
+            std::vector<size_t> cut(n_workers + 1, usable);
+            cut[0] = 0;
+            for (int w = 1; w < n_workers; ++w) {
+                size_t c = std::max(cut[w - 1], usable / n_workers * w);
+                while (c > 0 && c < usable && buf[c - 1] != '\n') ++c;       // a piece starts right after a newline
+                cut[w] = std::min(c, usable);
+            }
+            std::vector<std::thread> th;
+            for (int w = 0; w < n_workers; ++w)
+                th.emplace_back([&, w] { parse(buf.data() + cut[w], buf.data() + cut[w + 1], parts[w]); });
+            for (auto& t : th) t.join();
+            keys.clear(); want.clear();
+            for (auto& pt : parts) {
+                keys.insert(keys.end(), pt.keys.begin(), pt.keys.end());
+                want.insert(want.end(), pt.want.begin(), pt.want.end());
+                for (auto& nm : pt.bad_names) std::cout << "kmer: ( " << nm << " ) cannot be encoded" << std::endl;
+                total_errors += pt.bad; ref_count += pt.bad;
+            }
+            if (!want.empty()) {
+                std::cout << "Going to check " << want.size() << " kmers" << std::endl;
+                got.resize(want.size());
+                map.getKmerCounts(keys.data(), want.size(), got.data());
+                for (size_t i = 0; i < want.size(); ++i) {
+                    if (got[i] != 0) ++found;
+                    if (got[i] != want[i]) {                                                    // testExecution.h:50-92
+                        std::cout << "kmer: ( " << decode_kmer(keys.data() + i * kw, k) << " ): " << got[i] << " Should be " << want[i] << std::endl;
+                        ++total_errors;
+                        if (args.checkabort) exit(200);                                         // main.cpp:285-291
+                    }
+                }
+                std::cout << "Checked " << want.size() << " kmers" << std::endl;
+                ref_count += want.size();
+            }
+            carry = n - usable;
+            if (carry) std::memmove(buf.data(), buf.data() + usable, carry);
+            if (eof) break;
         }
-        flush();
+        std::fclose(file);
     }
     const uint64_t distinct = map.getKmerCount();
     std::cout << "total errors" << total_errors << std::endl;                                  // main.cpp:367
