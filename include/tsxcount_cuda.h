@@ -60,9 +60,15 @@ enum {
 /* Always use the single fused extract+insert kernel, never the region-sorted pipeline that large tables take by
  * default (DESIGN.md "Why a sort by table region") — for A/B measurements. */
 #define TSXC_FLAG_DIRECT 4u
-/* (Round 1 had TSXC_FLAG_SKEWED = 8, a caller hint for inputs dominated by a few k-mers.  The pipeline's bins now grow
- * page by page as the data demands and duplicates are combined in shared memory before they reach the table, so there
- * is nothing left to hint; the bit is ignored.) */
+/* (Round 1 had a caller hint TSXC_FLAG_SKEWED for inputs dominated by a few k-mers.  The pipeline's bins now grow page by
+ * page as the data demands and duplicates are combined in shared memory before they reach the table, so there is
+ * nothing left to hint and the flag is gone.) */
+
+/* Count canonical k-mers: every k-mer (from reads, tsxc_add_kmers, tsxc_lookup) is replaced by the lexicographically
+ * smaller of itself and its reverse complement before it is hashed; dumps list the canonical form.  An opt-in
+ * extension: the reference counts forward k-mers only (src/mains/testExecution.h:15-36,
+ * no reverse-complement code anywhere in src/). */
+#define TSXC_FLAG_CANONICAL 8u
 
 typedef struct tsxc_table tsxc_table; /* opaque */
 
@@ -163,6 +169,9 @@ int tsxc_dump(tsxc_table* t, uint64_t* kmers_out, uint64_t* counts_out, uint64_t
 int tsxc_dump_file(tsxc_table* t, const char* path);
 /* TSXHashMap::print_stats() numbers — TSXHashMap.h:390-395 */
 int tsxc_stats(tsxc_table* t, tsxc_stats_t* out);
+/* Count histogram (extension): hist_out[c] = number of distinct k-mers whose count is c for
+ * c < n_bins - 1, hist_out[n_bins - 1] = number with a larger count; hist_out[0] is always 0.  2 <= n_bins <= 4096. */
+int tsxc_histogram(tsxc_table* t, uint64_t* hist_out, uint32_t n_bins);
 
 /* ---- multi-GPU routing (hash-sharded table) ------------------------------- */
 /* One process per GPU, each holding one shard (tsxc_create_shard).  A batch of reads is counted in rounds; in every
@@ -279,6 +288,8 @@ int tsxc_k0_region_sweep(tsxc_table* t, uint64_t footprint_bytes, uint64_t regio
  * TSXHashMap.h:724-735).  key/out are KW words. */
 int tsxc_debug_hash(uint32_t k, const uint64_t* key, uint64_t* out);
 int tsxc_debug_unhash(uint32_t k, const uint64_t* hash, uint64_t* out);
+/* min(k-mer, reverse complement) in the library's encoding (what TSXC_FLAG_CANONICAL tables count); host-side. */
+int tsxc_debug_canonical(uint32_t k, const uint64_t* key, uint64_t* out);
 /* Entry layout chosen for (k, l, s, flags, n_shards) without touching a GPU. */
 int tsxc_debug_layout(uint32_t k, uint32_t l, uint32_t s, uint32_t flags, uint32_t n_shards, tsxc_stats_t* out);
 

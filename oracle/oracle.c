@@ -70,7 +70,29 @@ static int cmp_ent_first(const void* pa, const void* pb) {
     return (a->first > b->first) - (a->first < b->first);
 }
 
+/* Canonical form of the k-mer starting at s (all ACGT): the lexicographically smaller of the k-mer and its reverse
+ * complement, compared as TEXT.  An extension: the reference counts forward k-mers only and has no
+ * reverse-complement code; this is the convention of jellyfish -C and KMC.  Deliberately string-level, so that it shares
+ * nothing with the bit tricks of the CUDA path. */
+static void canonical_text(const char* s, unsigned k, char* out) {
+    char rc[ORC_MAX_K];
+    for (unsigned i = 0; i < k; ++i) {
+        const char c = s[k - 1 - i];
+        rc[i] = c == 'A' ? 'T' : (c == 'C' ? 'G' : (c == 'G' ? 'C' : 'A'));
+    }
+    memcpy(out, memcmp(s, rc, k) <= 0 ? s : rc, k);
+}
+
+static orc_counts* count_reads_impl(const char* bases, const uint64_t* offsets, uint64_t n_reads, unsigned k, int canonical);
+
 orc_counts* orc_count_reads(const char* bases, const uint64_t* offsets, uint64_t n_reads, unsigned k) {
+    return count_reads_impl(bases, offsets, n_reads, k, 0);
+}
+orc_counts* orc_count_reads_canonical(const char* bases, const uint64_t* offsets, uint64_t n_reads, unsigned k) {
+    return count_reads_impl(bases, offsets, n_reads, k, 1);
+}
+
+static orc_counts* count_reads_impl(const char* bases, const uint64_t* offsets, uint64_t n_reads, unsigned k, int canonical) {
     if (k == 0 || k > ORC_MAX_K) return NULL;
     uint64_t cap = 0;
     for (uint64_t r = 0; r < n_reads; ++r) {
@@ -99,7 +121,13 @@ orc_counts* orc_count_reads(const char* bases, const uint64_t* offsets, uint64_t
             win[(nbits - 2) >> 6] |= (uint64_t)c << ((nbits - 2) & 63);
             if (i + 1 >= k) {
                 if (good >= k) {
-                    memcpy(recs[n].key, win, sizeof win);
+                    if (canonical) {
+                        char text[ORC_MAX_K];
+                        canonical_text(s + i + 1 - k, k, text);
+                        orc_encode_kmer(text, k, recs[n].key);
+                    } else {
+                        memcpy(recs[n].key, win, sizeof win);
+                    }
                     recs[n].idx = stream_idx;
                     ++n;
                 } else {

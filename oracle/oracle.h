@@ -63,6 +63,9 @@ void orc_decode_kmer(const uint64_t* key, unsigned k, char* out);
  * n_reads+1 offsets (testExecution.h:15-36 applied per read as main.cpp:168-192 does).
  * Returns NULL on allocation failure or invalid k. */
 orc_counts* orc_count_reads(const char* bases, const uint64_t* offsets, uint64_t n_reads, unsigned k);
+/* The same with every k-mer replaced by the lexicographically smaller of itself and its reverse complement
+ * (extension; the reference has no such mode). */
+orc_counts* orc_count_reads_canonical(const char* bases, const uint64_t* offsets, uint64_t n_reads, unsigned k);
 
 /* Parse a FASTQ file the way FASTXreader<FASTQEntry> does and count. */
 orc_counts* orc_count_fastq(const char* path, unsigned k);

@@ -31,6 +31,8 @@ def lib():
         L = C.CDLL(LIB)
         L.orc_count_reads.restype = C.POINTER(OrcCounts)
         L.orc_count_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint]
+        L.orc_count_reads_canonical.restype = C.POINTER(OrcCounts)
+        L.orc_count_reads_canonical.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint]
         L.orc_count_fastq.restype = C.POINTER(OrcCounts)
         L.orc_count_fastq.argtypes = [C.c_char_p, C.c_uint]
         L.orc_write_dump.restype = C.c_int
@@ -65,20 +67,21 @@ class Counts:
         return {tuple(k): int(c) for k, c in zip(self.keys[:, :kw].tolist(), self.counts.tolist())}
 
 
-def count_reads(ascii_, offsets, k):
+def count_reads(ascii_, offsets, k, canonical=False):
     ascii_ = np.ascontiguousarray(ascii_, dtype=np.uint8)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-    p = lib().orc_count_reads(ascii_.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k)
+    fn = lib().orc_count_reads_canonical if canonical else lib().orc_count_reads
+    p = fn(ascii_.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k)
     assert p, "oracle failed"
     return Counts(p)
 
 
-def count_seqs(seqs, k):
+def count_seqs(seqs, k, canonical=False):
     lens = np.array([len(s) for s in seqs], dtype=np.uint64)
     offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
     np.cumsum(lens, out=offsets[1:])
     ascii_ = np.frombuffer(b"".join(seqs), dtype=np.uint8) if len(seqs) else np.zeros(0, np.uint8)
-    return count_reads(ascii_, offsets, k)
+    return count_reads(ascii_, offsets, k, canonical)
 
 
 def count_fastq(path, k):

@@ -51,6 +51,31 @@ def test_cli_count_check_dump_on_bundled_example(tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_canonical_and_histogram_on_bundled_example(tmp_path):
+    """--canonical / --histogram (extensions): the dump equals the oracle's canonical counts of the bundled reads, the
+    histogram their count distribution; --check with a large reference file goes through the block parser."""
+    import collections
+    import tsxcount_b200 as tsx
+    fastq = orc.golden_path("c1_bundled_k14.fastq", tmp_path)
+    dump, hist = tmp_path / "canon.count", tmp_path / "canon.hist"
+    p = subprocess.run([CLI, f"--input={fastq}", "--mode=CUDA", "--canonical", f"--dump={dump}", f"--histogram={hist}", "--threads=4"],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    oc = orc.count_seqs(tsx.sequtils.read_fastq(fastq), 14, canonical=True)
+    want = {tsx.sequtils.to_sequence(k[:1], 14): int(c) for k, c in zip(oc.keys, oc.counts)}
+    got = dict((a, int(b)) for a, b in (line.split("\t") for line in open(dump).read().splitlines()))
+    assert got == want
+    assert f"Added a total of {oc.n_distinct} different kmers" in p.stdout
+    hwant = collections.Counter(min(c, 256) for c in want.values())
+    hgot = {(256 if a == "256+" else int(a)): int(b) for a, b in (line.split("\t") for line in open(hist).read().splitlines())}
+    assert hgot == dict(hwant)
+    # --check against its own canonical dump (194 000 lines, parsed by 4 workers in one block)
+    os.replace(dump, str(fastq) + ".14.count")
+    p = subprocess.run([CLI, f"--input={fastq}", "--mode=CUDA", "--canonical", "--check", "--threads=4"], capture_output=True, text=True)
+    assert p.returncode == 0 and "total errors0" in p.stdout and "queried (Xor) kmer count: 0" in p.stdout, p.stdout[-500:]
+
+
+@pytest.mark.gpu
 def test_cli_check_detects_a_wrong_reference_and_checkabort_exits_200(tmp_path):
     fastq = orc.golden_path("c2_fakeseq_k31.fastq", tmp_path)
     good = orc.golden_path("c2_fakeseq_k31.fastq.31.count", tmp_path)
@@ -263,7 +288,7 @@ def test_reference_tree_binding_drives_addkmer_and_getkmercount():
 
 def test_cli_new_options_are_listed_and_n_policy_is_explicit():
     out = subprocess.run([CLI, "--help"], capture_output=True, text=True).stdout
-    for opt in ("--gpus=", "--n-policy=", "--dump=", "--readers="):
+    for opt in ("--gpus=", "--n-policy=", "--dump=", "--readers=", "--canonical", "--histogram="):
         assert opt in out, opt
     p = subprocess.run([CLI, "--input=x.fastq", "--mode=CUDA", "--n-policy=random"], capture_output=True, text=True)
     assert p.returncode == 2 and "only 'skip' exists" in p.stderr

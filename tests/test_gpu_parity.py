@@ -510,6 +510,58 @@ def test_sorted_lookup_handles_absent_duplicate_and_out_of_range_queries(tsx, sm
         assert hm.stats()["kernel_launches"] - before >= 7      # hash, partition passes, probe
 
 
+# ---- opt-in extensions the reference lacks: canonical k-mers, count histogram ------------------------
+@pytest.mark.parametrize("k,l", [(5, 9), (14, 16), (31, 20), (32, 20), (33, 19), (63, 19), (64, 18), (65, 18), (127, 18)])
+def test_canonical_mode_matches_the_oracle(tsx, k, l):
+    """TSXC_FLAG_CANONICAL: counts of min(k-mer, reverse complement); the oracle canonicalises the TEXT.  Lookups accept
+    either strand; the dump lists canonical k-mers only."""
+    seqs = orc.gen_reads(seed=77 + k, n_reads=2500 if k > 20 else 300, read_len=150, mode=3, genome_len=4000 if k > 8 else 300,
+                         sub_rate_q16=200)
+    seqs += [s.translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1] for s in seqs[:400]]      # reverse strands of some reads
+    oc = orc.count_seqs(seqs, k, canonical=True)
+    fwd = orc.count_seqs(seqs, k)
+    assert oc.n_distinct < fwd.n_distinct and oc.n_total == fwd.n_total
+    with tsx.TSXHashMapCUDA(l, 0, k, flags=tsx.TSXC_FLAG_CANONICAL) as hm:
+        hm.addSequences(seqs)
+        check_against_oracle(tsx, hm, oc)
+        # every forward k-mer answers with the count of its canonical form
+        want = oc.as_dict(hm.kw)
+        lib = tsx._lib.load()
+        keys = fwd.keys_kw(hm.kw)[:2000]
+        canon = np.zeros((len(keys), 4), dtype=np.uint64)
+        for i, key in enumerate(keys):
+            src = np.zeros(4, dtype=np.uint64); src[:hm.kw] = key
+            assert lib.tsxc_debug_canonical(k, src.ctypes.data, canon[i].ctypes.data) == 0
+        got = hm.getKmerCounts(keys)
+        assert [int(x) for x in got] == [want[tuple(c[:hm.kw].tolist())] for c in canon]
+
+
+def test_canonical_mode_through_the_pipeline(tsx, small_regions):
+    seqs = orc.gen_reads(seed=5, n_reads=3000, read_len=150, mode=3, genome_len=30_000, sub_rate_q16=300)
+    seqs += [s.translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1] for s in seqs[:1000]]
+    oc = orc.count_seqs(seqs, 31, canonical=True)
+    with tsx.TSXHashMapCUDA(20, 0, 31, flags=tsx.TSXC_FLAG_CANONICAL) as hm:
+        hm.addSequences(seqs)
+        assert hm.stats()["main_kernel_launches"] >= 4
+        check_against_oracle(tsx, hm, oc)
+
+
+@pytest.mark.parametrize("k,l,s,flags", [(14, 16, 2, 1), (31, 20, 0, 0), (63, 19, 4, 1), (127, 18, 0, 0)])
+def test_count_histogram(tsx, k, l, s, flags):
+    """hist[c] = number of distinct k-mers with count c; counts beyond the last bin (and beyond the value field: overflow
+    entries) land in the last bin."""
+    seqs = orc.gen_reads(seed=3 + k, n_reads=3000, read_len=150, mode=2, genome_len=1 << 7, sub_rate_q16=400)
+    oc = orc.count_seqs(seqs, k)
+    assert oc.counts.max() > 64
+    with tsx.TSXHashMapCUDA(l, s, k, flags=flags) as hm:
+        hm.addSequences(seqs)
+        for n_bins in (2, 17, 64, 4096):
+            want = np.bincount(np.minimum(oc.counts, n_bins - 1).astype(np.int64), minlength=n_bins).astype(np.uint64)
+            assert np.array_equal(hm.histogram(n_bins), want), n_bins
+        with pytest.raises(tsx.TsxcError):
+            hm.histogram(5000)
+
+
 def test_direct_flag_forces_single_kernel(tsx, small_regions):
     seqs = orc.gen_reads(seed=3, n_reads=2000, read_len=150, mode=0)
     st, oc = run_case(tsx, seqs, 31, 20, 0, flags=4)

@@ -225,3 +225,28 @@ def test_reference_tree_binding_compiles_against_the_reference_headers():
     assert os.path.exists(exe)
     out = subprocess.run([exe, "--no-gpu"], capture_output=True, text=True, check=True).stdout
     assert "ref-adapter built" in out
+
+
+# ---- canonical k-mers (opt-in extension) ----------------------------------------------------------
+def _revcomp(s):
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 14, 31, 32, 33, 48, 63, 64, 65, 96, 127, 128])
+def test_canonical_key_is_the_lexicographic_minimum_of_kmer_and_reverse_complement(k):
+    """tsxc_debug_canonical runs the host build of the very functions the kernels use (tsx_hash.cuh: canonical_key):
+    compared with the definition on TEXT for random k-mers, palindromes and the extremes."""
+    lib = tsx._lib.load()
+    rng = np.random.default_rng(k)
+    kw = lib.tsxc_key_words(k)
+    texts = ["".join(rng.choice(list("ACGT"), size=k)) for _ in range(200)] + ["A" * k, "T" * k, "C" * k, "G" * k]
+    if k % 2 == 0:
+        half = "".join(rng.choice(list("ACGT"), size=k // 2))
+        texts.append(half + _revcomp(half))                      # its own reverse complement
+    for s in texts:
+        want = min(s, _revcomp(s))
+        key = np.zeros(4, dtype=np.uint64)
+        key[:kw] = sequtils.from_sequence(s)[:kw]
+        out = np.zeros(4, dtype=np.uint64)
+        assert lib.tsxc_debug_canonical(k, key.ctypes.data, out.ctypes.data) == 0
+        assert sequtils.to_sequence(out[:kw], k) == want, (s, want)

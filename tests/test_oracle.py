@@ -97,3 +97,29 @@ def test_generator_is_deterministic_and_shaped():
     z = orc.gen_reads(seed=2, n_reads=2000, read_len=50, mode=2, genome_len=1 << 10)
     top = max(set(z), key=z.count)
     assert z.count(top) > 100                       # log-uniform ranks: heavy hitters
+
+
+def test_canonical_counting_against_a_plain_python_counter():
+    """orc_count_reads_canonical (string-level reverse complement + memcmp) against collections.Counter over
+    min(kmer, revcomp(kmer)) on the README example and on random reads, k on both sides of a word boundary."""
+    from collections import Counter
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    rng = np.random.default_rng(4)
+    seqs = [b"ATCGAGTCAGTA"] + [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(n))) for n in rng.integers(1, 90, size=60)]
+    seqs += [b"ACGT" * 10, b"ACGTNACGTTGCA"]
+    for k in (3, 5, 31, 33):
+        want = Counter()
+        for s in seqs:
+            for i in range(len(s) - k + 1):
+                w = s[i:i + k]
+                if b"N" in w:
+                    continue
+                want[min(w, w.translate(comp)[::-1])] += 1
+        oc = orc.count_seqs(seqs, k, canonical=True)
+        got = {}
+        for key, c in zip(oc.keys, oc.counts):
+            text = np.zeros(k + 1, dtype=np.uint8)
+            orc.lib().orc_decode_kmer(np.ascontiguousarray(key).ctypes.data, k, text.ctypes.data_as(__import__("ctypes").c_char_p))
+            got[bytes(text[:k])] = int(c)
+        assert got == dict(want), k
+        assert oc.n_total == sum(want.values())

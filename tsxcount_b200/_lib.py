@@ -23,6 +23,7 @@ TSXC_FLAG_NONE = 0
 TSXC_FLAG_EXACT_S = 1
 TSXC_FLAG_NO_WARP_AGG = 2
 TSXC_FLAG_DIRECT = 4
+TSXC_FLAG_CANONICAL = 8
 
 TSXC_IPC_HANDLE_BYTES = 64
 
@@ -91,6 +92,7 @@ PROTOTYPES = {
     "tsxc_dump": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _u64p]),
     "tsxc_dump_file": (C.c_int, [_vp, C.c_char_p]),
     "tsxc_stats": (C.c_int, [_vp, C.POINTER(TsxcStats)]),
+    "tsxc_histogram": (C.c_int, [_vp, _vp, C.c_uint32]),
     "tsxc_route_info": (C.c_int, [_vp, C.POINTER(TsxcRouteInfo)]),
     "tsxc_route_recv_buffer": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp), _u64p]),
     "tsxc_route_set_peers": (C.c_int, [_vp, C.POINTER(_vp), C.c_uint64]),
@@ -122,6 +124,7 @@ PROTOTYPES = {
     "tsxc_copy_async": (C.c_int, [C.c_int, _vp, _vp, C.c_uint64, _vp]),
     "tsxc_debug_hash": (C.c_int, [C.c_uint32, _vp, _vp]),
     "tsxc_debug_unhash": (C.c_int, [C.c_uint32, _vp, _vp]),
+    "tsxc_debug_canonical": (C.c_int, [C.c_uint32, _vp, _vp]),
     "tsxc_debug_layout": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(TsxcStats)]),
 }
 

@@ -1117,6 +1117,27 @@ int tsxc_dump_file(tsxc_table* t, const char* path) {
     return TSXC_OK;
 }
 
+// hist_out[c] = number of distinct k-mers with count c, c < n_bins - 1; hist_out[n_bins - 1] = all with a larger count
+int tsxc_histogram(tsxc_table* t, uint64_t* hist_out, uint32_t n_bins) {
+    if (!t || !hist_out || n_bins < 2 || n_bins > 4096) return fail(t, TSXC_E_INVALID, "histogram: 2 <= n_bins <= 4096");
+    std::lock_guard<std::mutex> g(t->mu);
+    CU(cudaSetDevice(t->device));
+    { const int frc = flush_acc(t); if (frc) return frc; }
+    CU(cudaStreamSynchronize(t->copy_stream));
+    int rc = ensure(t, &t->d_counts, &t->cap_counts, (size_t)n_bins);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(t->d_counts, 0, n_bins * sizeof(uint64_t), t->stream));
+    const int grid = grid_for(t, t->L.n_slots);
+#define M(KW_, W_) k_histogram<KW_, W_><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, n_bins, (unsigned long long*)t->d_counts)
+    TSX_DISPATCH(t->L, M);
+#undef M
+    t->n_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hist_out, t->d_counts, n_bins * sizeof(uint64_t), cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    return TSXC_OK;
+}
+
 /* ---- multi-GPU routing -------------------------------------------------------------------------------------- */
 int tsxc_route_info(tsxc_table* t, tsxc_route_info_t* out) {
     if (!t || !out) return fail(t, TSXC_E_INVALID, "null argument");
@@ -1442,6 +1463,17 @@ int tsxc_debug_hash(uint32_t k, const uint64_t* key, uint64_t* out) {
     if (KW == 1) { Key<1> x{{key[0]}}; auto h = hash_key<1>(x, hp); out[0] = h.w[0]; }
     else if (KW == 2) { Key<2> x{{key[0], key[1]}}; auto h = hash_key<2>(x, hp); out[0] = h.w[0]; out[1] = h.w[1]; }
     else { Key<4> x{{key[0], key[1], key[2], key[3]}}; auto h = hash_key<4>(x, hp); for (int j = 0; j < 4; ++j) out[j] = h.w[j]; }
+    return TSXC_OK;
+}
+
+// min(k-mer, reverse complement) as TSXC_FLAG_CANONICAL tables see it (host code path of the same functions)
+int tsxc_debug_canonical(uint32_t k, const uint64_t* key, uint64_t* out) {
+    const uint32_t KW = tsxc_key_words(k);
+    if (!KW || !key || !out) return TSXC_E_INVALID;
+    const HashParams hp = make_hash_params(k, true);
+    if (KW == 1) { Key<1> x{{key[0]}}; auto c = canonical_key<1>(x, hp); out[0] = c.w[0]; }
+    else if (KW == 2) { Key<2> x{{key[0], key[1]}}; auto c = canonical_key<2>(x, hp); out[0] = c.w[0]; out[1] = c.w[1]; }
+    else { Key<4> x{{key[0], key[1], key[2], key[3]}}; auto c = canonical_key<4>(x, hp); for (int j = 0; j < 4; ++j) out[j] = c.w[j]; }
     return TSXC_OK;
 }
 

@@ -78,11 +78,12 @@ struct HashParams {
     uint32_t top_word;  // index of the highest word holding key bits
     uint64_t top_mask;  // valid bits of that word
     uint32_t xs;        // KW=1: xorshift distance ceil(n/2)
-    uint32_t pad;
+    uint32_t canonical; // 1: every k-mer is replaced by min(k-mer, reverse complement) before it is hashed
 };
 
-inline HashParams make_hash_params(uint32_t k) {
+inline HashParams make_hash_params(uint32_t k, bool canonical = false) {
     HashParams p{};
+    p.canonical = canonical ? 1u : 0u;
     p.nbits = 2 * k;
     p.top_word = (p.nbits - 1) / 64;
     p.top_mask = low_mask(p.nbits - 64 * p.top_word);
@@ -112,9 +113,61 @@ TSX_HD uint64_t word_mask(int j, const HashParams& p) {
     return (uint32_t)j < p.top_word ? ~0ULL : ((uint32_t)j == p.top_word ? p.top_mask : 0ULL);
 }
 
+// ---- canonical k-mers (opt-in; the reference counts forward k-mers only and has no reverse-complement code) ----------
+// Base i sits at bits [2i, 2i+1], A=0 C=1 G=2 T=3, so the complement of a base is its bitwise NOT and the reverse
+// complement is: NOT inside the 2k bits, reverse the order of the 2-bit groups, shift down to bit 0.
+// "The lexicographically smaller of the k-mer and its reverse complement" (jellyfish -C, KMC; the tests' checker
+// computes it on the text) is the NUMERICALLY smaller of the two encodings although base 0 is the least significant
+// digit: lex(f) < lex(r)  <=>  rev(f) < rev(r)  <=>  NOT r < NOT f  <=>  f < r, because rev(f) = NOT r and rev(r) = NOT f.
+TSX_HD uint64_t rev2_64(uint64_t x) {   // reverses the order of the 32 2-bit groups of a word
+#if defined(__CUDA_ARCH__)
+    x = __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0f0f0f0f0f0f0f0fULL) | ((x & 0x0f0f0f0f0f0f0f0fULL) << 4);
+    x = ((x >> 8) & 0x00ff00ff00ff00ffULL) | ((x & 0x00ff00ff00ff00ffULL) << 8);
+    x = ((x >> 16) & 0x0000ffff0000ffffULL) | ((x & 0x0000ffff0000ffffULL) << 16);
+    x = (x >> 32) | (x << 32);
+#endif
+    return ((x & 0x5555555555555555ULL) << 1) | ((x >> 1) & 0x5555555555555555ULL);   // the bit pairs back in order
+}
+
 template <int KW>
-TSX_HD Key<KW> hash_key(const Key<KW>& x, const HashParams& p) {
+TSX_HD Key<KW> revcomp_key(const Key<KW>& x, const HashParams& p) {
+    Key<KW> r;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) r.w[j] = rev2_64(~x.w[KW - 1 - j] & word_mask<KW>(KW - 1 - j, p));
+    const unsigned s = 64u * KW - p.nbits, ws = s >> 6, bs = s & 63u;
+    Key<KW> out;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+        uint64_t lo = 0, hi = 0;
+#pragma unroll
+        for (int i = 0; i < KW; ++i) {          // r.w[j + ws] and r.w[j + ws + 1] without dynamic indexing
+            if ((unsigned)i == (unsigned)j + ws) lo = r.w[i];
+            if ((unsigned)i == (unsigned)j + ws + 1) hi = r.w[i];
+        }
+        out.w[j] = bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
+    }
+    return out;
+}
+
+template <int KW>
+TSX_HD Key<KW> canonical_key(const Key<KW>& x, const HashParams& p) {
+    const Key<KW> r = revcomp_key<KW>(x, p);
+    bool r_less = false, decided = false;
+#pragma unroll
+    for (int j = KW - 1; j >= 0; --j) {
+        if (!decided && r.w[j] != x.w[j]) { r_less = r.w[j] < x.w[j]; decided = true; }
+    }
+    return r_less ? r : x;
+}
+
+template <int KW>
+TSX_HD Key<KW> hash_key(const Key<KW>& x_in, const HashParams& p) {
     Key<KW> h;
+    const Key<KW> x = p.canonical ? canonical_key<KW>(x_in, p) : x_in;
     if constexpr (KW == 1) {
         h.w[0] = hash1(x.w[0], p);
     } else {

@@ -281,6 +281,36 @@ __global__ void __launch_bounds__(kBlockThreads) k_dump(const __grid_constant__ 
     }
 }
 
+// ---- count histogram: hist[c] = number of distinct k-mers with count c (the last bin takes everything above) --------
+// An opt-in extension (the reference has no histogram).  One scan of the table; per-block
+// histogram in shared memory (n_bins <= 4096), flushed with one global atomic per non-empty bin.
+template <int KW, int W>
+__global__ void __launch_bounds__(kBlockThreads) k_histogram(const __grid_constant__ TableView tv, uint32_t n_bins,
+                                                             unsigned long long* __restrict__ hist) {
+    constexpr int SPB = 4 / W;
+    __shared__ unsigned int sh[4096];
+    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_slots = tv.L.n_buckets * SPB;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        const uint64_t bucket = i / SPB;
+        const uint32_t sl = (uint32_t)(i % SPB);
+        const uint64_t h = __ldcg(tv.words + (bucket << 2) + sl * W + (W - 1));
+        if (h == 0 || (h & tv.f_ovf)) continue;
+        uint64_t cnt = h >> tv.vshift;
+        if (h & tv.f_hasovf) {
+            const uint32_t pi = (uint32_t)(h & tv.rmask);
+            const uint64_t home = (bucket - tri(pi)) & tv.lbl_mask;
+            cnt += overflow_lookup<KW, W>(tv, home, pi, sl) << tv.L.V;
+        }
+        atomicAdd(&sh[cnt < n_bins ? (uint32_t)cnt : n_bins - 1], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x)
+        if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+}
+
 // ---- K5b: (k-mer, count) pairs -> text lines "KMER<TAB>COUNT\n" on the device ---------------------------------------
 // Format of count_kmers.py:32-34 of the reference; bases decoded like TSXSeqUtils::toSequence (SequenceUtils.h:47-84).
 // One thread per pair: line length = k + 2 + decimal digits; a block-wide scan places the block's lines back to

@@ -131,7 +131,7 @@ inline bool make_layout(uint32_t k, uint32_t l, uint32_t s, uint32_t flags, uint
 inline TableView make_view(const Layout& L, uint64_t* words, unsigned long long* ctr) {
     TableView tv{};
     tv.words = words; tv.ctr = ctr;
-    tv.hp = make_hash_params(L.k);
+    tv.hp = make_hash_params(L.k, (L.flags & 8u) != 0);     // TSXC_FLAG_CANONICAL
     tv.L = L;
     tv.lbg_mask = low_mask(L.LBg);
     tv.lbl_mask = low_mask(L.LBl);

@@ -184,6 +184,12 @@ class TSXHashMapCUDA:
         """KMER<TAB>COUNT lines, the format of count_kmers.py:32-34."""
         _lib.check(self._lib.tsxc_dump_file(self._h, str(path).encode()), self._h)
 
+    def histogram(self, n_bins=256):
+        """hist[c] = number of distinct k-mers with count c (c < n_bins-1); hist[n_bins-1] = all with a larger count."""
+        out = np.zeros(n_bins, dtype=np.uint64)
+        _lib.check(self._lib.tsxc_histogram(self._h, out.ctypes.data, n_bins), self._h)
+        return out
+
     def stats(self):
         st = _lib.TsxcStats()
         _lib.check(self._lib.tsxc_stats(self._h, C.byref(st)), self._h)

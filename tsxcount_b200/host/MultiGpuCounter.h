@@ -114,6 +114,14 @@ public:
             for (uint64_t i = 0; i < n; ++i) counts[i] += part[i];
         }
     }
+    std::vector<uint64_t> histogram(uint32_t n_bins) {          // shards hold disjoint k-mers: histograms add up
+        std::vector<uint64_t> h(n_bins, 0), part(n_bins);
+        for (auto* t : m_shard) {
+            check(tsxc_histogram(t, part.data(), n_bins), t);
+            for (uint32_t i = 0; i < n_bins; ++i) h[i] += part[i];
+        }
+        return h;
+    }
     void dump(const std::string& path) {
         for (int d = 0; d < m_n; ++d) {
             const std::string part = path + ".shard" + std::to_string(d);

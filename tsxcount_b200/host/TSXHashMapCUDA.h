@@ -56,6 +56,8 @@ public:
     uint64_t getKmerCount(const uint64_t* kmer) { uint64_t c = 0; check(tsxc_lookup(m_h, kmer, 1, &c)); return c; }
     void getKmerCounts(const uint64_t* kmers, uint64_t n, uint64_t* counts) { check(tsxc_lookup(m_h, kmers, n, counts)); }
     void dump(const std::string& path) { check(tsxc_dump_file(m_h, path.c_str())); }
+    // hist[c] = distinct k-mers with count c (c < n_bins-1), hist[n_bins-1] = all with a larger count
+    std::vector<uint64_t> histogram(uint32_t n_bins) { std::vector<uint64_t> h(n_bins); check(tsxc_histogram(m_h, h.data(), n_bins)); return h; }
 
     tsxc_stats_t stats() { tsxc_stats_t s; check(tsxc_stats(m_h, &s)); return s; }
 

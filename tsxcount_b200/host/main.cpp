@@ -55,6 +55,8 @@ static struct argp_option options[] = {
     {"gpus", 'G', "N", 0, "shard the table over N GPUs of this box (power of two; default 1)"},
     {"batch-reads", 'B', "N", 0, "reads per GPU and super-batch with --gpus (default 4194304)"},
     {"n-policy", 'N', "POLICY", 0, "k-mers spanning a non-ACGT base: skip (the only policy; default)"},
+    {"canonical", 'C', 0, 0, "count canonical k-mers: min(k-mer, reverse complement), like jellyfish -C (default: forward k-mers, as the reference)"},
+    {"histogram", 'H', "FILE", 0, "write COUNT<TAB>NUMBER_OF_KMERS lines for counts 1..255 and one line '256+' for the rest"},
     {0}};
 
 struct arguments {
@@ -67,6 +69,9 @@ struct arguments {
     int gpus = 1;
     uint64_t batch_reads = 1u << 22;
     std::string n_policy = "skip";
+    bool canonical = false;
+    std::string histogram_path;
+    uint32_t flags() const { return (wide ? TSXC_FLAG_NONE : TSXC_FLAG_EXACT_S) | (canonical ? TSXC_FLAG_CANONICAL : 0u); }
 };
 
 static error_t parse_opt(int key, char* arg, struct argp_state* state) {
@@ -87,6 +92,8 @@ static error_t parse_opt(int key, char* arg, struct argp_state* state) {
         case 'G': a->gpus = atoi(arg); break;
         case 'B': a->batch_reads = std::max<uint64_t>(1, std::strtoull(arg, nullptr, 10)); break;
         case 'N': a->n_policy = arg ? arg : ""; break;
+        case 'C': a->canonical = true; break;
+        case 'H': a->histogram_path = arg ? arg : ""; break;
         case ARGP_KEY_ARG: return 0;
         default: return ARGP_ERR_UNKNOWN;
     }
@@ -319,6 +326,17 @@ void countKMersMulti(MultiGpuCounter& mg, const arguments& args) {
     std::cout << "Added a total of " << mg.getKmerCount() << " different kmers" << std::endl;   // main.cpp:222
 }
 
+// --histogram: COUNT<TAB>NUMBER_OF_DISTINCT_KMERS for every count that occurs, counts above 255 in one last line
+template <typename Map>
+void writeHistogram(Map& map, const std::string& path) {
+    const std::vector<uint64_t> h = map.histogram(257);
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot open " + path);
+    for (uint32_t c = 1; c < 256; ++c) if (h[c]) std::fprintf(f, "%u\t%llu\n", c, (unsigned long long)h[c]);
+    if (h[256]) std::fprintf(f, "256+\t%llu\n", (unsigned long long)h[256]);
+    std::fclose(f);
+}
+
 // KW words -> k-mer text (inverse of encode_kmer; only needed for the error messages of --check)
 std::string decode_kmer(const uint64_t* w, uint32_t k) {
     std::string s(k, 'A');
@@ -470,7 +488,7 @@ int main(int argc, char* argv[]) {
             std::cerr << "Creating TSXHashMap CUDA, hash-sharded over " << args.gpus << " GPUs" << std::endl;
             // receive buffers: room for what one super-batch can bring to a shard (the batches are hash-uniform)
             const uint64_t recv_cap = args.batch_reads * 400 + (1u << 22);
-            MultiGpuCounter mg(args.k, args.l, args.storagebits, args.gpus, args.wide ? TSXC_FLAG_NONE : TSXC_FLAG_EXACT_S, recv_cap);
+            MultiGpuCounter mg(args.k, args.l, args.storagebits, args.gpus, args.flags(), recv_cap);
             const auto t0 = std::chrono::steady_clock::now();
             countKMersMulti(mg, args);
             const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -480,6 +498,7 @@ int main(int argc, char* argv[]) {
             int rc = 0;
             if (args.check) rc = checkCounts(mg, args);
             if (!args.dump_path.empty()) mg.dump(args.dump_path);
+            if (!args.histogram_path.empty()) writeHistogram(mg, args.histogram_path);
             std::cerr << "Used fields: " << st.used_slots << std::endl;                         // print_stats, TSXHashMap.h:390-395
             std::cerr << "Available fields: " << (double)st.n_slots << std::endl;
             std::cerr << "adds: " << st.kmers_added << std::endl;
@@ -487,7 +506,7 @@ int main(int argc, char* argv[]) {
             return rc;
         }
         std::cerr << "Creating TSXHashMap CUDA" << std::endl;
-        TSXHashMapCUDA map((uint8_t)args.l, args.storagebits, args.k, args.device, args.wide ? TSXC_FLAG_NONE : TSXC_FLAG_EXACT_S);
+        TSXHashMapCUDA map((uint8_t)args.l, args.storagebits, args.k, args.device, args.flags());
         const auto t0 = std::chrono::steady_clock::now();
         countKMers(map, args);
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -497,6 +516,7 @@ int main(int argc, char* argv[]) {
         int rc = 0;
         if (args.check) rc = checkCounts(map, args);
         if (!args.dump_path.empty()) map.dump(args.dump_path);
+        if (!args.histogram_path.empty()) writeHistogram(map, args.histogram_path);
         map.print_stats();                                                                      // main.cpp:479
         std::cerr << "adds: " << st.kmers_added << std::endl;
         std::cerr << "overflow entries: " << st.overflow_entries << std::endl;
