@@ -36,9 +36,10 @@ def parity_check(wl, rank, world, local_rank, n_reads=20_000, l_small=22, region
     gp = _lib.TsxcGenParams(wl["seed"], max(wl["reads"], n_reads) * world, read_len, wl["mode"], wl["genome"], wl["sub"], 0)
     _lib.check(lib.tsxc_gen_reads_device(C.byref(gp), rank * n_reads, n_reads, local_rank, None, d_packed.data_ptr(), d_off.data_ptr()))
     torch.cuda.synchronize()
-    old = {v: os.environ.get(v) for v in ("TSXC_REGION_LOG2", "TSXC_SEG_LOG2", "TSXC_CHUNK_KEYS")}
+    old = {v: os.environ.get(v) for v in ("TSXC_REGION_LOG2", "TSXC_SEG_LOG2", "TSXC_CHUNK_KEYS", "TSXC_PAGE_LOG2")}
     os.environ["TSXC_REGION_LOG2"] = region_log2      # small regions: the small shards take the routed pipeline
     os.environ["TSXC_SEG_LOG2"] = "11"                # several segments, several rounds
+    os.environ["TSXC_PAGE_LOG2"] = "5"                # 32-key pages: the small receive buffers still get a page pool (fine pass)
     try:
         be = CudaRouteBackend(k, l_small + shard_bits, 0, rank, world, local_rank)
         sc = ShardedCounter(be, rank, world, recv_cap_keys=n_reads * read_len // 2 + (1 << 17))
@@ -46,6 +47,7 @@ def parity_check(wl, rank, world, local_rank, n_reads=20_000, l_small=22, region
         be.sync()
         keys, counts = be.hm.getAllKmers()
         st = be.hm.stats()
+        assert world == 1 or st["group_cap_keys"] == 32, "the parity preamble must take the two-level path (page pool) of the benchmark"
         rounds = sc.rounds
         be.close()
     finally:

@@ -223,6 +223,12 @@ int status_from_flags(tsxc_table* t, uint64_t flags) {
 
 // ---- region-sorted pipeline: geometry, buffers, launch sequence -------------------------------------------------
 
+uint64_t env_u64(const char* name, uint64_t dflt) {
+    const char* e = std::getenv(name);
+    if (!e || !*e) return dflt;
+    return std::strtoull(e, nullptr, 10);
+}
+
 // Digits of the insert pipeline: regions of 2^region_log2 bytes of a shard of 2^LBl buckets (32 bytes each), at most
 // kNB1 of them.  One shard: one digit.  Hash-sharded: a routing digit (owner + coarse local bits) and a local fine digit.
 RadixGeom make_radix_geom(const Layout& L, uint32_t region_log2, uint32_t seg_log2) {
@@ -236,9 +242,16 @@ RadixGeom make_radix_geom(const Layout& L, uint32_t region_log2, uint32_t seg_lo
     } else {
         // hash-sharded: the routing pass keeps runs of 128 bytes for NVLink (at most 256 bins over all shards), the
         // receiver adds the remaining bits in a second, local pass (tsx_radix.cuh, two-level mode)
-        g.d1 = std::min<uint32_t>(8, L.shard_bits + fb);
+        // coarse local bits of the routing digit: the fewer, the longer the runs that cross NVLink (2^c bins per shard).
+        // 3 bits = runs of 64-256 k-mers; a routing digit of exactly 6 bits would fall between the cheap ballot ranking
+        // (<= 5 bits) and the conflict-detect ranking (>= 7 bits), so 8 shards take 4.  Measured at 2 GPUs: route 82.8 /
+        // 75.2 / 72.4 ms for 5 / 3 / 2 bits, step 437 / 429.5 / 430 ms.
+        uint32_t coarse = 3;
+        if (L.shard_bits + coarse == 6) coarse = 4;
+        coarse = (uint32_t)std::min<uint64_t>(8, env_u64("TSXC_ROUTE_COARSE_BITS", coarse));
+        g.d1 = std::min<uint32_t>(std::min<uint32_t>(8, L.shard_bits + coarse), L.shard_bits + fb);
         const uint32_t c = g.d1 - L.shard_bits;
-        g.d2 = std::min<uint32_t>(10 - c, fb - c);
+        g.d2 = std::min<uint32_t>(std::min<uint32_t>(10 - c, 8), fb - c);    // the fine pass sorts by at most 8 bits
     }
     g.nb1 = 1u << g.d1; g.nb2 = 1u << g.d2; g.nbl = 1u << (g.d1 - L.shard_bits);
     g.shift1 = L.LBg - g.d1; g.shift2 = L.LBg - g.d1 - g.d2;
@@ -262,11 +275,6 @@ RadixGeom make_lookup_geom(const Layout& L, uint32_t region_log2, uint32_t seg_l
     return g;
 }
 
-uint64_t env_u64(const char* name, uint64_t dflt) {
-    const char* e = std::getenv(name);
-    if (!e || !*e) return dflt;
-    return std::strtoull(e, nullptr, 10);
-}
 
 uint32_t slice_keys_of(const Layout& L) { return kBlockThreads * (L.KW == 1 ? 4u : (L.KW == 2 ? 2u : 1u)); }
 
