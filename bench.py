@@ -397,11 +397,12 @@ def main():
             return st, clear_s
 
         log(f"{w['name']}: inputs generated: {n_reads} reads, {n_kmers} k-mers; table {layout['table_bytes'] / 2**30:.1f} GiB")
+        sampler = ClockSampler(dev)
+        sampler.start()              # nvidia-smi needs a few hundred ms to deliver its first sample: start it before the warm-up ...
         for i in range(warmup):
             st, _ = one_step()
             log(f"{w['name']} warmup {i}: {st['step_ms']:.1f} ms")
-        sampler = ClockSampler(dev)
-        sampler.start()
+        sampler.rows.clear()         # ... and keep only what it reports during the timed steps
         step_ms, launches, clear_ms, phases = [], 0, [], []
         for _ in range(steps):
             st, clear_s = one_step()

@@ -155,15 +155,17 @@ def bench_main(args, wl, rank, world, local_rank, log=lambda m: None, extra_work
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t[0].item()), float(t[1].item())
 
-        for i in range(args.warmup):
-            dt, dms = one_step()
-            if rank == 0:
-                log(f"{w['name']} warmup {i}: wall {dt * 1e3:.1f} ms, device {dms * 1e3:.1f} ms")
         sampler = None
         if rank == 0:
             import bench as _bench
             sampler = _bench.ClockSampler(local_rank)
-            sampler.start()
+            sampler.start()          # before the warm-up: nvidia-smi needs a few hundred ms for its first sample
+        for i in range(args.warmup):
+            dt, dms = one_step()
+            if rank == 0:
+                log(f"{w['name']} warmup {i}: wall {dt * 1e3:.1f} ms, device {dms * 1e3:.1f} ms")
+        if sampler:
+            sampler.rows.clear()     # keep only the samples of the timed steps
         steps = [one_step() for _ in range(args.steps)]
         clocks = sampler.stop() if sampler else None
         st = be.hm.stats()
