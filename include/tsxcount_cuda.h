@@ -209,8 +209,6 @@ int tsxc_route_begin(tsxc_table* t, const uint64_t* d_packed, const uint64_t* d_
 int tsxc_route_hist(tsxc_table* t, uint32_t round, uint32_t* d_hist_out);
 int tsxc_route_send(tsxc_table* t, uint32_t round, const uint32_t* d_hist_all);
 int tsxc_route_insert(tsxc_table* t);
-/* Insert n already-hashed k-mers (KW words each) owned by this shard. */
-int tsxc_add_hashes_device(tsxc_table* t, const uint64_t* d_hashes, uint64_t n);
 
 /* ---- peer-memory plumbing for the multi-GPU exchange (one process per GPU) ------------------------ */
 /* The owner exports its receive buffer (CUDA IPC), the other ranks open it and pass the mapped pointers to

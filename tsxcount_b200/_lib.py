@@ -100,7 +100,6 @@ PROTOTYPES = {
     "tsxc_route_hist": (C.c_int, [_vp, C.c_uint32, _vp]),
     "tsxc_route_send": (C.c_int, [_vp, C.c_uint32, _vp]),
     "tsxc_route_insert": (C.c_int, [_vp]),
-    "tsxc_add_hashes_device": (C.c_int, [_vp, _vp, C.c_uint64]),
     "tsxc_pack_reads": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _u64p, _u64p]),
     "tsxc_gen_reads_device": (C.c_int, [C.POINTER(TsxcGenParams), C.c_uint64, C.c_uint64, C.c_int, _vp, _vp, _vp]),
     "tsxc_k0_random_rmw": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),

@@ -667,17 +667,15 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
     return TSXC_OK;
 }
 
-static int add_keys_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n, bool hashed) {
+static int add_keys_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n) {
     if (n == 0) return TSXC_OK;
     const int grid = grid_for(t, n);
     const bool agg = !(t->L.flags & TSXC_FLAG_NO_WARP_AGG);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     const bool timed = main_begin(t, t->stream, &ev);
-#define M(KW_, W_)                                                                                              \
-    if (hashed) { if (agg) k_add_kmers<KW_, W_, true, true><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n);  \
-                  else k_add_kmers<KW_, W_, true, false><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n); }   \
-    else { if (agg) k_add_kmers<KW_, W_, false, true><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n);        \
-           else k_add_kmers<KW_, W_, false, false><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n); }
+#define M(KW_, W_)                                                                                      \
+    if (agg) k_add_kmers<KW_, W_, true><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n);      \
+    else k_add_kmers<KW_, W_, false><<<grid, kBlockThreads, 0, t->stream>>>(t->tv, d_kmers, n)
     TSX_DISPATCH(t->L, M);
 #undef M
     t->n_launches++;
@@ -911,14 +909,7 @@ int tsxc_add_kmers_device(tsxc_table* t, const uint64_t* d_kmers, uint64_t n) {
     if (!t || (!d_kmers && n)) return fail(t, TSXC_E_INVALID, "null argument");
     std::lock_guard<std::mutex> g(t->mu);
     CU(cudaSetDevice(t->device));
-    return add_keys_device(t, d_kmers, n, false);
-}
-
-int tsxc_add_hashes_device(tsxc_table* t, const uint64_t* d_hashes, uint64_t n) {
-    if (!t || (!d_hashes && n)) return fail(t, TSXC_E_INVALID, "null argument");
-    std::lock_guard<std::mutex> g(t->mu);
-    CU(cudaSetDevice(t->device));
-    return add_keys_device(t, d_hashes, n, true);
+    return add_keys_device(t, d_kmers, n);
 }
 
 int tsxc_add_kmers(tsxc_table* t, const uint64_t* kmers, uint64_t n) {
@@ -933,7 +924,7 @@ int tsxc_add_kmers(tsxc_table* t, const uint64_t* kmers, uint64_t n) {
     int rc = ensure(t, &t->d_keys, &t->cap_keys, words);
     if (rc) return rc;
     CU(cudaMemcpyAsync(t->d_keys, kmers, words * sizeof(uint64_t), cudaMemcpyHostToDevice, t->stream));
-    return add_keys_device(t, t->d_keys, n, false);
+    return add_keys_device(t, t->d_keys, n);
 }
 
 int tsxc_sync(tsxc_table* t) {

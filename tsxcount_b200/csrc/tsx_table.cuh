@@ -158,10 +158,6 @@ __device__ __forceinline__ void load_bucket(const uint64_t* b, uint64_t (&w)[4])
     asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(b) : "memory");
 }
 
-__device__ __forceinline__ void prefetch_bucket_l2(const uint64_t* b) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(b));
-}
-
 // 128-bit compare-and-swap (sm_90+): returns the old value in (o0, o1)
 __device__ __forceinline__ void cas128(uint64_t* addr, uint64_t c0, uint64_t c1, uint64_t s0, uint64_t s1, uint64_t& o0,
                                        uint64_t& o1) {
@@ -395,13 +391,6 @@ __device__ __forceinline__ void insert_hashed(const TableView& tv, const Key<KW>
     }
     st.errors |= ERR_TABLE_FULL;
     if (LEAN) atomicOr(tv.ctr + CTR_ERRORS, (unsigned long long)ERR_TABLE_FULL);
-}
-
-// Out-of-line copy for kernels where inserting is the rare path (phase A of the two-phase insert): keeps the
-// probe loop out of their register budget.
-template <int KW, int W>
-__device__ __noinline__ void insert_hashed_cold(const TableView& tv, const Key<KW>& H, uint64_t count, LocalStats& st) {
-    insert_hashed<KW, W>(tv, H, count, st);
 }
 
 // Reference: findOverflowCounts, TSXHashMap.h:951-1039

@@ -121,10 +121,6 @@ class TSXHashMapCUDA:
     def addKmersDevice(self, d_kmers, n):
         _lib.check(self._lib.tsxc_add_kmers_device(self._h, d_kmers, n), self._h)
 
-    def addHashesDevice(self, d_hashes, n):
-        _lib.check(self._lib.tsxc_add_hashes_device(self._h, d_hashes, n), self._h)
-
-    # -- multi-GPU routing (see include/tsxcount_cuda.h "multi-GPU routing") ------------------------
     def routeInfo(self):
         info = _lib.TsxcRouteInfo()
         _lib.check(self._lib.tsxc_route_info(self._h, C.byref(info)), self._h)
