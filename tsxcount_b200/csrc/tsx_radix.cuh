@@ -1086,26 +1086,29 @@ k_part_keys_paged(const __grid_constant__ TableView tv, const __grid_constant__ 
 // ---- phase B: insert keys in region order ---------------------------------------------------------------------------
 // Work item = one slice of consecutive keys of `src` (ticket order = table-region order).
 //
-// What was measured about this kernel (profiles/r02_k0r_modes.md, profiles/r02_pipeline_c2_scaled_summary.txt):
-//  * all blocks sweeping 8 MiB regions, sector loads alone run at 150 G/s, a load followed by a fire-and-forget atomic
-//    at 64-73 G/s, a load followed by an atomic whose result the thread needs (the insert's claim) at 43-49 G/s;
+// What was measured about this kernel (profiles/r02_k0r_modes.md, profiles/r02_pipeline_history.md,
+// profiles/r02_single_pass_c2_quarter_summary.txt):
+//  * all blocks sweeping one table region at a time, sector loads alone run at 165-177 G/s, a load followed by a
+//    fire-and-forget RED at 70 G/s, a load followed by ANY 64-bit atomic whose result returns to the SM at 45 G/s (37 G/s
+//    with 128 MiB regions), whether the thread waits for the result or not and at any occupancy from 1280 to 2048 threads
+//    per SM: the insert's claim is bound by the atomic-return path, and this kernel runs at 0.92-0.94 of that rate;
+//  * 40 registers (6 resident blocks per SM) beat 48 / 64 / 32 (221 / 239 / 221 vs 202 ms on config 2), provided the
+//    per-k-mer statistics stay out of local memory (see insert_hashed<LEAN>);
+//  * prefetching the next slice's home buckets with prefetch.global.L2 costs 10 % (221 -> 242 ms);
 //  * merging equal keys of a warp with __match_any_sync on every step kept the XU pipe 93 % busy (MATCH.ANY.U64);
-//  * issuing several probes and claims per thread before looking at any result made it SLOWER (439 vs 257 ms on
-//    config 2): at load factors near 0.5 almost every warp has a lane whose home bucket is full, and that lane's
-//    re-probe chain then runs with the other 31 lanes idle.
-// So: one key per thread and step, all keys of the slice loaded up front, and the duplicate handling only where it
-// pays.  A slice in which two neighbouring keys are equal (with a k-mer that makes up a few per cent of the input this
-// is all but certain) is "skewed": equal keys of a warp are merged with __match_any_sync and the warp's keys go
-// through a shared-memory combiner: slot word = index of the first key that claimed it (+1) in the low 16 bits | 48
-// fingerprint bits of hash word 0; a later key with the same fingerprint compares itself with the claimer's key in
-// `src` and, if equal, just adds to the slot's count.  The slots are flushed once per slice, so a k-mer that dominates
-// the input costs one table update per slice instead of one per occurrence.  All other slices take every key straight
-// to insert_hashed().
+//  * issuing several probes and claims per thread before looking at any result made it slower (439 vs 257 ms): at load
+//    factors near 0.5 almost every warp has a lane whose home bucket is full, and that lane's re-probe chain then runs
+//    with the other 31 lanes idle.
+// So: one key per thread and step, and the duplicate handling only where it pays.  A slice in which two neighbouring
+// keys are equal (with a k-mer that makes up a few per cent of a region this is all but certain) is "skewed": equal keys
+// of a warp are merged with __match_any_sync and every key of the slice goes through a shared-memory combiner: slot word
+// = index of the first key that claimed it (+1) in the low 16 bits | 48 fingerprint bits of hash word 0; a later key with
+// the same fingerprint compares itself with the claimer's key in `src` and, if equal, just adds to the slot's count.  The
+// slots are flushed once per slice, so a k-mer that dominates a region costs one table update per slice instead of one
+// per occurrence.  All other slices take every key straight to insert_hashed().
 #ifndef TSX_INSERT_MINB
 #define TSX_INSERT_MINB 6
 #endif
-// (Measured and dropped: prefetching the next slice's home buckets into L2 with prefetch.global.L2 costs 10 %,
-// 221 -> 242 ms on config 2; the kernel is bound by the atomic-return path, not by latency.)
 
 struct CombSmem {
     unsigned long long key[kCombSlots];

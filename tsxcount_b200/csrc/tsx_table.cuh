@@ -153,7 +153,7 @@ inline TableView make_view(const Layout& L, uint64_t* words, unsigned long long*
 // Table words are written by atomics from every SM: reads must come from L2 (ld.global.cg), never a
 // stale L1 line.
 // One 256-bit load (sm_100: LDG.E.256) instead of two 128-bit ones: a scattered warp-wide load costs the LSU one
-// wavefront per lane PER INSTRUCTION, and phase B is bound by exactly that (profiles/r02_pipeline_c2_scaled_summary.txt).
+// wavefront per lane PER INSTRUCTION.
 __device__ __forceinline__ void load_bucket(const uint64_t* b, uint64_t (&w)[4]) {
     asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(b) : "memory");
 }
