@@ -257,6 +257,61 @@ def test_feeder_multiline_fasta_split_keeps_the_kmer_multiset(tmp_path):
     assert max(len(x) for x in want_pieces) == 1000
 
 
+def _write_bgzf(path, data, block=30000, eof_marker=True):
+    """BGZF as bgzip / htslib write it: independent gzip members of <= 64 KiB with a 'BC' extra subfield holding the
+    member size - 1, then the empty end-of-file member."""
+    import struct
+    import zlib
+    out = bytearray()
+    for i in list(range(0, len(data), block)) + ([None] if eof_marker else []):
+        chunk = b"" if i is None else data[i:i + block]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        payload = co.compress(chunk) + co.flush()
+        bsize = 18 + len(payload) + 8
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize - 1)
+        out += payload + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk))
+    with open(path, "wb") as f:
+        f.write(out)
+    return bytes(out)
+
+
+def test_feeder_inflates_bgzf_in_parallel_and_rejects_damage(tmp_path):
+    """A bgzip (BGZF) input is inflated block-parallel and must deliver exactly the stream of the plain file; a flipped
+    payload byte (CRC), a file cut inside a block and garbage where a block header should be all make the reader throw.
+    An ordinary single-stream .gz still goes through gzread."""
+    import gzip
+    import random
+    rnd = random.Random(5)
+    seqs = ["".join(rnd.choice("ACGT") for _ in range(rnd.randint(1, 400))) for _ in range(6000)]
+    text = "".join(f"@r{i}\n{s}\n+\n{'I' * len(s)}\n" for i, s in enumerate(seqs)).encode()
+    plain, bgz, gz = tmp_path / "r.fastq", tmp_path / "r.fastq.bgz", tmp_path / "r.fastq.gz"
+    plain.write_bytes(text)
+    raw = _write_bgzf(bgz, text)
+    with gzip.open(gz, "wb") as f:
+        f.write(text)
+
+    def ingest(path, threads, block=8 << 20):
+        env = dict(os.environ, INGEST_INFLATE_THREADS=str(threads))
+        return subprocess.run([INGEST, str(path), "1000", str(block)], capture_output=True, text=True, env=env)
+
+    want = ingest(plain, 1).stdout
+    assert "reads=6000" in want
+    for threads in (2, 4, 16):
+        p = ingest(bgz, threads, block=1 << 16)
+        assert p.returncode == 0 and p.stdout == want, p.stderr
+        assert "parallel inflate: yes (BGZF)" in p.stderr
+    assert ingest(bgz, 1).stdout == want                     # one thread: plain gzread reads BGZF too
+    p = ingest(gz, 4)
+    assert p.stdout == want and "parallel inflate: no" in p.stderr
+    # damage
+    flipped = bytearray(raw); flipped[len(raw) // 2] ^= 0x55
+    (tmp_path / "flip.bgz").write_bytes(flipped)
+    (tmp_path / "cut.bgz").write_bytes(raw[:len(raw) * 2 // 3])
+    for name in ("flip.bgz", "cut.bgz"):
+        p = ingest(tmp_path / name, 4)
+        assert p.returncode != 0 and "damaged or truncated" in p.stderr, (name, p.stderr[-300:])
+
+
 def test_feeder_rejects_truncated_gzip(tmp_path):
     """A damaged .gz must not look like a (shorter) input: the reader throws, the tool exits non-zero."""
     import gzip

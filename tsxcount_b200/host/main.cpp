@@ -155,7 +155,8 @@ void countKMers(TSXHashMapCUDA& map, const arguments& args) {
         try {
             const uint64_t lo = n_readers > 1 ? file_bytes / n_readers * idx : 0;
             const uint64_t hi = n_readers > 1 && idx + 1 < n_readers ? file_bytes / n_readers * (idx + 1) : ~0ULL;
-            FastxReader rd(args.input_path, multi_fasta ? 0 : 4, 8u << 20, lo, hi);
+            // a bgzip (BGZF) input is inflated block-parallel by up to 8 threads; plain gzip is one deflate stream
+            FastxReader rd(args.input_path, multi_fasta ? 0 : 4, 8u << 20, lo, hi, std::max(1, std::min(args.threads, 8)));
             if (multi_fasta) rd.setFastaSplit(1u << 20, args.k - 1);   // pieces overlap by k-1 bases: same k-mer multiset
             for (;;) {
                 Raw* r;
@@ -267,7 +268,7 @@ void countKMers(TSXHashMapCUDA& map, const arguments& args) {
 void countKMersMulti(MultiGpuCounter& mg, const arguments& args) {
     const int N = mg.gpus();
     const bool multi_fasta = FastxReader::sniff(args.input_path) == '>';
-    FastxReader rd(args.input_path, multi_fasta ? 0 : 4, 8u << 20);
+    FastxReader rd(args.input_path, multi_fasta ? 0 : 4, 8u << 20, 0, ~0ULL, std::max(1, std::min(args.threads, 8)));
     if (multi_fasta) rd.setFastaSplit(1u << 20, args.k - 1);
     struct Raw { std::string bases; std::vector<uint64_t> offsets; size_t n = 0; };
     std::vector<Raw> raw(N);

@@ -2,7 +2,8 @@
 // reads, bases, non-ACGT bases, an FNV-1a hash of the concatenated sequences and of the packed stream, and the
 // throughput.  Used by tests/test_cli.py (no GPU needed) and for ingest measurements.
 //   ingest_check <file> [batch_reads] [block_bytes] [ranges] [parallel]
-// The format (FASTQ / multi-line FASTA) is taken from the content; INGEST_PIECE / INGEST_OVERLAP set the FASTA split.
+// The format (FASTQ / multi-line FASTA) is taken from the content; INGEST_PIECE / INGEST_OVERLAP set the FASTA split;
+// INGEST_INFLATE_THREADS > 1 lets a BGZF (bgzip) input be inflated by that many threads.
 // ranges > 1 reads the file as that many byte ranges (FastxReader's range mode, the CLI's --readers), one after the
 // other, which must reproduce the sequential stream exactly (same reads/bases/hash_bases/hash_lens); with a 5th
 // argument the ranges are read and packed by one thread each and only the totals and the throughput are printed.
@@ -69,7 +70,9 @@ int main(int argc, char** argv) {
     double t_read = 0, t_pack = 0;
     const auto t0 = std::chrono::steady_clock::now();
     for (int range = 0; range < ranges; ++range) {
-    FastxReader reader(argv[1], 0, block, lo_of(range), hi_of(range));   // 0: FASTQ or multi-line FASTA by content
+    const int inflate_threads = std::getenv("INGEST_INFLATE_THREADS") ? atoi(std::getenv("INGEST_INFLATE_THREADS")) : 1;
+    FastxReader reader(argv[1], 0, block, lo_of(range), hi_of(range), inflate_threads);   // 0: FASTQ or multi-line FASTA by content
+    if (inflate_threads > 1) std::fprintf(stderr, "parallel inflate: %s\n", reader.parallelInflate() ? "yes (BGZF)" : "no");
     if (const char* e = std::getenv("INGEST_PIECE")) {                   // multi-line FASTA: piece length, overlap (= k-1)
         const char* o = std::getenv("INGEST_OVERLAP");
         reader.setFastaSplit(std::strtoull(e, nullptr, 0), o ? std::strtoull(o, nullptr, 0) : 0);
