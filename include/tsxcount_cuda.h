@@ -288,6 +288,11 @@ int tsxc_debug_hash(uint32_t k, const uint64_t* key, uint64_t* out);
 int tsxc_debug_unhash(uint32_t k, const uint64_t* hash, uint64_t* out);
 /* min(k-mer, reverse complement) in the library's encoding (what TSXC_FLAG_CANONICAL tables count); host-side. */
 int tsxc_debug_canonical(uint32_t k, const uint64_t* key, uint64_t* out);
+/* One block round of the partition pass's walk over valid k-mer starts, on the host through the functions the kernel
+ * calls: the k-mers (KW words each) that start in stream words [round, round + 512) and before word w_end of a packed
+ * stream with its read-end bitmap (bit g set: base g is the last base of a read).  keys_out: room for 16384 k-mers. */
+int tsxc_debug_sparse_round(uint32_t k, const uint64_t* packed, const uint32_t* ends, uint64_t n_words, uint64_t n_bases,
+                            uint64_t round, uint64_t w_end, uint64_t* keys_out, uint32_t* n_out);
 /* Entry layout chosen for (k, l, s, flags, n_shards) without touching a GPU. */
 int tsxc_debug_layout(uint32_t k, uint32_t l, uint32_t s, uint32_t flags, uint32_t n_shards, tsxc_stats_t* out);
 

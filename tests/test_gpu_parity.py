@@ -289,8 +289,11 @@ def _route_all(tsx, shards, d_packed, d_off, n_reads, n_bases, recv_cap_keys=0):
 @pytest.mark.parametrize("pool", [False, True], ids=["from_receive_buffer", "fine_pass_into_page_pool"])
 @pytest.mark.parametrize("k,n_shards,mode,region", [(31, 2, 1, "12"), (31, 8, 0, "12"), (63, 4, 2, "14"), (127, 2, 1, "12"),
                                                     (31, 4, 3, "30")])
-def test_sharded_route_and_insert(tsx, k, n_shards, mode, region, pool, monkeypatch):
+@pytest.mark.parametrize("walk", ["", "101"], ids=["walk_by_density", "sparse_walk"])
+def test_sharded_route_and_insert(tsx, k, n_shards, mode, region, pool, walk, monkeypatch):
     monkeypatch.setenv("TSXC_REGION_LOG2", region)    # "30": no fine regions at all, routing by owner only
+    if walk:
+        monkeypatch.setenv("TSXC_SPARSE_PCT", walk)   # the routing pass enumerates valid k-mer starts only, whatever their density
     monkeypatch.setenv("TSXC_SEG_LOG2", "9")          # many planner segments, several rounds
     if pool:
         # the two-level mode of large shards: groups of the receive buffer take a second, local partition pass into a
@@ -400,6 +403,24 @@ def test_pipeline_parity(tsx, small_regions, case):
     seqs = orc.gen_reads(n_reads=n_reads, read_len=read_len, **gen)
     st, oc = run_case(tsx, seqs, k, l, s, flags)
     assert st["main_kernel_launches"] >= 4, "expected the pipeline (histogram, partition, insert)"
+
+
+@pytest.mark.parametrize("pct", ["0", "101"], ids=["dense_walk", "sparse_walk"])
+@pytest.mark.parametrize("case", [PART_CASES[0], PART_CASES[1], PART_CASES[4], PART_CASES[6], PART_CASES[7]], ids=lambda c: c[0])
+def test_pipeline_both_walks_of_the_partition_pass(tsx, small_regions, monkeypatch, case, pct):
+    """S1 walks every base position (dense) or only the positions that start a k-mer (sparse: validity masks of a block
+    round, scan, i-th valid position); the planner's density of a chunk picks one.  Both forced on the same inputs,
+    k = 31 / 63 / 96 / 127, in all three geometries; ragged reads around k with the sparse walk."""
+    monkeypatch.setenv("TSXC_SPARSE_PCT", pct)
+    name, gen, n_reads, read_len, k, l, s, flags = case
+    seqs = orc.gen_reads(n_reads=n_reads, read_len=read_len, **gen)
+    st, oc = run_case(tsx, seqs, k, l, s, flags)
+    assert st["main_kernel_launches"] >= 4
+    if pct == "101" and k == 127:
+        rng = np.random.default_rng(127)
+        ragged = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(n))) for n in rng.integers(100, 200, size=3000)]
+        ragged += [b"", b"ACGT" * 31 + b"AC", b"T" * 127, b"G" * 126]
+        run_case(tsx, ragged, k, l, s, flags)
 
 
 @pytest.mark.parametrize("case", [PART_CASES[0], PART_CASES[4], PART_CASES[7]], ids=lambda c: c[0])

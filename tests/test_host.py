@@ -250,3 +250,46 @@ def test_canonical_key_is_the_lexicographic_minimum_of_kmer_and_reverse_compleme
         out = np.zeros(4, dtype=np.uint64)
         assert lib.tsxc_debug_canonical(k, key.ctypes.data, out.ctypes.data) == 0
         assert sequtils.to_sequence(out[:kw], k) == want, (s, want)
+
+
+@pytest.mark.parametrize("k,read_lens", [
+    (127, [150] * 300), (128, [128, 127, 129, 150, 400, 1, 0, 128] * 20), (63, [70, 64, 63, 62, 150] * 40),
+    (31, [40, 31, 30, 33, 150, 2] * 60), (33, [50] * 300), (5, [4, 5, 6, 1000, 3] * 30), (97, [100, 96, 97, 4000, 98] * 12),
+])
+def test_sparse_walk_of_the_partition_pass_enumerates_exactly_the_kmers(k, read_lens):
+    """S1's walk over valid k-mer starts (tsx_radix.cuh: valid_starts / locate_word / select_bit / kmer_from_stream32),
+    run on the host through tsxc_debug_sparse_round, yields exactly the forward k-mers of the reads
+    (testExecution.h:15-36), round by round, for reads around k and stream ends inside a round."""
+    lib = _lib.load()
+    rng = np.random.default_rng(k * 1000 + len(read_lens))
+    seqs = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n)) for n in read_lens]
+    seqs = [s for s in seqs if len(s)]
+    ascii_, offsets = sequtils.concat_reads(seqs)
+    packed, seg, nbad = sequtils.pack_reads(ascii_, offsets)
+    assert nbad == 0
+    n_bases = int(seg[-1])
+    n_words = (n_bases + 31) // 32
+    ends = np.zeros(n_words + 1, dtype=np.uint32)
+    for e in seg[1:].tolist():
+        if e > 0:
+            ends[(e - 1) >> 5] |= np.uint32(1 << ((e - 1) & 31))
+    kw = sequtils.key_words(k)
+    got = []
+    out = np.zeros(16384 * kw, dtype=np.uint64)
+    n_out = C.c_uint32(0)
+    for rnd in range(0, n_words, 512):
+        assert lib.tsxc_debug_sparse_round(k, packed.ctypes.data, ends.ctypes.data, n_words, n_bases, rnd, n_words,
+                                           out.ctypes.data, C.byref(n_out)) == 0
+        got.append(out[: n_out.value * kw].reshape(-1, kw).copy())
+    got = np.concatenate(got) if got else np.zeros((0, kw), dtype=np.uint64)
+    want = [s[i:i + k].decode() for s in seqs for i in range(len(s) - k + 1)]
+    assert len(got) == len(want)
+    want_arr = sequtils.kmers_to_array(want, k) if want else np.zeros((0, kw), dtype=np.uint64)
+    # the walk lists the k-mers in stream order, which is the order of the reads
+    assert np.array_equal(got, want_arr)
+    # a segment that ends inside the round: words at and after w_end start nothing
+    if n_words > 3:
+        assert lib.tsxc_debug_sparse_round(k, packed.ctypes.data, ends.ctypes.data, n_words, n_bases, 0, 3,
+                                           out.ctypes.data, C.byref(n_out)) == 0
+        starts = [int(offsets[r]) + i for r, s in enumerate(seqs) for i in range(len(s) - k + 1)]
+        assert n_out.value == sum(1 for g in starts if g < 96)

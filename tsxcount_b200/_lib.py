@@ -124,6 +124,7 @@ PROTOTYPES = {
     "tsxc_debug_hash": (C.c_int, [C.c_uint32, _vp, _vp]),
     "tsxc_debug_unhash": (C.c_int, [C.c_uint32, _vp, _vp]),
     "tsxc_debug_canonical": (C.c_int, [C.c_uint32, _vp, _vp]),
+    "tsxc_debug_sparse_round": (C.c_int, [C.c_uint32, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "tsxc_debug_layout": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(TsxcStats)]),
 }
 

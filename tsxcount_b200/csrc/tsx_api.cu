@@ -71,6 +71,8 @@ struct tsxc_table {
     int part_grid = 0;                                         // thread blocks of S1 the page pool was planned for
     bool radix_on = false;                                     // tables this large take the pipeline by default
     uint32_t region_log2 = 27;                                 // target size of a table region (bytes, log2)
+    uint32_t sparse_pct = 62;                                  // S1 walks valid positions only when fewer than this % of the positions start a k-mer
+                                                               // (measured: S1 9 % faster at 59 % (config 3), 23 % slower at 80 % (config 2))
     uint16_t* d_page_bin = nullptr; size_t cap_page_bin = 0;   // paged mode: bin of every pool page
     uint16_t* d_page_len = nullptr; size_t cap_page_len = 0;   //             keys in it
     ulonglong2* d_slices = nullptr; size_t cap_slices = 0;     // phase B work items: (first key, keys)
@@ -353,9 +355,9 @@ int radix_reserve(tsxc_table* t, uint64_t positions, bool for_peers = false) {
     return TSXC_OK;
 }
 
-template <int KW> constexpr size_t part_smem_bytes(bool paged) {
+template <int KW> constexpr size_t part_smem_bytes(bool paged, bool sparse) {
     return ((paged ? sizeof(TileSmem<KW, kNB1, true>) : sizeof(TileSmem<KW, kNB1, false>)) + 15) / 16 * 16 + 256 * sizeof(uint64_t*) +
-           (paged ? sizeof(PageState) : 0);
+           (paged ? sizeof(PageState) : 0) + (sparse ? sizeof(SparseStage<KW>) : 0);
 }
 template <int KW> constexpr size_t fine_smem_bytes() {
     return ((sizeof(TileSmem<KW, kNB, true>) + 15) / 16 * 16 + sizeof(ItemFeed<KW>) + 15) / 16 * 16 + sizeof(PageState);
@@ -419,27 +421,38 @@ int launch_sort_insert(tsxc_table* t, cudaStream_t s) {
 int opt_in_shared_memory(tsxc_table* t) {
 #define M(KW_)                                                                                                                     \
     CU(cudaFuncSetAttribute(k_hist_reads<KW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes));                    \
-    CU(cudaFuncSetAttribute(k_part_reads<KW_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(false))); \
-    CU(cudaFuncSetAttribute(k_part_reads<KW_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(true)));   \
+    CU(cudaFuncSetAttribute(k_part_reads<KW_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(false, false))); \
+    CU(cudaFuncSetAttribute(k_part_reads<KW_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(true, false)));   \
+    CU(cudaFuncSetAttribute(k_part_reads<KW_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(false, true)));   \
+    CU(cudaFuncSetAttribute(k_part_reads<KW_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes<KW_>(true, true)));     \
     CU(cudaFuncSetAttribute(k_part_keys_paged<KW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fine_smem_bytes<KW_>()))
     TSX_DISPATCH_KW(t->L, M);
 #undef M
     return TSXC_OK;
 }
 
-// S1 of chunk c (exact mode: into A or the owners' buffers; paged mode: into the pool)
+// S1 of chunk c (exact mode: into A or the owners' buffers; paged mode: into the pool).  The dense and the sparse walk
+// are both launched; the planner's numbers of the chunk (on the device) decide which of them does the work.
 int launch_part_reads(tsxc_table* t, uint32_t c, const uint64_t* d_packed, const uint32_t* d_ends, uint64_t n_words, uint64_t n_bases,
                       uint64_t seg0, uint64_t* const* d_peers, cudaStream_t s) {
     const RadixGeom& g = t->rg;
     const int grid_p = t->part_grid > 0 ? t->part_grid : t->sms * 2;
     unsigned long long* err = t->d_ctr + CTR_ERRORS;
+    const uint32_t pct = t->sparse_pct;
+#define PART_(KW_, PAGED_, SPARSE_, PEERS_, PB_, PL_)                                                                                   \
+    k_part_reads<KW_, PAGED_, SPARSE_><<<grid_p, kRadixThreads, part_smem_bytes<KW_>(PAGED_, SPARSE_), s>>>(                           \
+        t->tv, g, t->pg, t->d_ctl, c, d_packed, d_ends, n_words, n_bases, seg0, t->d_A, PEERS_, PB_, PL_, err, pct)
 #define M(KW_)                                                                                                                          \
-    if (t->pg.paged && !d_peers)                                                                                                         \
-        k_part_reads<KW_, true><<<grid_p, kRadixThreads, part_smem_bytes<KW_>(true), s>>>(t->tv, g, t->pg, t->d_ctl, c, d_packed, d_ends, n_words, n_bases, seg0, t->d_A, nullptr, t->d_page_bin, t->d_page_len, err); \
-    else                                                                                                                                 \
-        k_part_reads<KW_, false><<<grid_p, kRadixThreads, part_smem_bytes<KW_>(false), s>>>(t->tv, g, t->pg, t->d_ctl, c, d_packed, d_ends, n_words, n_bases, seg0, t->d_A, d_peers, nullptr, nullptr, err)
+    if (t->pg.paged && !d_peers) {                                                                                                       \
+        PART_(KW_, true, false, nullptr, t->d_page_bin, t->d_page_len);                                                                  \
+        PART_(KW_, true, true, nullptr, t->d_page_bin, t->d_page_len);                                                                   \
+    } else {                                                                                                                             \
+        PART_(KW_, false, false, d_peers, nullptr, nullptr);                                                                             \
+        PART_(KW_, false, true, d_peers, nullptr, nullptr);                                                                              \
+    }
     TSX_DISPATCH_KW(t->L, M);
 #undef M
+#undef PART_
     return TSXC_OK;
 }
 
@@ -507,7 +520,7 @@ int launch_count_reads_radix(tsxc_table* t, const uint64_t* d_packed, const uint
                 }
                 if ((rc = launch_part_reads(t, c, d_packed, d_ends, n_words, n_bases, seg0, nullptr, s))) return rc;
                 if (paged) k_chunk_end_paged<<<1, 1024, 0, s>>>(t->d_ctl);
-                pt.end(paged ? 3 : 2);
+                pt.end(paged ? 4 : 3);
             }
             if ((rc = launch_sort_insert(t, s))) return rc;
         }
@@ -658,6 +671,7 @@ int create_impl(uint32_t k, uint32_t l, uint32_t s, int device, uint32_t flags, 
     h->rg = make_radix_geom(L, h->region_log2, seg_log2);
     h->rg_lookup = make_lookup_geom(L, std::min<uint32_t>(h->region_log2, 24), seg_log2);
     h->radix_on = (L.LBl + 5 >= min_table_log2) && (h->rg.d1 > L.shard_bits);
+    h->sparse_pct = (uint32_t)std::min<uint64_t>(env_u64("TSXC_SPARSE_PCT", h->sparse_pct), 101);   // 0: never, 101: always
     { const int arc = opt_in_shared_memory(h); if (arc != TSXC_OK) return bail(arc); }
     h->tv = make_view(L, h->d_words, h->d_ctr);
     CU(cudaMemsetAsync(h->d_ctl, 0, sizeof(RadixCtl), h->stream));
@@ -1232,7 +1246,7 @@ int tsxc_route_send(tsxc_table* t, uint32_t round, const uint32_t* d_hist_all) {
     k_route_offsets<<<1, 1024, 0, s>>>(t->d_ctl, round, d_hist_all, 1u << t->L.shard_bits, t->L.shard_rank, rg.nb1, rg.nbl, t->cap_A,
                                        slice_keys_of(t->L), t->d_ctr + CTR_ERRORS);
     { const int prc = launch_part_reads(t, round, t->route_packed, t->d_ends, t->route_n_words, t->route_n_bases, 0, t->d_peers, s); if (prc) return prc; }
-    pt.end(2);
+    pt.end(3);
     CU(cudaGetLastError());
     return TSXC_OK;
 }
@@ -1473,6 +1487,45 @@ int tsxc_debug_canonical(uint32_t k, const uint64_t* key, uint64_t* out) {
     if (KW == 1) { Key<1> x{{key[0]}}; auto c = canonical_key<1>(x, hp); out[0] = c.w[0]; }
     else if (KW == 2) { Key<2> x{{key[0], key[1]}}; auto c = canonical_key<2>(x, hp); out[0] = c.w[0]; out[1] = c.w[1]; }
     else { Key<4> x{{key[0], key[1], key[2], key[3]}}; auto c = canonical_key<4>(x, hp); for (int j = 0; j < 4; ++j) out[j] = c.w[j]; }
+    return TSXC_OK;
+}
+
+// One block round of S1's sparse walk (SparseStage in tsx_radix.cuh) on the host, through the same helper functions the
+// kernel calls: the k-mers that start in stream words [round, round + 512) and before word w_end, in the order the
+// kernel's threads would take them.  keys_out: room for 512 * 32 k-mers.
+int tsxc_debug_sparse_round(uint32_t k, const uint64_t* packed, const uint32_t* ends, uint64_t n_words, uint64_t n_bases,
+                            uint64_t round, uint64_t w_end, uint64_t* keys_out, uint32_t* n_out) {
+    const uint32_t KW = tsxc_key_words(k);
+    if (!KW || !packed || !ends || !keys_out || !n_out) return TSXC_E_INVALID;
+    const HashParams hp = make_hash_params(k);
+    const uint32_t NE = KW == 1 ? 1 : (KW == 2 ? 2 : 4);
+    std::vector<uint32_t> stream(2 * (kRadixThreads + 4 + 1)), vb(kRadixThreads), pre(kRadixThreads);
+    auto word = [&](uint64_t w) { return w < n_words ? packed[w] : 0ULL; };
+    auto eword = [&](uint64_t w) { return w < n_words ? ends[w] : 0u; };
+    for (uint32_t t = 0; t < (uint32_t)kRadixThreads + KW + 1; ++t) {
+        const uint64_t v = word(round + t);
+        stream[2 * t] = (uint32_t)v; stream[2 * t + 1] = (uint32_t)(v >> 32);
+    }
+    uint32_t total = 0;
+    for (uint32_t t = 0; t < (uint32_t)kRadixThreads; ++t) {
+        const uint64_t wi = round + t;
+        uint32_t dist_after = 0xffffffffu;                 // first_end_after over the NE following words
+        for (uint32_t j = NE; j >= 1; --j) { const uint32_t e = eword(wi + j); if (e) dist_after = 32u * (j - 1) + (uint32_t)__builtin_ctz(e); }
+        const uint64_t g0 = wi << 5;
+        int omax = -1;
+        if (wi < w_end && g0 + k <= n_bases) omax = n_bases - g0 - k < 31 ? (int)(n_bases - g0 - k) : 31;
+        vb[t] = valid_starts(eword(wi), dist_after, k, omax);
+        pre[t] = total;
+        total += popc32(vb[t]);
+    }
+    for (uint32_t i = 0; i < total; ++i) {
+        const uint32_t w = locate_word(pre.data(), kRadixThreads, i);
+        const uint32_t o = select_bit(vb[w], i - pre[w]);
+        if (KW == 1) { auto key = kmer_from_stream32<1>(stream.data(), w, o, hp); keys_out[i] = key.w[0]; }
+        else if (KW == 2) { auto key = kmer_from_stream32<2>(stream.data(), w, o, hp); keys_out[2 * (uint64_t)i] = key.w[0]; keys_out[2 * (uint64_t)i + 1] = key.w[1]; }
+        else { auto key = kmer_from_stream32<4>(stream.data(), w, o, hp); for (int j = 0; j < 4; ++j) keys_out[4 * (uint64_t)i + j] = key.w[j]; }
+    }
+    *n_out = total;
     return TSXC_OK;
 }
 

@@ -160,6 +160,93 @@ struct KmerLane {
     }
 };
 
+// ---- sparse streams: enumerate only the positions that start a k-mer ---------------------------------------------
+// With reads of 150 bases only 24 of 150 positions start a 127-mer.  The dense walk above hashes and ranks every
+// position and hands tiles that are 16 % full to tile_partition, whose per-tile cost does not depend on the fill
+// (config 4: 204 ms of S1 for 1.6e9 k-mers).  The sparse walk first turns the read-end bitmap of a block round
+// (512 stream words) into one validity mask per word, scans the popcounts, and then every thread takes the i-th valid
+// position of the round: word by binary search over the scanned counts, offset = i-th set bit of the word's mask.
+// Tiles are full, and only real k-mers are extracted and hashed.  The helpers are host-callable so that
+// tsxc_debug_sparse_round runs the same arithmetic on the CPU (tests/test_host.py).
+TSX_HD uint32_t popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+TSX_HD uint32_t funnel_r32(uint32_t lo, uint32_t hi, uint32_t s) {   // bits [s, s+32) of hi:lo, 0 <= s < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (s & 31u));
+#endif
+}
+
+// Mask of the offsets o of one stream word at which a k-mer starts.  ends_cur: the word's read-end bits; dist_after:
+// distance from bit 0 of the NEXT word to the first read end at or after it (0xffffffff: none within reach);
+// omax: largest offset that still leaves k bases in the stream (-1: none).  The recurrence is KmerLane::kmer_at's.
+TSX_HD uint32_t valid_starts(uint32_t ends_cur, uint32_t dist_after, uint32_t k, int omax) {
+    uint32_t dist = dist_after, vbits = 0;
+#pragma unroll 8
+    for (int o = 31; o >= 0; --o) {
+        dist = ((ends_cur >> o) & 1u) ? 0u : (dist == 0xffffffffu ? dist : dist + 1u);
+        if (dist >= k - 1 && o <= omax) vbits |= 1u << o;
+    }
+    return vbits;
+}
+
+// Position of the r-th (0-based) set bit of m; m has more than r set bits.
+TSX_HD uint32_t select_bit(uint32_t m, uint32_t r) {
+    uint32_t pos = 0, c;
+    c = popc32(m & 0xffffu); if (r >= c) { pos += 16; r -= c; m >>= 16; }
+    c = popc32(m & 0xffu);   if (r >= c) { pos += 8;  r -= c; m >>= 8; }
+    c = popc32(m & 0xfu);    if (r >= c) { pos += 4;  r -= c; m >>= 4; }
+    c = popc32(m & 0x3u);    if (r >= c) { pos += 2;  r -= c; m >>= 2; }
+    c = m & 1u;              if (r >= c) { pos += 1; }
+    return pos;
+}
+
+// pre[0..n) = exclusive scan of the words' popcounts (n a power of two), i < total: the word that holds the i-th valid
+// position = the largest w with pre[w] <= i (words without valid positions share their successor's prefix and lose).
+TSX_HD uint32_t locate_word(const uint32_t* pre, uint32_t n, uint32_t i) {
+    uint32_t w = 0;
+    for (uint32_t step = n >> 1; step; step >>= 1)
+        if (pre[w + step] <= i) w += step;
+    return w;
+}
+
+// The k-mer that starts at offset o of word w of a staged piece of the stream (s32: its 32-bit halves, little end first;
+// words w .. w+KW are read).  Same funnel shifts as KmerLane::kmer_at with the half chosen at run time.
+template <int KW>
+TSX_HD Key<KW> kmer_from_stream32(const uint32_t* s32, uint32_t w, uint32_t o, const HashParams& hp) {
+    const uint32_t* a = s32 + 2 * w + (o >> 4);
+    const uint32_t sb = (2u * o) & 31u;
+    Key<KW> key;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+        const uint32_t lo = funnel_r32(a[2 * j], a[2 * j + 1], sb);
+        const uint32_t hi = funnel_r32(a[2 * j + 1], a[2 * j + 2], sb);
+        key.w[j] = (((uint64_t)hi << 32) | lo) & word_mask<KW>(j, hp);
+    }
+    return key;
+}
+
+// One block round of the sparse walk in shared memory
+template <int KW>
+struct SparseStage {
+    alignas(16) uint32_t stream[2 * (kRadixThreads + KW + 1)];   // words [round, round + 512 + KW] of the stream
+    uint32_t vb[kRadixThreads];                                  // valid_starts of word round + t
+    uint32_t pre[kRadixThreads];                                 // exclusive scan of their popcounts
+};
+
+// A chunk takes the sparse walk when fewer than pct % of its base positions start a k-mer (both numbers come from the
+// planner: k-mers of the chunk, segments of the chunk).  Uniform over the whole launch.
+__device__ __forceinline__ bool chunk_is_sparse(const RadixCtl* __restrict__ ctl, uint32_t c, const RadixGeom& rg, uint32_t pct) {
+    const uint64_t positions = (ctl->chunk[c].seg_end - ctl->chunk[c].seg_begin) << (rg.seg_log2 + 5);
+    return ctl->chunk[c].n_keys * 100ULL < positions * (uint64_t)pct;
+}
+
 // ---- warp-private ranking -------------------------------------------------------------------------------------
 // Lanes holding the same digit form a group; the group's first lane bumps the warp's own counter by the group
 // size, every lane's rank is the old counter value + its position inside the group.  No atomics: the counter row
@@ -735,21 +822,27 @@ __global__ void __launch_bounds__(1024) k_route_offsets(RadixCtl* __restrict__ c
 // Exact mode (PAGED = false): run of bin d goes to position cursor1[d]++ of dst_of_owner[owner of d] (multi-GPU: the
 // owner's receive buffer, peer-mapped over NVLink for the other ranks: the routing kernel IS the exchange) or of A.
 // Paged mode: see PageGeom.
-// Dynamic shared memory: TileSmem<KW, kNB1, PAGED> + 256 owner pointers.
-template <int KW, bool PAGED>
+// SPARSE: the walk over valid positions only (see SparseStage); both flavours are launched for every chunk and the one
+// that does not match the chunk's density returns at once.
+// Dynamic shared memory: TileSmem<KW, kNB1, PAGED> + 256 owner pointers (+ PageState) (+ SparseStage<KW>).
+template <int KW, bool PAGED, bool SPARSE>
 __global__ void __launch_bounds__(kRadixThreads, RadixCfg<KW>::MINB)
 k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, const __grid_constant__ PageGeom pg,
              RadixCtl* __restrict__ ctl, uint32_t c, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ends,
              uint64_t n_words, uint64_t n_bases, uint64_t seg0, uint64_t* __restrict__ A, uint64_t* const* __restrict__ dst_of_owner,
-             uint16_t* __restrict__ page_bin, uint16_t* __restrict__ page_len, unsigned long long* __restrict__ err_ctr) {
+             uint16_t* __restrict__ page_bin, uint16_t* __restrict__ page_len, unsigned long long* __restrict__ err_ctr,
+             uint32_t sparse_pct) {
     constexpr int OPT = RadixCfg<KW>::OPT;
     using Smem = TileSmem<KW, kNB1, PAGED>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     constexpr size_t kSmemA = (sizeof(Smem) + 15) & ~(size_t)15;
+    constexpr size_t kSmemSp = kSmemA + 256 * sizeof(uint64_t*) + (PAGED ? sizeof(PageState) : 0);
+    static_assert(kSmemSp % 16 == 0, "SparseStage is 16-byte aligned");
     uint64_t** owner_base = reinterpret_cast<uint64_t**>(smem_raw + kSmemA);
     PagePool pool{reinterpret_cast<PageState*>(smem_raw + kSmemA + 256 * sizeof(uint64_t*)), ctl, page_bin, page_len, err_ctr, pg.page_log2, pg.n_pages, 0ULL};
     if (!ctl->chunk_active) return;
+    if (chunk_is_sparse(ctl, c, rg, sparse_pct) != SPARSE) return;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     tile_smem_init<KW, kNB1, PAGED>(sm);
     if (threadIdx.x < 256) owner_base[threadIdx.x] = (dst_of_owner && threadIdx.x < (rg.nb1 >> rg.owner_shift)) ? dst_of_owner[threadIdx.x] : A;
@@ -772,28 +865,71 @@ k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ Radix
         const uint64_t w0 = (seg0 + seg) << rg.seg_log2;
         const uint64_t w1 = w0 + seg_words < n_words ? w0 + seg_words : n_words;
         for (uint64_t round = w0; round < w1; round += kRadixWarps * 32) {
-            KmerLane<KW> kl;
-            kl.load(packed, ends, round + warp * 32, n_words, w1, n_bases, lane, tv.L.k);
-#pragma unroll 1
-            for (int o0 = 31; o0 >= 0; o0 -= OPT) {
-                Key<KW> Hs[OPT];
-                uint32_t vmask = 0;
-                if (o0 >= 16) {
-#pragma unroll
-                    for (int j = 0; j < OPT; ++j) {
-                        Key<KW> key;
-                        if (kl.template kmer_at<true>(o0 - j, tv.L.k, tv.hp, key)) vmask |= 1u << j;
-                        Hs[j] = hash_key<KW>(key, tv.hp);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < OPT; ++j) {
-                        Key<KW> key;
-                        if (kl.template kmer_at<false>(o0 - j, tv.L.k, tv.hp, key)) vmask |= 1u << j;
-                        Hs[j] = hash_key<KW>(key, tv.hp);
-                    }
+            if constexpr (SPARSE) {
+                constexpr int NE = KmerLane<KW>::NE;
+                constexpr uint32_t TILE = RadixCfg<KW>::TILE;
+                SparseStage<KW>& sp = *reinterpret_cast<SparseStage<KW>*>(smem_raw + kSmemSp);
+                uint64_t* stream64 = reinterpret_cast<uint64_t*>(sp.stream);
+                const uint32_t k = tv.L.k;
+                const uint64_t wi = round + threadIdx.x;
+                stream64[threadIdx.x] = wi < n_words ? __ldg(packed + wi) : 0ULL;
+                if (threadIdx.x <= (unsigned)KW) {
+                    const uint64_t u = round + kRadixThreads + threadIdx.x;
+                    stream64[kRadixThreads + threadIdx.x] = u < n_words ? __ldg(packed + u) : 0ULL;
                 }
-                tile_partition<KW, kNB1, PAGED>(sm, Hs, vmask, rg.d1, digit, reserve, place, dst);
+                uint32_t ewin[NE + 1];
+                load_window<NE, uint32_t>(ends, round + warp * 32, n_words, lane, ewin);
+                const uint64_t g0 = wi << 5;
+                int omax = -1;
+                if (wi < w1 && g0 + k <= n_bases) omax = n_bases - g0 - k < 31 ? (int)(n_bases - g0 - k) : 31;
+                const uint32_t vbits = valid_starts(ewin[0], first_end_after<NE>(ewin), k, omax);
+                uint32_t n_valid = 0;
+                const uint32_t before = block_exscan(popc32(vbits), sm.scratch, &n_valid);
+                sp.vb[threadIdx.x] = vbits;
+                sp.pre[threadIdx.x] = before;
+                __syncthreads();
+                for (uint32_t t0 = 0; t0 < n_valid; t0 += TILE) {
+                    Key<KW> Hs[OPT];
+                    uint32_t vmask = 0;
+#pragma unroll
+                    for (int j = 0; j < OPT; ++j) {
+                        const uint32_t i = t0 + (uint32_t)j * kRadixThreads + threadIdx.x;
+#pragma unroll
+                        for (int w = 0; w < KW; ++w) Hs[j].w[w] = 0ULL;
+                        if (i < n_valid) {
+                            const uint32_t w = locate_word(sp.pre, kRadixThreads, i);
+                            const uint32_t o = select_bit(sp.vb[w], i - sp.pre[w]);
+                            Hs[j] = hash_key<KW>(kmer_from_stream32<KW>(sp.stream, w, o, tv.hp), tv.hp);
+                            vmask |= 1u << j;
+                        }
+                    }
+                    tile_partition<KW, kNB1, PAGED>(sm, Hs, vmask, rg.d1, digit, reserve, place, dst);
+                }
+                __syncthreads();      // the stage is rewritten by the next round
+            } else {
+                KmerLane<KW> kl;
+                kl.load(packed, ends, round + warp * 32, n_words, w1, n_bases, lane, tv.L.k);
+#pragma unroll 1
+                for (int o0 = 31; o0 >= 0; o0 -= OPT) {
+                    Key<KW> Hs[OPT];
+                    uint32_t vmask = 0;
+                    if (o0 >= 16) {
+#pragma unroll
+                        for (int j = 0; j < OPT; ++j) {
+                            Key<KW> key;
+                            if (kl.template kmer_at<true>(o0 - j, tv.L.k, tv.hp, key)) vmask |= 1u << j;
+                            Hs[j] = hash_key<KW>(key, tv.hp);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < OPT; ++j) {
+                            Key<KW> key;
+                            if (kl.template kmer_at<false>(o0 - j, tv.L.k, tv.hp, key)) vmask |= 1u << j;
+                            Hs[j] = hash_key<KW>(key, tv.hp);
+                        }
+                    }
+                    tile_partition<KW, kNB1, PAGED>(sm, Hs, vmask, rg.d1, digit, reserve, place, dst);
+                }
             }
         }
     }
