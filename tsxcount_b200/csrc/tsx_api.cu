@@ -71,8 +71,8 @@ struct tsxc_table {
     int part_grid = 0;                                         // thread blocks of S1 the page pool was planned for
     bool radix_on = false;                                     // tables this large take the pipeline by default
     uint32_t region_log2 = 27;                                 // target size of a table region (bytes, log2)
-    uint32_t sparse_pct = 62;                                  // S1 walks valid positions only when fewer than this % of the positions start a k-mer
-                                                               // (measured: S1 9 % faster at 59 % (config 3), 23 % slower at 80 % (config 2))
+    uint32_t sparse_pct = 70;                                  // S1 walks valid positions only when fewer than this % of the positions start a k-mer
+                                                               // (measured: S1 18 % faster at 59 % (config 3), 3 % slower at 80 % (config 2))
     uint16_t* d_page_bin = nullptr; size_t cap_page_bin = 0;   // paged mode: bin of every pool page
     uint16_t* d_page_len = nullptr; size_t cap_page_len = 0;   //             keys in it
     ulonglong2* d_slices = nullptr; size_t cap_slices = 0;     // phase B work items: (first key, keys)
@@ -1518,12 +1518,17 @@ int tsxc_debug_sparse_round(uint32_t k, const uint64_t* packed, const uint32_t* 
         pre[t] = total;
         total += popc32(vb[t]);
     }
-    for (uint32_t i = 0; i < total; ++i) {
-        const uint32_t w = locate_word(pre.data(), kRadixThreads, i);
-        const uint32_t o = select_bit(vb[w], i - pre[w]);
+    // tiles of kRadixThreads * OPT positions, thread t of a tile takes OPT consecutive ones (as k_part_reads does)
+    const uint32_t OPT = 8 / KW;
+    for (uint32_t i0 = 0; i0 < total; i0 += OPT) {
+      SparseCursor cur = sparse_seek(pre.data(), vb.data(), kRadixThreads, i0);
+      for (uint32_t i = i0; i < i0 + OPT && i < total; ++i) {
+        const uint32_t o = sparse_next(cur, vb.data());
+        const uint32_t w = cur.w;
         if (KW == 1) { auto key = kmer_from_stream32<1>(stream.data(), w, o, hp); keys_out[i] = key.w[0]; }
         else if (KW == 2) { auto key = kmer_from_stream32<2>(stream.data(), w, o, hp); keys_out[2 * (uint64_t)i] = key.w[0]; keys_out[2 * (uint64_t)i + 1] = key.w[1]; }
         else { auto key = kmer_from_stream32<4>(stream.data(), w, o, hp); for (int j = 0; j < 4; ++j) keys_out[4 * (uint64_t)i + j] = key.w[j]; }
+      }
     }
     *n_out = total;
     return TSXC_OK;

@@ -164,8 +164,9 @@ struct KmerLane {
 // With reads of 150 bases only 24 of 150 positions start a 127-mer.  The dense walk above hashes and ranks every
 // position and hands tiles that are 16 % full to tile_partition, whose per-tile cost does not depend on the fill
 // (config 4: 204 ms of S1 for 1.6e9 k-mers).  The sparse walk first turns the read-end bitmap of a block round
-// (512 stream words) into one validity mask per word, scans the popcounts, and then every thread takes the i-th valid
-// position of the round: word by binary search over the scanned counts, offset = i-th set bit of the word's mask.
+// (512 stream words) into one validity mask per word, scans the popcounts, and then every thread takes OPT consecutive
+// valid positions of the round: the first by binary search over the scanned counts + select of the i-th set bit of the
+// word's mask, the following ones by stepping through the masks.
 // Tiles are full, and only real k-mers are extracted and hashed.  The helpers are host-callable so that
 // tsxc_debug_sparse_round runs the same arithmetic on the CPU (tests/test_host.py).
 TSX_HD uint32_t popc32(uint32_t x) {
@@ -214,6 +215,31 @@ TSX_HD uint32_t locate_word(const uint32_t* pre, uint32_t n, uint32_t i) {
     for (uint32_t step = n >> 1; step; step >>= 1)
         if (pre[w + step] <= i) w += step;
     return w;
+}
+
+// A thread takes OPT consecutive valid positions: it seeks the first one (binary search + select) and steps to the
+// following ones with one find-first-set each.
+struct SparseCursor { uint32_t w, m; };      // word, and the word's valid starts at and above the cursor
+TSX_HD uint32_t ctz32(uint32_t x) {          // x != 0
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)(__ffs((int)x) - 1);
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
+TSX_HD SparseCursor sparse_seek(const uint32_t* pre, const uint32_t* vb, uint32_t n, uint32_t i) {
+    SparseCursor c;
+    c.w = locate_word(pre, n, i);
+    c.m = vb[c.w] & (0xffffffffu << select_bit(vb[c.w], i - pre[c.w]));
+    return c;
+}
+// offset of the valid position under the cursor (its word is c.w afterwards); the cursor moves on.  The caller knows
+// that a valid position is left at or after the cursor.
+TSX_HD uint32_t sparse_next(SparseCursor& c, const uint32_t* vb) {
+    while (c.m == 0) c.m = vb[++c.w];
+    const uint32_t o = ctz32(c.m);
+    c.m &= c.m - 1;
+    return o;
 }
 
 // The k-mer that starts at offset o of word w of a staged piece of the stream (s32: its 32-bit halves, little end first;
@@ -826,7 +852,7 @@ __global__ void __launch_bounds__(1024) k_route_offsets(RadixCtl* __restrict__ c
 // that does not match the chunk's density returns at once.
 // Dynamic shared memory: TileSmem<KW, kNB1, PAGED> + 256 owner pointers (+ PageState) (+ SparseStage<KW>).
 template <int KW, bool PAGED, bool SPARSE>
-__global__ void __launch_bounds__(kRadixThreads, RadixCfg<KW>::MINB)
+__global__ void __launch_bounds__(kRadixThreads, SPARSE ? 2 : RadixCfg<KW>::MINB)
 k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ RadixGeom rg, const __grid_constant__ PageGeom pg,
              RadixCtl* __restrict__ ctl, uint32_t c, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ends,
              uint64_t n_words, uint64_t n_bases, uint64_t seg0, uint64_t* __restrict__ A, uint64_t* const* __restrict__ dst_of_owner,
@@ -891,15 +917,16 @@ k_part_reads(const __grid_constant__ TableView tv, const __grid_constant__ Radix
                 for (uint32_t t0 = 0; t0 < n_valid; t0 += TILE) {
                     Key<KW> Hs[OPT];
                     uint32_t vmask = 0;
+                    const uint32_t i0 = t0 + threadIdx.x * OPT;          // this thread's valid positions [i0, i0 + OPT)
+                    SparseCursor cur{0u, 0u};
+                    if (i0 < n_valid) cur = sparse_seek(sp.pre, sp.vb, kRadixThreads, i0);
 #pragma unroll
                     for (int j = 0; j < OPT; ++j) {
-                        const uint32_t i = t0 + (uint32_t)j * kRadixThreads + threadIdx.x;
 #pragma unroll
                         for (int w = 0; w < KW; ++w) Hs[j].w[w] = 0ULL;
-                        if (i < n_valid) {
-                            const uint32_t w = locate_word(sp.pre, kRadixThreads, i);
-                            const uint32_t o = select_bit(sp.vb[w], i - sp.pre[w]);
-                            Hs[j] = hash_key<KW>(kmer_from_stream32<KW>(sp.stream, w, o, tv.hp), tv.hp);
+                        if (i0 + j < n_valid) {
+                            const uint32_t o = sparse_next(cur, sp.vb);
+                            Hs[j] = hash_key<KW>(kmer_from_stream32<KW>(sp.stream, cur.w, o, tv.hp), tv.hp);
                             vmask |= 1u << j;
                         }
                     }
