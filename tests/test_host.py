@@ -293,3 +293,39 @@ def test_sparse_walk_of_the_partition_pass_enumerates_exactly_the_kmers(k, read_
                                            out.ctypes.data, C.byref(n_out)) == 0
         starts = [int(offsets[r]) + i for r, s in enumerate(seqs) for i in range(len(s) - k + 1)]
         assert n_out.value == sum(1 for g in starts if g < 96)
+
+
+def test_sparse_walk_randomized_k_and_read_lengths():
+    """The same check as above over 40 random (k, read-length distribution) pairs, including streams that end in the
+    first word of a round and reads shorter than k only."""
+    lib = _lib.load()
+    rng = np.random.default_rng(20261019)
+    for trial in range(40):
+        k = int(rng.integers(1, 129))
+        lo = int(rng.integers(0, k + 10))
+        hi = lo + int(rng.integers(1, 3 * k + 40))
+        n_reads = int(rng.integers(1, 400))
+        seqs = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(n))) for n in rng.integers(lo, hi, size=n_reads)]
+        seqs = [s for s in seqs if len(s)]
+        if not seqs:
+            continue
+        ascii_, offsets = sequtils.concat_reads(seqs)
+        packed, seg, nbad = sequtils.pack_reads(ascii_, offsets)
+        n_bases = int(seg[-1])
+        n_words = (n_bases + 31) // 32
+        ends = np.zeros(n_words + 1, dtype=np.uint32)
+        for e in seg[1:].tolist():
+            ends[(e - 1) >> 5] |= np.uint32(1 << ((e - 1) & 31))
+        kw = sequtils.key_words(k)
+        out = np.zeros(16384 * kw, dtype=np.uint64)
+        n_out = C.c_uint32(0)
+        got = []
+        for rnd in range(0, n_words, 512):
+            assert lib.tsxc_debug_sparse_round(k, packed.ctypes.data, ends.ctypes.data, n_words, n_bases, rnd, n_words,
+                                               out.ctypes.data, C.byref(n_out)) == 0
+            got.append(out[: n_out.value * kw].reshape(-1, kw).copy())
+        got = np.concatenate(got)
+        want = [s[i:i + k].decode() for s in seqs for i in range(len(s) - k + 1)]
+        assert len(got) == len(want), (trial, k, lo, hi)
+        if want:
+            assert np.array_equal(got, sequtils.kmers_to_array(want, k)), (trial, k, lo, hi)
