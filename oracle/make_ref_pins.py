@@ -49,6 +49,21 @@ CASES = [
 ]
 
 
+# Pins of the restatement alone (word-boundary and in-between k; the GPU tests do not replay these, so no fixture is
+# committed: tests/test_oracle.py regenerates the FASTQ with the same generator call and compares the hashes).
+# Domain of the reference's --check: 2k - l + 2s <= 64 once an overflow entry exists, so k >= 48 stays flat (counts <= 15).
+ORACLE_ONLY_CASES = [
+    # (OMP at 8 threads lost one increment of a contended k-mer in one run: the reference's own race, recorded for information)
+    ("k28_genome", (3, 0x28, 400, 150, 3000, 328), 28, 22, 4, [("SERIAL", 1), ("OMP", 8, "info")]),
+    ("k32_genome_overflow", (3, 0x32, 400, 150, 3000, 328), 32, 22, 4, [("SERIAL", 1), ("OMP", 8)]),
+    ("k34_genome_overflow", (3, 0x34, 300, 150, 3000, 328), 34, 22, 4, [("OMP", 8)]),
+    ("k36_fakeseq", (1, 0x36, 200, 150, 0, 0), 36, 22, 4, [("SERIAL", 1)]),
+    ("k48_genome_flat", (3, 0x48, 150, 150, 5000, 200), 48, 20, 4, [("OMP", 8)]),
+    ("k64_genome_flat", (3, 0x64, 100, 150, 4000, 100), 64, 20, 4, [("OMP", 8)]),
+    ("k64_uniform", (0, 0x65, 120, 150, 0, 0), 64, 20, 4, [("SERIAL", 1)]),
+]
+
+
 def sha(path):
     h = hashlib.sha256()
     with open(path, "rb") as f:
@@ -86,10 +101,19 @@ def main():
         if not os.path.exists(need):
             sys.exit(f"missing {need}: run `make -C oracle all` in the build container first")
     os.makedirs(GOLD, exist_ok=True)
-    pins = {"made_by": "oracle/make_ref_pins.py", "reference_binary": "oracle/_ref/tsxCount (unmodified sources)",
-            "cases": []}
+    pins_path = os.path.join(GOLD, "ref_binary_pins.json")
+    oracle_only = "--oracle-only" in sys.argv[1:]     # add / refresh the fixture-less pins, keep the others as they are
+    if oracle_only:
+        pins = json.load(open(pins_path))
+        pins["oracle_only_cases"] = []
+    else:
+        pins = {"made_by": "oracle/make_ref_pins.py", "reference_binary": "oracle/_ref/tsxCount (unmodified sources)",
+                "cases": [], "oracle_only_cases": []}
+    todo = [(c, "oracle_only_cases") for c in ORACLE_ONLY_CASES]
+    if not oracle_only:
+        todo = [(c, "cases") for c in CASES] + todo
     with tempfile.TemporaryDirectory() as tmp:
-        for name, gen, k, l, s, runs in CASES:
+        for (name, gen, k, l, s, runs), dest in todo:
             fastq = os.path.join(tmp, name + ".fastq")
             if gen is None:
                 shutil.copy(REFDATA, fastq)
@@ -113,15 +137,20 @@ def main():
                 print(name, r)
                 case["runs"].append(r)
             case["pinned"] = all(r["pinned"] for r in case["runs"] if not r["informational"])
-            pins["cases"].append(case)
+            if dest == "oracle_only_cases":
+                lines = [ln.rstrip("\n").split("\t") for ln in open(count)]
+                case["max_count"] = max(int(c) for _, c in lines)
+            pins[dest].append(case)
+            if dest != "cases":
+                continue
             # fixtures: FASTQ + count dump, gzip'ed
             for src in (fastq, count):
                 with open(src, "rb") as fi, gzip.GzipFile(os.path.join(GOLD, os.path.basename(src) + ".gz"), "wb",
                                                           mtime=0) as fo:
                     shutil.copyfileobj(fi, fo)
-    with open(os.path.join(GOLD, "ref_binary_pins.json"), "w") as f:
+    with open(pins_path, "w") as f:
         json.dump(pins, f, indent=1)
-    bad = [c["name"] for c in pins["cases"] if not c["pinned"]]
+    bad = [c["name"] for c in pins["cases"] + pins["oracle_only_cases"] if not c["pinned"]]
     print("UNPINNED:", bad if bad else "none")
     return 1 if bad else 0
 

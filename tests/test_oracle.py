@@ -56,6 +56,33 @@ def test_reference_binary_pins_are_green_and_fixtures_unchanged(tmp_path):
         assert hashlib.sha256(open(out, "rb").read()).hexdigest() == case["count_sha256"]
 
 
+def test_fixtureless_reference_pins_at_word_boundary_k(tmp_path):
+    """oracle_only_cases of the same file: the unmodified reference binary checked the restatement's dump at k = 28, 32, 34,
+    36 (with overflow entries: counts > 15), 48 and 64 (flat).  No fixtures are committed for them; the FASTQ comes from
+    the same generator call and must have the recorded hash, and so must the dump the oracle writes today."""
+    import subprocess
+    pins = json.load(open(os.path.join(GOLD, "ref_binary_pins.json")))
+    cases = pins["oracle_only_cases"]
+    assert {c["k"] for c in cases} >= {28, 32, 34, 36, 48, 64}
+    assert any(c["max_count"] > 15 for c in cases if c["k"] in (28, 32, 34, 36))      # overflow entries were exercised
+    tool = os.path.join(os.path.dirname(GOLD), "..", "oracle", "_build", "kmer_oracle")
+    for case in cases:
+        assert case["pinned"], case["name"]
+        for r in case["runs"]:
+            if r.get("informational"):
+                continue
+            assert r["total_errors"] == 0 and r["xor_kmer_count"] == 0
+            assert r["reference_kmer_count"] == case["oracle_distinct"] == r["tsxcount_kmer_count"]
+        fastq = tmp_path / (case["name"] + ".fastq")
+        subprocess.run([tool, "gen"] + [str(x) for x in case["gen"]] + [str(fastq)], check=True)
+        assert hashlib.sha256(open(fastq, "rb").read()).hexdigest() == case["fastq_sha256"]
+        out = tmp_path / (case["name"] + ".count")
+        orc.write_dump_fastq(fastq, case["k"], out)
+        assert hashlib.sha256(open(out, "rb").read()).hexdigest() == case["count_sha256"]
+        oc = orc.count_fastq(fastq, case["k"])
+        assert (oc.n_distinct, oc.n_total, int(oc.counts.max())) == (case["oracle_distinct"], case["oracle_total"], case["max_count"])
+
+
 def test_readme_example():
     # README.md:13-24 of the reference
     oc = orc.count_seqs([b"ATCGAGTCAGTA"], 5)
